@@ -1,0 +1,1572 @@
+// Host side of libdjets_b200: contexts (one rank = one GPU = one former Distributed.jl worker),
+// device-resident DBArrays, the distributed block operator with its tile schedules, the
+// cross-rank exchange and the C ABI of include/djets.h.  See DESIGN.md for the layout.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <exception>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/djets.h"
+#include "djets_kernels.h"
+#include "djets_nccl.h"
+
+using namespace djets;
+
+// ---- errors ---------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Err {
+  int code;
+  std::string msg;
+};
+
+[[noreturn]] void fail(int code, const std::string& msg) { throw Err{code, msg}; }
+
+#define CK(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      fail(DJETS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorName(e__) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+#define NCK(api, expr)                                                                    \
+  do {                                                                                    \
+    ncclResult_t r__ = (expr);                                                            \
+    if (r__ != ncclSuccess) fail(DJETS_ERR_NCCL, std::string(#expr) + ": " + (api)->GetErrorString(r__)); \
+  } while (0)
+
+#define REQUIRE(cond, code, msg) \
+  do {                           \
+    if (!(cond)) fail(code, msg); \
+  } while (0)
+
+template <class F>
+int32_t guard(F&& f) {
+  try {
+    f();
+    return DJETS_OK;
+  } catch (const Err& e) {
+    g_last_error = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = std::string("internal: ") + e.what();
+    return DJETS_ERR_INVALID;
+  } catch (...) {
+    g_last_error = "internal: unknown exception";
+    return DJETS_ERR_INVALID;
+  }
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+constexpr int kMaxParts = 1024;
+
+}  // namespace
+
+// ---- context --------------------------------------------------------------------------------------
+struct KernelEvent {
+  int kind;
+  cudaEvent_t a, b;
+};
+
+struct RankCtx {
+  int rank = -1, device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev = nullptr;  // scratch event for cross-stream ordering
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  double* d_partials = nullptr;  // reduce stage-1 partials
+  double* d_result = nullptr;    // 2*kMaxParts doubles: per-part results, then the all-reduce buffer
+  double* h_result = nullptr;    // pinned mirror
+  ncclComm_t comm = nullptr;
+  int64_t launches[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
+  double ms[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
+  std::vector<KernelEvent> pending;
+  std::vector<cudaEvent_t> pool;
+};
+
+struct djets_ctx_s {
+  int world = 0;
+  std::vector<RankCtx> ranks;
+  std::vector<int> local_of_rank;
+  bool has_nccl = false;
+  bool timing = false;
+  int64_t fwd_tx = 32, fwd_tc = 512, adj_ru = 4, adj_tc = 32, ld_policy = 0;
+  std::mutex mu;
+
+  RankCtx* local(int rank) {
+    if (rank < 0 || rank >= world) return nullptr;
+    const int l = local_of_rank[rank];
+    return l < 0 ? nullptr : &ranks[l];
+  }
+};
+
+namespace {
+
+void use(RankCtx& rc) { CK(cudaSetDevice(rc.device)); }
+
+cudaEvent_t pool_event(RankCtx& rc) {
+  if (!rc.pool.empty()) {
+    cudaEvent_t e = rc.pool.back();
+    rc.pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  return e;
+}
+
+void drain_events(RankCtx& rc) {
+  if (rc.pending.empty()) return;
+  use(rc);
+  CK(cudaStreamSynchronize(rc.stream));
+  for (auto& k : rc.pending) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, k.a, k.b));
+    rc.ms[k.kind] += ms;
+    rc.pool.push_back(k.a);
+    rc.pool.push_back(k.b);
+  }
+  rc.pending.clear();
+}
+
+template <class F>
+void launch_counted(djets_ctx ctx, RankCtx& rc, int kind, F&& f) {
+  rc.launches[kind] += 1;
+  if (ctx->timing) {
+    if (rc.pending.size() > 200000) drain_events(rc);
+    KernelEvent k{kind, pool_event(rc), pool_event(rc)};
+    CK(cudaEventRecord(k.a, rc.stream));
+    CK(f());
+    CK(cudaEventRecord(k.b, rc.stream));
+    rc.pending.push_back(k);
+  } else {
+    CK(f());
+  }
+}
+
+// dst stream waits for everything enqueued so far on src stream
+void stream_after(RankCtx& src, RankCtx& dst) {
+  if (&src == &dst) return;
+  use(src);
+  CK(cudaEventRecord(src.ev, src.stream));
+  use(dst);
+  CK(cudaStreamWaitEvent(dst.stream, src.ev, 0));
+}
+
+struct Transfer {
+  int src_rank;
+  const char* src;
+  int dst_rank;
+  char* dst;
+  size_t bytes;
+};
+
+// One exchange phase: local->local pairs are device copies ordered with events; pairs with one end
+// in another process go through ncclSend/ncclRecv inside one group.
+void run_transfers(djets_ctx ctx, const std::vector<Transfer>& ts) {
+  if (ts.empty()) return;
+  const NcclApi* api = nullptr;
+  bool grouped = false;
+  for (const Transfer& t : ts) {
+    if (t.bytes == 0) continue;
+    RankCtx* s = ctx->local(t.src_rank);
+    RankCtx* d = ctx->local(t.dst_rank);
+    if (s && d) {
+      stream_after(*d, *s);  // destination buffer is free once d's earlier work is done
+      use(*s);
+      if (s->device == d->device)
+        CK(cudaMemcpyAsync(t.dst, t.src, t.bytes, cudaMemcpyDeviceToDevice, s->stream));
+      else
+        CK(cudaMemcpyPeerAsync(t.dst, d->device, t.src, s->device, t.bytes, s->stream));
+      stream_after(*s, *d);
+    } else if (s || d) {
+      REQUIRE(ctx->has_nccl, DJETS_ERR_NCCL,
+              "exchange with a rank of another process needs a context created with an NCCL unique id");
+      if (!api) {
+        const char* why = nullptr;
+        api = nccl_api(&why);
+        REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
+      }
+      if (!grouped) {
+        NCK(api, api->GroupStart());
+        grouped = true;
+      }
+      if (s) {
+        use(*s);
+        NCK(api, api->Send(t.src, t.bytes, ncclChar, t.dst_rank, s->comm, s->stream));
+      } else {
+        use(*d);
+        NCK(api, api->Recv(t.dst, t.bytes, ncclChar, t.src_rank, d->comm, d->stream));
+      }
+    }
+  }
+  if (grouped) NCK(api, api->GroupEnd());
+}
+
+}  // namespace
+
+// ---- DBArray --------------------------------------------------------------------------------------
+struct VecPart {
+  int rank = 0;
+  int64_t blk_first = 0, blk_count = 0, elem_first = 0, elem_count = 0;
+  char* d = nullptr;  // device storage on the owner (nullptr when the owner is another process)
+};
+
+struct djets_vec_s {
+  djets_ctx ctx = nullptr;
+  int dtype = 0;
+  std::vector<VecPart> parts;
+  std::vector<int64_t> block_len, block_off;  // block_off: global element offset, nblocks+1 entries
+  std::vector<int> block_part;
+  int64_t length = 0;
+};
+
+namespace {
+
+djets_vec make_vec(djets_ctx ctx, int dtype, int nparts, const int32_t* part_rank, const int64_t* part_nblocks,
+                   const int64_t* block_len) {
+  REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+  REQUIRE(dtype == DJETS_F32 || dtype == DJETS_F64, DJETS_ERR_INVALID, "dtype must be DJETS_F32 or DJETS_F64");
+  REQUIRE(nparts >= 1 && nparts <= kMaxParts, DJETS_ERR_INVALID, "nparts out of range");
+  auto v = std::make_unique<djets_vec_s>();
+  v->ctx = ctx;
+  v->dtype = dtype;
+  int64_t nblocks = 0;
+  for (int p = 0; p < nparts; ++p) {
+    REQUIRE(part_nblocks[p] >= 0, DJETS_ERR_INVALID, "negative block count");
+    REQUIRE(part_rank[p] >= 0 && part_rank[p] < ctx->world, DJETS_ERR_INVALID, "part rank outside the job");
+    nblocks += part_nblocks[p];
+  }
+  v->block_len.assign(block_len, block_len + nblocks);
+  v->block_off.resize(nblocks + 1);
+  v->block_part.resize(nblocks);
+  v->block_off[0] = 0;
+  for (int64_t b = 0; b < nblocks; ++b) {
+    REQUIRE(block_len[b] >= 0, DJETS_ERR_INVALID, "negative block length");
+    v->block_off[b + 1] = v->block_off[b] + block_len[b];
+  }
+  v->length = v->block_off[nblocks];
+  v->parts.resize(nparts);
+  int64_t b0 = 0;
+  const int es = elem_size(dtype);
+  for (int p = 0; p < nparts; ++p) {
+    VecPart& part = v->parts[p];
+    part.rank = part_rank[p];
+    part.blk_first = b0;
+    part.blk_count = part_nblocks[p];
+    part.elem_first = v->block_off[b0];
+    part.elem_count = v->block_off[b0 + part.blk_count] - part.elem_first;
+    for (int64_t b = b0; b < b0 + part.blk_count; ++b) v->block_part[b] = p;
+    b0 += part.blk_count;
+    if (RankCtx* rc = ctx->local(part.rank)) {
+      use(*rc);
+      const size_t bytes = (size_t)part.elem_count * es + 256;  // slack: 16-byte bulk copies may over-read
+      CK(cudaMalloc(&part.d, bytes));
+      CK(cudaMemsetAsync(part.d, 0, bytes, rc->stream));
+    }
+  }
+  return v.release();
+}
+
+void free_vec(djets_vec v) {
+  if (!v) return;
+  for (VecPart& p : v->parts) {
+    if (!p.d) continue;
+    if (RankCtx* rc = v->ctx->local(p.rank)) {
+      cudaSetDevice(rc->device);
+      cudaStreamSynchronize(rc->stream);
+      cudaFree(p.d);
+    }
+  }
+  delete v;
+}
+
+bool same_layout(djets_vec a, djets_vec b) {
+  if (a->ctx != b->ctx || a->parts.size() != b->parts.size() || a->block_len != b->block_len) return false;
+  for (size_t p = 0; p < a->parts.size(); ++p)
+    if (a->parts[p].rank != b->parts[p].rank || a->parts[p].blk_count != b->parts[p].blk_count) return false;
+  return true;
+}
+
+double round_to(int dtype, double v) { return dtype == DJETS_F32 ? (double)(float)v : v; }
+
+// Per-part partial reductions: one result per part in out_parts (all parts, after the cross-process
+// exchange when some parts live elsewhere).
+void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_parts) {
+  djets_ctx ctx = x->ctx;
+  const int np = (int)x->parts.size();
+  bool any_remote = false;
+  for (RankCtx& rc : ctx->ranks) {
+    use(rc);
+    CK(cudaMemsetAsync(rc.d_result, 0, sizeof(double) * np, rc.stream));
+  }
+  for (int p = 0; p < np; ++p) {
+    VecPart& part = x->parts[p];
+    RankCtx* rc = ctx->local(part.rank);
+    if (!rc) {
+      any_remote = true;
+      continue;
+    }
+    use(*rc);
+    const void* yp = y ? y->parts[p].d : nullptr;
+    launch_counted(ctx, *rc, DJETS_K_REDUCE, [&] {
+      return launch_reduce(x->dtype, kind, part.d, yp, part.elem_count, param, rc->d_partials, rc->d_result + p,
+                           rc->stream);
+    });
+  }
+  if (any_remote) {
+    REQUIRE(ctx->has_nccl, DJETS_ERR_NCCL, "vector has parts in other processes but the context has no NCCL");
+    const char* why = nullptr;
+    const NcclApi* api = nccl_api(&why);
+    REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
+    // every rank contributes its own parts and zeros elsewhere: the sum is exact
+    NCK(api, api->GroupStart());
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      NCK(api, api->AllReduce(rc.d_result, rc.d_result, np, ncclDouble, ncclSum, rc.comm, rc.stream));
+    }
+    NCK(api, api->GroupEnd());
+  }
+  for (RankCtx& rc : ctx->ranks) {
+    use(rc);
+    CK(cudaMemcpyAsync(rc.h_result, rc.d_result, sizeof(double) * np, cudaMemcpyDeviceToHost, rc.stream));
+  }
+  for (RankCtx& rc : ctx->ranks) {
+    use(rc);
+    CK(cudaStreamSynchronize(rc.stream));
+  }
+  for (int p = 0; p < np; ++p) {
+    RankCtx* rc = ctx->local(x->parts[p].rank);
+    out_parts[p] = rc ? rc->h_result[p] : ctx->ranks[0].h_result[p];
+  }
+}
+
+bool kind_is_min(int kind) { return kind == DJETS_RED_MIN || kind == DJETS_RED_ABSMIN; }
+bool kind_is_max(int kind) { return kind == DJETS_RED_MAX || kind == DJETS_RED_ABSMAX; }
+
+// master-side fold over the per-worker partials in the element type (src:222, 236, 249, 262, 276)
+double fold_parts(int dtype, int kind, const double* z, int np) {
+  if (kind_is_min(kind)) {
+    double m = INFINITY;
+    for (int p = 0; p < np; ++p) m = fmin(m, round_to(dtype, z[p]));
+    return m;
+  }
+  if (kind_is_max(kind)) {
+    double m = -INFINITY;
+    for (int p = 0; p < np; ++p) m = fmax(m, round_to(dtype, z[p]));
+    return m;
+  }
+  double s = 0.0;
+  for (int p = 0; p < np; ++p) s = round_to(dtype, s + round_to(dtype, z[p]));
+  return s;
+}
+
+}  // namespace
+
+// ---- distributed block operator -------------------------------------------------------------------
+struct Block {
+  int kind = DJETS_BLOCK_ZERO;
+  char* d = nullptr;
+  int64_t ld = 0;
+};
+
+struct DirPlan {
+  DenseTile* d_tiles = nullptr;
+  int ntiles = 0;
+  FinishItem* d_items = nullptr;
+  int nitems = 0;
+  DiagTerm* d_diags = nullptr;
+  char* W = nullptr;
+  char* stage_in = nullptr;   // input slice received from its owner
+  char* stage_out = nullptr;  // reduced partial pushed to the owner
+  char* R = nullptr;          // planes received from the other cells of the grid row / column
+};
+
+struct Cell {
+  int r = 0, c = 0, rank = 0;
+  DirPlan fwd, adj;
+};
+
+struct djets_op_s {
+  djets_ctx ctx = nullptr;
+  int dtype = 0;
+  int64_t nbrow = 0, nbcol = 0;
+  std::vector<int64_t> row_len, col_len;
+  int n1 = 1, n2 = 1;
+  std::vector<int> grid;  // column-major n1 x n2
+  std::vector<int64_t> row_cuts, col_cuts;
+  bool isdiag = false;
+  std::vector<Block> blocks;  // nbrow x nbcol, row-major; payloads only for blocks of local cells
+  std::vector<Cell> cells;    // column-major n1 x n2
+  std::vector<int64_t> row_off, col_off;         // element offset of block row / column inside its part
+  std::vector<int64_t> rowpart_len, colpart_len;  // elements per range / domain part
+  bool finalized = false;
+  int64_t p_fwd_tx = 32, p_adj_ru = 4, p_ld_policy = 0;
+
+  int rank_at(int r, int c) const { return grid[r + c * n1]; }
+  Cell& cell(int r, int c) { return cells[r + c * n1]; }
+  Block& block(int64_t i, int64_t j) { return blocks[i * nbcol + j]; }
+  int row_cell(int64_t i) const {
+    return (int)(std::upper_bound(row_cuts.begin(), row_cuts.end(), i) - row_cuts.begin()) - 1;
+  }
+  int col_cell(int64_t j) const {
+    return (int)(std::upper_bound(col_cuts.begin(), col_cuts.end(), j) - col_cuts.begin()) - 1;
+  }
+  int ndom_parts() const { return isdiag ? n1 : n2; }
+};
+
+namespace {
+
+void free_plan(DirPlan& p) {
+  cudaFree(p.d_tiles);
+  cudaFree(p.d_items);
+  cudaFree(p.d_diags);
+  cudaFree(p.W);
+  cudaFree(p.stage_in);
+  cudaFree(p.stage_out);
+  cudaFree(p.R);
+  p = DirPlan();
+}
+
+template <class T>
+T* upload(const std::vector<T>& v) {
+  if (v.empty()) return nullptr;
+  T* d = nullptr;
+  CK(cudaMalloc(&d, v.size() * sizeof(T)));
+  CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+char* dalloc(size_t bytes) {
+  if (bytes == 0) return nullptr;
+  char* d = nullptr;
+  CK(cudaMalloc(&d, bytes + 256));
+  CK(cudaMemset(d, 0, bytes + 256));
+  return d;
+}
+
+struct TileShape {
+  int64_t tile_rows, tile_cols, ntiles, nplanes;
+};
+
+// Forward: row strips of fwd_tx*VEC rows, column panels of at most fwd_tc (<= kFwdMaxTC) columns,
+// balanced.  Adjoint: row panels of at most adj_max_rows rows, column groups of adj_tc columns.
+TileShape plan_shape(int dtype, int64_t m, int64_t n, bool adjoint, int64_t fwd_tx, int64_t fwd_tc, int64_t adj_tc) {
+  TileShape s{0, 0, 0, 0};
+  if (m <= 0 || n <= 0) return s;
+  if (!adjoint) {
+    const int64_t tr = fwd_tx * vec_elems(dtype);
+    const int64_t tcmax = std::max<int64_t>(1, std::min<int64_t>(fwd_tc, kFwdMaxTC));
+    const int64_t npan = ceil_div(n, tcmax);
+    s.tile_rows = tr;
+    s.tile_cols = ceil_div(n, npan);
+    s.nplanes = npan;
+    s.ntiles = ceil_div(m, tr) * npan;
+  } else {
+    const int64_t trmax = adj_max_rows(dtype);
+    const int64_t npan = ceil_div(m, trmax);
+    s.tile_rows = round_up(ceil_div(m, npan), vec_elems(dtype));
+    s.tile_cols = std::max<int64_t>(kAdjCW, round_up(adj_tc, kAdjCW));
+    s.nplanes = ceil_div(m, s.tile_rows);
+    s.ntiles = s.nplanes * ceil_div(n, s.tile_cols);
+  }
+  return s;
+}
+
+// Builds one direction of one cell.  `outs` are the block indices along the output dimension that
+// the cell owns (block rows for forward, block columns for adjoint), `ins` along the input one.
+void build_plan(djets_op op, Cell& cell, bool adjoint) {
+  djets_ctx ctx = op->ctx;
+  RankCtx* rc = ctx->local(cell.rank);
+  if (!rc) return;
+  use(*rc);
+  DirPlan& plan = adjoint ? cell.adj : cell.fwd;
+  free_plan(plan);
+  const int es = elem_size(op->dtype);
+  const int64_t r0 = op->row_cuts[cell.r], r1 = op->row_cuts[cell.r + 1];
+  const int64_t c0 = op->isdiag ? r0 : op->col_cuts[cell.c], c1 = op->isdiag ? r1 : op->col_cuts[cell.c + 1];
+  const int64_t o0 = adjoint ? c0 : r0, o1 = adjoint ? c1 : r1;  // output blocks
+  const int64_t i0 = adjoint ? r0 : c0, i1 = adjoint ? r1 : c1;  // input blocks
+  const std::vector<int64_t>& out_len = adjoint ? op->col_len : op->row_len;
+  const std::vector<int64_t>& out_off = adjoint ? op->col_off : op->row_off;
+  const std::vector<int64_t>& in_off = adjoint ? op->row_off : op->col_off;
+  // the cell that owns the output part is on grid column 0 (forward) / grid row 0 (adjoint)
+  const bool owner = adjoint ? (op->isdiag || cell.r == 0) : (cell.c == 0);
+  const int nremote = owner ? ((adjoint ? (op->isdiag ? 1 : op->n1) : op->n2) - 1) : 0;
+  const int64_t part_len = adjoint ? (op->isdiag ? op->colpart_len[cell.r] : op->colpart_len[cell.c])
+                                   : op->rowpart_len[cell.r];
+
+  std::vector<DenseTile> tiles;
+  std::vector<FinishItem> items;
+  std::vector<DiagTerm> diags;
+  int64_t wtotal = 0;
+
+  for (int64_t o = o0; o < o1; ++o) {
+    const int64_t olen = out_len[o];
+    if (olen == 0) continue;
+    struct Contribution {
+      int64_t in;
+      Block* b;
+    };
+    std::vector<Contribution> dense, diag;
+    int64_t nplanes = 0;
+    for (int64_t in = i0; in < i1; ++in) {
+      if (op->isdiag && in != o) continue;
+      const int64_t i = adjoint ? in : o, j = adjoint ? o : in;
+      Block& b = op->block(i, j);
+      if (b.kind == DJETS_BLOCK_DENSE && op->row_len[i] > 0 && op->col_len[j] > 0) {
+        dense.push_back({in, &b});
+        nplanes += plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, op->p_fwd_tx, ctx->fwd_tc,
+                              ctx->adj_tc)
+                       .nplanes;
+      } else if (b.kind == DJETS_BLOCK_DIAG) {
+        diag.push_back({in, &b});
+      }
+    }
+    const bool direct = (nplanes == 1 && diag.empty() && nremote == 0);
+    const int64_t wbase = wtotal;
+    if (!direct) wtotal += nplanes * olen;
+    int64_t plane = 0;
+    for (const Contribution& cb : dense) {
+      const int64_t i = adjoint ? cb.in : o, j = adjoint ? o : cb.in;
+      const int64_t m = op->row_len[i], n = op->col_len[j];
+      const TileShape sh = plan_shape(op->dtype, m, n, adjoint, op->p_fwd_tx, ctx->fwd_tc, ctx->adj_tc);
+      if (!adjoint) {
+        for (int64_t col0 = 0, p = 0; col0 < n; col0 += sh.tile_cols, ++p) {
+          for (int64_t row0 = 0; row0 < m; row0 += sh.tile_rows) {
+            DenseTile t;
+            t.A = cb.b->d + (row0 + col0 * cb.b->ld) * es;
+            t.ld = cb.b->ld;
+            t.vin = in_off[j] + col0;
+            t.rows = (int)std::min<int64_t>(sh.tile_rows, m - row0);
+            t.cols = (int)std::min<int64_t>(sh.tile_cols, n - col0);
+            t.direct = direct ? 1 : 0;
+            t.wout = direct ? out_off[o] + row0 : wbase + (plane + p) * olen + row0;
+            t.pad_ = 0;
+            tiles.push_back(t);
+          }
+        }
+      } else {
+        for (int64_t row0 = 0, p = 0; row0 < m; row0 += sh.tile_rows, ++p) {
+          for (int64_t col0 = 0; col0 < n; col0 += sh.tile_cols) {
+            DenseTile t;
+            t.A = cb.b->d + (row0 + col0 * cb.b->ld) * es;
+            t.ld = cb.b->ld;
+            t.vin = in_off[i] + row0;
+            t.rows = (int)std::min<int64_t>(sh.tile_rows, m - row0);
+            t.cols = (int)std::min<int64_t>(sh.tile_cols, n - col0);
+            t.direct = direct ? 1 : 0;
+            t.wout = direct ? out_off[o] + col0 : wbase + (plane + p) * olen + col0;
+            t.pad_ = 0;
+            tiles.push_back(t);
+          }
+        }
+      }
+      plane += sh.nplanes;
+    }
+    if (direct) continue;
+    for (int64_t e0 = 0; e0 < olen; e0 += kFinishChunk) {
+      FinishItem it;
+      it.out = out_off[o] + e0;
+      it.w0 = wbase + e0;
+      it.wstride = olen;
+      it.r0 = out_off[o] + e0;
+      it.rstride = part_len;
+      it.nplanes = (int)nplanes;
+      it.nremote = nremote;
+      it.diag_begin = (int)diags.size();
+      for (const Contribution& cb : diag) {
+        DiagTerm d;
+        d.d = cb.b->d + e0 * es;
+        d.vin = in_off[cb.in] + e0;
+        diags.push_back(d);
+      }
+      it.diag_end = (int)diags.size();
+      it.len = (int)std::min<int64_t>(kFinishChunk, olen - e0);
+      it.pad_ = 0;
+      items.push_back(it);
+    }
+  }
+  plan.ntiles = (int)tiles.size();
+  plan.nitems = (int)items.size();
+  plan.d_tiles = upload(tiles);
+  plan.d_items = upload(items);
+  plan.d_diags = upload(diags);
+  plan.W = dalloc((size_t)wtotal * es);
+  // exchange buffers
+  const int64_t in_len = adjoint ? op->rowpart_len[cell.r]
+                                 : (op->isdiag ? op->colpart_len[cell.r] : op->colpart_len[cell.c]);
+  const bool in_owner = adjoint ? (cell.c == 0) : (op->isdiag || cell.r == 0);
+  if (!in_owner) plan.stage_in = dalloc((size_t)in_len * es);
+  if (!owner) plan.stage_out = dalloc((size_t)part_len * es);
+  if (nremote > 0) plan.R = dalloc((size_t)nremote * part_len * es);
+}
+
+void check_vec(djets_op op, djets_vec v, bool is_range, const char* what) {
+  REQUIRE(v && v->ctx == op->ctx, DJETS_ERR_INVALID, std::string(what) + ": vector of another context");
+  REQUIRE(v->dtype == op->dtype, DJETS_ERR_MISMATCH, std::string(what) + ": element type differs from the operator's");
+  const int np = is_range ? op->n1 : op->ndom_parts();
+  const std::vector<int64_t>& len = is_range ? op->row_len : op->col_len;
+  const std::vector<int64_t>& cuts = (is_range || op->isdiag) ? op->row_cuts : op->col_cuts;
+  REQUIRE((int)v->parts.size() == np && v->block_len == len, DJETS_ERR_MISMATCH,
+          std::string(what) + ": block layout differs from the operator's " + (is_range ? "range" : "domain"));
+  for (int p = 0; p < np; ++p) {
+    const int rank = (is_range || op->isdiag) ? op->rank_at(p, 0) : op->rank_at(0, p);
+    REQUIRE(v->parts[p].rank == rank && v->parts[p].blk_first == cuts[p] &&
+                v->parts[p].blk_count == cuts[p + 1] - cuts[p],
+            DJETS_ERR_MISMATCH, std::string(what) + ": partition differs from the operator's");
+  }
+}
+
+void finalize_op(djets_op op) {
+  if (op->finalized) return;
+  op->p_fwd_tx = op->ctx->fwd_tx;
+  op->p_adj_ru = op->ctx->adj_ru;
+  op->p_ld_policy = op->ctx->ld_policy;
+  for (Cell& c : op->cells) {
+    build_plan(op, c, false);
+    build_plan(op, c, true);
+  }
+  op->finalized = true;
+}
+
+// mul!(out, A, in) (adjoint = false) or mul!(out, A', in) (adjoint = true)
+void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
+  djets_ctx ctx = op->ctx;
+  check_vec(op, out, !adjoint, adjoint ? "mul!(m, A', d): m" : "mul!(d, A, m): d");
+  check_vec(op, in, adjoint, adjoint ? "mul!(m, A', d): d" : "mul!(d, A, m): m");
+  REQUIRE(out != in, DJETS_ERR_INVALID, "mul!: output aliases input");
+  finalize_op(op);
+  const int es = elem_size(op->dtype);
+  const int n1 = op->n1, n2 = op->isdiag ? 1 : op->n2;
+
+  // phase A: every cell gets the input blocks of its block columns (forward) / block rows (adjoint)
+  // from the cell of grid row 0 / grid column 0 that owns them (replaces the per-(i,j) remote
+  // getblock(m, icol) of src:588,635 and getblock(d, irow) of src:682).
+  std::vector<Transfer> ts;
+  if (!op->isdiag) {
+    for (int c = 0; c < n2; ++c)
+      for (int r = 0; r < n1; ++r) {
+        const bool in_owner = adjoint ? (c == 0) : (r == 0);
+        if (in_owner) continue;
+        Cell& cell = op->cell(r, c);
+        DirPlan& plan = adjoint ? cell.adj : cell.fwd;
+        const int ip = adjoint ? r : c;
+        const VecPart& part = in->parts[ip];
+        ts.push_back({part.rank, part.d, cell.rank, plan.stage_in, (size_t)part.elem_count * es});
+      }
+    run_transfers(ctx, ts);
+  }
+
+  // phase B: tile kernels, then the segmented sum on cells that do not own the output part
+  for (int c = 0; c < n2; ++c)
+    for (int r = 0; r < n1; ++r) {
+      Cell& cell = op->cell(r, c);
+      RankCtx* rc = ctx->local(cell.rank);
+      if (!rc) continue;
+      use(*rc);
+      DirPlan& plan = adjoint ? cell.adj : cell.fwd;
+      const bool in_owner = op->isdiag || (adjoint ? (c == 0) : (r == 0));
+      const bool owner = op->isdiag || (adjoint ? (r == 0) : (c == 0));
+      const int ip = op->isdiag ? r : (adjoint ? r : c);
+      const int opart = op->isdiag ? r : (adjoint ? c : r);
+      const char* inp = in_owner ? in->parts[ip].d : plan.stage_in;
+      char* outp = owner ? out->parts[opart].d : plan.stage_out;
+      if (plan.ntiles > 0) {
+        if (!adjoint)
+          launch_counted(ctx, *rc, DJETS_K_GEMV_N, [&] {
+            return launch_gemv_n(op->dtype, (int)op->p_fwd_tx, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles, inp,
+                                 plan.W, outp, rc->stream);
+          });
+        else
+          launch_counted(ctx, *rc, DJETS_K_GEMV_T, [&] {
+            return launch_gemv_t(op->dtype, (int)op->p_adj_ru, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles, inp,
+                                 plan.W, outp, rc->stream);
+          });
+      }
+      if (!owner && plan.nitems > 0)
+        launch_counted(ctx, *rc, DJETS_K_FINISH, [&] {
+          return launch_finish(op->dtype, plan.d_items, plan.nitems, plan.d_diags, inp, plan.W, nullptr, outp,
+                               rc->stream);
+        });
+    }
+
+  // phase C: partials of the other cells of a grid row (forward) / grid column (adjoint) go to the
+  // owner (replaces ArrayFutures + reduce! of src:600-604, 647-651, 694-698)
+  if (!op->isdiag && (adjoint ? n1 : n2) > 1) {
+    ts.clear();
+    for (int c = 0; c < n2; ++c)
+      for (int r = 0; r < n1; ++r) {
+        const bool owner = adjoint ? (r == 0) : (c == 0);
+        if (owner) continue;
+        Cell& cell = op->cell(r, c);
+        Cell& own = adjoint ? op->cell(0, c) : op->cell(r, 0);
+        DirPlan& plan = adjoint ? cell.adj : cell.fwd;
+        DirPlan& oplan = adjoint ? own.adj : own.fwd;
+        const int64_t part_len = adjoint ? op->colpart_len[c] : op->rowpart_len[r];
+        const int q = (adjoint ? r : c) - 1;
+        ts.push_back({cell.rank, plan.stage_out, own.rank, oplan.R ? oplan.R + (size_t)q * part_len * es : nullptr,
+                      (size_t)part_len * es});
+      }
+    run_transfers(ctx, ts);
+  }
+
+  // phase D: owners sum their planes, the received planes and their diagonal blocks
+  for (int c = 0; c < n2; ++c)
+    for (int r = 0; r < n1; ++r) {
+      const bool owner = op->isdiag || (adjoint ? (r == 0) : (c == 0));
+      if (!owner) continue;
+      Cell& cell = op->cell(r, c);
+      RankCtx* rc = ctx->local(cell.rank);
+      if (!rc) continue;
+      use(*rc);
+      DirPlan& plan = adjoint ? cell.adj : cell.fwd;
+      if (plan.nitems == 0) continue;
+      const int ip = op->isdiag ? r : (adjoint ? r : c);
+      const int opart = op->isdiag ? r : (adjoint ? c : r);
+      const bool in_owner = op->isdiag || (adjoint ? (c == 0) : (r == 0));
+      const char* inp = in_owner ? in->parts[ip].d : plan.stage_in;
+      launch_counted(ctx, *rc, DJETS_K_FINISH, [&] {
+        return launch_finish(op->dtype, plan.d_items, plan.nitems, plan.d_diags, inp, plan.W, plan.R,
+                             out->parts[opart].d, rc->stream);
+      });
+    }
+}
+
+}  // namespace
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+extern "C" {
+
+int32_t djets_version(void) { return 100; }
+const char* djets_last_error(void) { return g_last_error.c_str(); }
+
+int32_t djets_even_cuts(int64_t n, int32_t nparts, int64_t* cuts) {
+  return guard([&] {
+    REQUIRE(n >= 0 && nparts >= 1 && cuts, DJETS_ERR_INVALID, "even_cuts: bad arguments");
+    const int64_t q = n / nparts, rem = n % nparts;
+    cuts[0] = 0;
+    for (int k = 0; k < nparts; ++k) cuts[k + 1] = cuts[k] + q + (k < rem ? 1 : 0);
+  });
+}
+
+int32_t djets_grid_rank(int32_t n1, int32_t n2, int32_t r, int32_t c, const int32_t* grid_ranks, int32_t* rank) {
+  return guard([&] {
+    REQUIRE(n1 >= 1 && n2 >= 1 && r >= 0 && r < n1 && c >= 0 && c < n2 && rank, DJETS_ERR_INVALID,
+            "grid_rank: bad arguments");
+    const int idx = r + c * n1;
+    *rank = grid_ranks ? grid_ranks[idx] : idx;
+  });
+}
+
+int32_t djets_plan_tiles(int32_t dtype, int64_t m, int64_t n, int32_t adjoint, int64_t* tile_rows, int64_t* tile_cols,
+                         int64_t* ntiles) {
+  return guard([&] {
+    REQUIRE(dtype == DJETS_F32 || dtype == DJETS_F64, DJETS_ERR_INVALID, "plan_tiles: bad dtype");
+    REQUIRE(m >= 0 && n >= 0, DJETS_ERR_INVALID, "plan_tiles: negative size");
+    djets_ctx_s defaults;
+    const TileShape s = plan_shape(dtype, m, n, adjoint != 0, defaults.fwd_tx, defaults.fwd_tc, defaults.adj_tc);
+    if (tile_rows) *tile_rows = s.tile_rows;
+    if (tile_cols) *tile_cols = s.tile_cols;
+    if (ntiles) *ntiles = s.ntiles;
+  });
+}
+
+int32_t djets_device_count(int32_t* n) {
+  return guard([&] {
+    int c = 0;
+    CK(cudaGetDeviceCount(&c));
+    *n = c;
+  });
+}
+
+int32_t djets_nccl_unique_id(uint8_t* out128) {
+  return guard([&] {
+    const char* why = nullptr;
+    const NcclApi* api = nccl_api(&why);
+    REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCK(api, api->GetUniqueId(&id));
+    memcpy(out128, &id, 128);
+  });
+}
+
+int32_t djets_host_alloc(int64_t bytes, void** out) {
+  return guard([&] {
+    REQUIRE(bytes >= 0 && out, DJETS_ERR_INVALID, "host_alloc: bad arguments");
+    CK(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable));
+  });
+}
+int32_t djets_host_free(void* p) {
+  return guard([&] {
+    if (p) CK(cudaFreeHost(p));
+  });
+}
+
+int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ranks, const int32_t* device_ids,
+                         const uint8_t* nccl_uid, djets_ctx* out) {
+  return guard([&] {
+    REQUIRE(out, DJETS_ERR_INVALID, "ctx_create: null out");
+    REQUIRE(world >= 1 && nlocal >= 1 && nlocal <= world, DJETS_ERR_INVALID, "ctx_create: bad world / nlocal");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    REQUIRE(ndev > 0, DJETS_ERR_CUDA, "no CUDA device: libdjets_b200 has no CPU path");
+    auto ctx = std::make_unique<djets_ctx_s>();
+    ctx->world = world;
+    ctx->local_of_rank.assign(world, -1);
+    ctx->ranks.resize(nlocal);
+    for (int l = 0; l < nlocal; ++l) {
+      RankCtx& rc = ctx->ranks[l];
+      rc.rank = local_ranks ? local_ranks[l] : l;
+      rc.device = device_ids ? device_ids[l] : (l % ndev);
+      REQUIRE(rc.rank >= 0 && rc.rank < world && ctx->local_of_rank[rc.rank] < 0, DJETS_ERR_INVALID,
+              "ctx_create: bad or repeated local rank");
+      REQUIRE(rc.device >= 0 && rc.device < ndev, DJETS_ERR_INVALID, "ctx_create: device id out of range");
+      ctx->local_of_rank[rc.rank] = l;
+      use(rc);
+      cudaDeviceProp prop;
+      CK(cudaGetDeviceProperties(&prop, rc.device));
+      REQUIRE(prop.major >= 10, DJETS_ERR_CUDA,
+              std::string("device ") + prop.name + " is not sm_100-class: libdjets_b200 carries sm_100a code only");
+      CK(cudaStreamCreateWithFlags(&rc.stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&rc.ev, cudaEventDisableTiming));
+      CK(cudaEventCreate(&rc.t0));
+      CK(cudaEventCreate(&rc.t1));
+      CK(cudaMalloc(&rc.d_partials, sizeof(double) * reduce_max_ctas()));
+      CK(cudaMalloc(&rc.d_result, sizeof(double) * 2 * kMaxParts));
+      CK(cudaHostAlloc(&rc.h_result, sizeof(double) * 2 * kMaxParts, cudaHostAllocPortable));
+    }
+    // peer access between the GPUs this process drives (local->local exchange is a peer copy)
+    for (RankCtx& a : ctx->ranks)
+      for (RankCtx& b : ctx->ranks) {
+        if (a.device == b.device) continue;
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, a.device, b.device));
+        if (can) {
+          use(a);
+          cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+          (void)cudaGetLastError();
+        }
+      }
+    if (nccl_uid) {
+      const char* why = nullptr;
+      const NcclApi* api = nccl_api(&why);
+      REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
+      ncclUniqueId id;
+      memcpy(&id, nccl_uid, 128);
+      NCK(api, api->GroupStart());
+      for (RankCtx& rc : ctx->ranks) {
+        use(rc);
+        NCK(api, api->CommInitRank(&rc.comm, world, id, rc.rank));
+      }
+      NCK(api, api->GroupEnd());
+      ctx->has_nccl = true;
+    }
+    *out = ctx.release();
+  });
+}
+
+int32_t djets_ctx_destroy(djets_ctx ctx) {
+  return guard([&] {
+    if (!ctx) return;
+    const NcclApi* api = ctx->has_nccl ? nccl_api(nullptr) : nullptr;
+    for (RankCtx& rc : ctx->ranks) {
+      cudaSetDevice(rc.device);
+      cudaStreamSynchronize(rc.stream);
+      if (rc.comm && api) api->CommDestroy(rc.comm);
+      for (auto& k : rc.pending) {
+        cudaEventDestroy(k.a);
+        cudaEventDestroy(k.b);
+      }
+      for (auto e : rc.pool) cudaEventDestroy(e);
+      cudaFree(rc.d_partials);
+      cudaFree(rc.d_result);
+      cudaFreeHost(rc.h_result);
+      cudaEventDestroy(rc.ev);
+      cudaEventDestroy(rc.t0);
+      cudaEventDestroy(rc.t1);
+      cudaStreamDestroy(rc.stream);
+    }
+    delete ctx;
+  });
+}
+
+int32_t djets_ctx_sync(djets_ctx ctx) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      CK(cudaStreamSynchronize(rc.stream));
+    }
+  });
+}
+
+int32_t djets_ctx_info(djets_ctx ctx, int32_t* world, int32_t* nlocal, int32_t* has_nccl) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    if (world) *world = ctx->world;
+    if (nlocal) *nlocal = (int32_t)ctx->ranks.size();
+    if (has_nccl) *has_nccl = ctx->has_nccl ? 1 : 0;
+  });
+}
+
+int32_t djets_ctx_is_local(djets_ctx ctx, int32_t rank, int32_t* is_local) {
+  return guard([&] {
+    REQUIRE(ctx && is_local, DJETS_ERR_INVALID, "null argument");
+    *is_local = ctx->local(rank) ? 1 : 0;
+  });
+}
+
+int32_t djets_timer_start(djets_ctx ctx) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      CK(cudaEventRecord(rc.t0, rc.stream));
+    }
+  });
+}
+
+int32_t djets_timer_stop(djets_ctx ctx, float* ms) {
+  return guard([&] {
+    REQUIRE(ctx && ms, DJETS_ERR_INVALID, "null argument");
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      CK(cudaEventRecord(rc.t1, rc.stream));
+    }
+    float worst = 0.f;
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      CK(cudaEventSynchronize(rc.t1));
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, rc.t0, rc.t1));
+      worst = std::max(worst, t);
+    }
+    *ms = worst;
+  });
+}
+
+int32_t djets_ctx_kernel_timing(djets_ctx ctx, int32_t enable) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    if (!enable)
+      for (RankCtx& rc : ctx->ranks) drain_events(rc);
+    ctx->timing = enable != 0;
+  });
+}
+
+int32_t djets_ctx_kernel_stats(djets_ctx ctx, int32_t kind, int64_t* launches, double* total_ms) {
+  return guard([&] {
+    REQUIRE(ctx && kind >= 0 && kind < DJETS_K_COUNT, DJETS_ERR_INVALID, "kernel_stats: bad arguments");
+    int64_t n = 0;
+    double ms = 0.0;
+    for (RankCtx& rc : ctx->ranks) {
+      drain_events(rc);
+      n += rc.launches[kind];
+      ms = std::max(ms, rc.ms[kind]);
+    }
+    if (launches) *launches = n;
+    if (total_ms) *total_ms = ms;
+  });
+}
+
+int32_t djets_ctx_reset_stats(djets_ctx ctx) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    for (RankCtx& rc : ctx->ranks) {
+      drain_events(rc);
+      for (int k = 0; k < DJETS_K_COUNT; ++k) {
+        rc.launches[k] = 0;
+        rc.ms[k] = 0.0;
+      }
+    }
+  });
+}
+
+int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
+  return guard([&] {
+    REQUIRE(ctx && name, DJETS_ERR_INVALID, "null argument");
+    const std::string n(name);
+    if (n == "fwd_tx") {
+      REQUIRE(value == 32 || value == 64 || value == 128 || value == 256, DJETS_ERR_INVALID, "fwd_tx in {32,64,128,256}");
+      ctx->fwd_tx = value;
+    } else if (n == "fwd_tc") {
+      REQUIRE(value >= 1 && value <= kFwdMaxTC, DJETS_ERR_INVALID, "fwd_tc in 1..1024");
+      ctx->fwd_tc = value;
+    } else if (n == "adj_ru") {
+      REQUIRE(value == 1 || value == 2 || value == 4, DJETS_ERR_INVALID, "adj_ru in {1,2,4}");
+      ctx->adj_ru = value;
+    } else if (n == "adj_tc") {
+      REQUIRE(value >= kAdjCW && value <= 4096, DJETS_ERR_INVALID, "adj_tc in 4..4096");
+      ctx->adj_tc = value;
+    } else if (n == "ld_policy") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "ld_policy in {0,1}");
+      ctx->ld_policy = value;
+    } else {
+      fail(DJETS_ERR_INVALID, "unknown parameter " + n);
+    }
+  });
+}
+
+// ---- DBArray ------------------------------------------------------------------------------------------
+int32_t djets_vec_create(djets_ctx ctx, int32_t dtype, int32_t nparts, const int32_t* part_rank,
+                         const int64_t* part_nblocks, const int64_t* block_len, djets_vec* out) {
+  return guard([&] {
+    REQUIRE(out && part_rank && part_nblocks && block_len, DJETS_ERR_INVALID, "vec_create: null argument");
+    *out = make_vec(ctx, dtype, nparts, part_rank, part_nblocks, block_len);
+  });
+}
+
+int32_t djets_vec_similar(djets_vec x, int32_t dtype, djets_vec* out) {
+  return guard([&] {
+    REQUIRE(x && out, DJETS_ERR_INVALID, "vec_similar: null argument");
+    std::vector<int32_t> ranks;
+    std::vector<int64_t> nb;
+    for (VecPart& p : x->parts) {
+      ranks.push_back(p.rank);
+      nb.push_back(p.blk_count);
+    }
+    *out = make_vec(x->ctx, dtype, (int)x->parts.size(), ranks.data(), nb.data(), x->block_len.data());
+  });
+}
+
+int32_t djets_vec_destroy(djets_vec x) {
+  return guard([&] {
+    if (!x) return;
+    std::lock_guard<std::mutex> lock(x->ctx->mu);
+    free_vec(x);
+  });
+}
+
+int32_t djets_vec_info(djets_vec x, int32_t* dtype, int64_t* length, int64_t* nblocks, int32_t* nparts) {
+  return guard([&] {
+    REQUIRE(x, DJETS_ERR_INVALID, "null vector");
+    if (dtype) *dtype = x->dtype;
+    if (length) *length = x->length;
+    if (nblocks) *nblocks = (int64_t)x->block_len.size();
+    if (nparts) *nparts = (int32_t)x->parts.size();
+  });
+}
+
+int32_t djets_vec_part_info(djets_vec x, int32_t part, int32_t* rank, int64_t* blk_first, int64_t* blk_count,
+                            int64_t* elem_first, int64_t* elem_count) {
+  return guard([&] {
+    REQUIRE(x && part >= 0 && part < (int)x->parts.size(), DJETS_ERR_INVALID, "part_info: bad part");
+    const VecPart& p = x->parts[part];
+    if (rank) *rank = p.rank;
+    if (blk_first) *blk_first = p.blk_first;
+    if (blk_count) *blk_count = p.blk_count;
+    if (elem_first) *elem_first = p.elem_first;
+    if (elem_count) *elem_count = p.elem_count;
+  });
+}
+
+int32_t djets_vec_block_info(djets_vec x, int64_t iblock, int32_t* part, int64_t* elem_first, int64_t* len) {
+  return guard([&] {
+    REQUIRE(x && iblock >= 0 && iblock < (int64_t)x->block_len.size(), DJETS_ERR_INVALID, "block index out of range");
+    if (part) *part = x->block_part[iblock];
+    if (elem_first) *elem_first = x->block_off[iblock];
+    if (len) *len = x->block_len[iblock];
+  });
+}
+
+static void block_copy(djets_vec x, int64_t iblock, void* host, bool to_device) {
+  REQUIRE(x && iblock >= 0 && iblock < (int64_t)x->block_len.size(), DJETS_ERR_INVALID, "block index out of range");
+  VecPart& p = x->parts[x->block_part[iblock]];
+  RankCtx* rc = x->ctx->local(p.rank);
+  if (!rc) {
+    if (to_device) return;  // setblock! on a process that does not drive the owner is a no-op
+    fail(DJETS_ERR_NOT_LOCAL, "getblock: block is owned by a rank of another process");
+  }
+  const int es = elem_size(x->dtype);
+  const size_t bytes = (size_t)x->block_len[iblock] * es;
+  if (bytes == 0) return;
+  REQUIRE(host, DJETS_ERR_INVALID, "null host pointer");
+  use(*rc);
+  char* d = p.d + (size_t)(x->block_off[iblock] - p.elem_first) * es;
+  if (to_device)
+    CK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, rc->stream));
+  else
+    CK(cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, rc->stream));
+  CK(cudaStreamSynchronize(rc->stream));
+}
+
+int32_t djets_vec_setblock(djets_vec x, int64_t iblock, const void* host_src) {
+  return guard([&] { block_copy(x, iblock, const_cast<void*>(host_src), true); });
+}
+int32_t djets_vec_getblock(djets_vec x, int64_t iblock, void* host_dst) {
+  return guard([&] { block_copy(x, iblock, host_dst, false); });
+}
+
+int32_t djets_vec_getindex(djets_vec x, int64_t i, double* out) {
+  return guard([&] {
+    REQUIRE(x && out, DJETS_ERR_INVALID, "null argument");
+    REQUIRE(i >= 0 && i < x->length, DJETS_ERR_INVALID, "BoundsError: index outside the DBArray");
+    for (VecPart& p : x->parts) {
+      if (i < p.elem_first || i >= p.elem_first + p.elem_count) continue;  // findfirst(rng->i in rng) src:175
+      RankCtx* rc = x->ctx->local(p.rank);
+      REQUIRE(rc, DJETS_ERR_NOT_LOCAL, "getindex: element is owned by a rank of another process");
+      use(*rc);
+      const int es = elem_size(x->dtype);
+      double buf = 0.0;
+      CK(cudaMemcpyAsync(&buf, p.d + (size_t)(i - p.elem_first) * es, es, cudaMemcpyDeviceToHost, rc->stream));
+      CK(cudaStreamSynchronize(rc->stream));
+      if (x->dtype == DJETS_F32) {
+        float f;
+        memcpy(&f, &buf, 4);
+        *out = (double)f;
+      } else {
+        *out = buf;
+      }
+      return;
+    }
+    fail(DJETS_ERR_INVALID, "getindex: no part holds the index");
+  });
+}
+
+static void bulk_copy(djets_vec x, void* host, bool to_device) {
+  REQUIRE(x, DJETS_ERR_INVALID, "null vector");
+  REQUIRE(host || x->length == 0, DJETS_ERR_INVALID, "null host pointer");
+  const int es = elem_size(x->dtype);
+  for (VecPart& p : x->parts) {
+    RankCtx* rc = x->ctx->local(p.rank);
+    if (!rc || p.elem_count == 0) continue;
+    use(*rc);
+    char* h = reinterpret_cast<char*>(host) + (size_t)p.elem_first * es;
+    if (to_device)
+      CK(cudaMemcpyAsync(p.d, h, (size_t)p.elem_count * es, cudaMemcpyHostToDevice, rc->stream));
+    else
+      CK(cudaMemcpyAsync(h, p.d, (size_t)p.elem_count * es, cudaMemcpyDeviceToHost, rc->stream));
+  }
+  for (VecPart& p : x->parts)
+    if (RankCtx* rc = x->ctx->local(p.rank)) {
+      use(*rc);
+      CK(cudaStreamSynchronize(rc->stream));
+    }
+}
+
+int32_t djets_vec_collect(djets_vec x, void* host_dst) {
+  return guard([&] { bulk_copy(x, host_dst, false); });
+}
+int32_t djets_vec_scatter(djets_vec x, const void* host_src) {
+  return guard([&] { bulk_copy(x, const_cast<void*>(host_src), true); });
+}
+
+int32_t djets_vec_fill(djets_vec x, double a) {
+  return guard([&] {
+    REQUIRE(x, DJETS_ERR_INVALID, "null vector");
+    for (VecPart& p : x->parts) {
+      RankCtx* rc = x->ctx->local(p.rank);
+      if (!rc) continue;
+      use(*rc);
+      launch_counted(x->ctx, *rc, DJETS_K_ELTWISE,
+                     [&] { return launch_fill(x->dtype, p.d, a, p.elem_count, rc->stream); });
+    }
+  });
+}
+
+int32_t djets_vec_lincomb(djets_vec dest, int32_t nterms, const double* coef, const djets_vec* xs, int32_t flags) {
+  return guard([&] {
+    REQUIRE(dest && coef && xs, DJETS_ERR_INVALID, "lincomb: null argument");
+    REQUIRE(nterms >= 1 && nterms <= 4, DJETS_ERR_UNSUPPORTED, "lincomb: 1 to 4 terms");
+    for (int k = 0; k < nterms; ++k) {
+      REQUIRE(xs[k], DJETS_ERR_INVALID, "lincomb: null operand");
+      REQUIRE(same_layout(dest, xs[k]), DJETS_ERR_MISMATCH,
+              "DimensionMismatch: broadcast operands have different block layouts");
+    }
+    for (size_t p = 0; p < dest->parts.size(); ++p) {
+      VecPart& dp = dest->parts[p];
+      RankCtx* rc = dest->ctx->local(dp.rank);
+      if (!rc) continue;
+      use(*rc);
+      LincombArgs a;
+      a.nterms = nterms;
+      for (int k = 0; k < nterms; ++k) {
+        a.x[k] = xs[k]->parts[p].d;
+        a.coef[k] = coef[k];
+        a.xdtype[k] = xs[k]->dtype;
+      }
+      launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE,
+                     [&] { return launch_lincomb(dest->dtype, dp.d, a, dp.elem_count, flags & 1, rc->stream); });
+    }
+  });
+}
+
+int32_t djets_vec_binary(djets_vec dest, int32_t op, djets_vec a, djets_vec b) {
+  return guard([&] {
+    REQUIRE(dest && a && b, DJETS_ERR_INVALID, "binary: null argument");
+    REQUIRE(op == 0 || op == 1, DJETS_ERR_UNSUPPORTED, "binary: op 0 (.*) or 1 (./)");
+    REQUIRE(same_layout(dest, a) && same_layout(dest, b), DJETS_ERR_MISMATCH,
+            "DimensionMismatch: broadcast operands have different block layouts");
+    REQUIRE(dest->dtype == a->dtype && dest->dtype == b->dtype, DJETS_ERR_UNSUPPORTED,
+            "binary: operands must share the element type");
+    for (size_t p = 0; p < dest->parts.size(); ++p) {
+      VecPart& dp = dest->parts[p];
+      RankCtx* rc = dest->ctx->local(dp.rank);
+      if (!rc) continue;
+      use(*rc);
+      launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE, [&] {
+        return launch_binary(dest->dtype, op, dp.d, a->parts[p].d, b->parts[p].d, dp.elem_count, rc->stream);
+      });
+    }
+  });
+}
+
+int32_t djets_vec_reduce_parts(djets_vec x, int32_t kind, double param, double* out_parts) {
+  return guard([&] {
+    REQUIRE(x && out_parts, DJETS_ERR_INVALID, "reduce: null argument");
+    REQUIRE(kind >= 0 && kind <= DJETS_RED_SUMSQ_SHIFT, DJETS_ERR_INVALID, "reduce: unknown kind");
+    reduce_parts(x, nullptr, kind, param, out_parts);
+  });
+}
+
+int32_t djets_vec_reduce(djets_vec x, int32_t kind, double param, double* out) {
+  return guard([&] {
+    REQUIRE(x && out, DJETS_ERR_INVALID, "reduce: null argument");
+    REQUIRE(kind >= 0 && kind <= DJETS_RED_SUMSQ_SHIFT, DJETS_ERR_INVALID, "reduce: unknown kind");
+    std::vector<double> z(x->parts.size());
+    reduce_parts(x, nullptr, kind, param, z.data());
+    *out = fold_parts(x->dtype, kind, z.data(), (int)z.size());
+  });
+}
+
+int32_t djets_vec_dot(djets_vec x, djets_vec y, double* out) {
+  return guard([&] {
+    REQUIRE(x && y && out, DJETS_ERR_INVALID, "dot: null argument");
+    REQUIRE(same_layout(x, y), DJETS_ERR_MISMATCH, "DimensionMismatch: dot of DBArrays with different block layouts");
+    REQUIRE(x->dtype == y->dtype, DJETS_ERR_MISMATCH, "dot: element types differ (reference: MethodError, src:214)");
+    std::vector<double> z(x->parts.size());
+    reduce_parts(x, y, RED_DOT, 0.0, z.data());
+    *out = fold_parts(x->dtype, DJETS_RED_SUM, z.data(), (int)z.size());
+  });
+}
+
+int32_t djets_vec_norm(djets_vec x, double p, double* out) {
+  return guard([&] {
+    REQUIRE(x && out, DJETS_ERR_INVALID, "norm: null argument");
+    const int np = (int)x->parts.size();
+    const int dt = x->dtype;
+    std::vector<double> z(np);
+    if (p == INFINITY) {  // src:200-201
+      reduce_parts(x, nullptr, DJETS_RED_ABSMAX, 0.0, z.data());
+      *out = fold_parts(dt, DJETS_RED_MAX, z.data(), np);
+    } else if (p == -INFINITY) {  // src:202-203
+      reduce_parts(x, nullptr, DJETS_RED_ABSMIN, 0.0, z.data());
+      *out = fold_parts(dt, DJETS_RED_MIN, z.data(), np);
+    } else if (p == 0.0 || p == 1.0) {  // src:204-205
+      reduce_parts(x, nullptr, p == 0.0 ? DJETS_RED_NNZ : DJETS_RED_ABSSUM, 0.0, z.data());
+      *out = fold_parts(dt, DJETS_RED_SUM, z.data(), np);
+    } else {  // src:206-209: per-worker norms z, then (sum z^p)^(1/p) in float(real(T))
+      const double pp = round_to(dt, p);
+      reduce_parts(x, nullptr, p == 2.0 ? DJETS_RED_SUMSQ : DJETS_RED_SUMPOW, pp, z.data());
+      double s = 0.0;
+      for (int k = 0; k < np; ++k) {
+        const double zk = round_to(dt, p == 2.0 ? sqrt(z[k]) : pow(z[k], 1.0 / pp));
+        s = round_to(dt, s + round_to(dt, p == 2.0 ? zk * zk : pow(zk, pp)));
+      }
+      *out = round_to(dt, p == 2.0 ? sqrt(s) : pow(s, round_to(dt, 1.0 / pp)));
+    }
+  });
+}
+
+// ---- operator ---------------------------------------------------------------------------------------
+int32_t djets_op_create(djets_ctx ctx, int32_t dtype, int64_t nbrow, int64_t nbcol, const int64_t* row_len,
+                        const int64_t* col_len, int32_t n1, int32_t n2, const int32_t* grid_ranks,
+                        const int64_t* row_cuts, const int64_t* col_cuts, int32_t isdiag, djets_op* out) {
+  return guard([&] {
+    REQUIRE(ctx && out && row_len && col_len, DJETS_ERR_INVALID, "op_create: null argument");
+    REQUIRE(dtype == DJETS_F32 || dtype == DJETS_F64, DJETS_ERR_INVALID, "dtype must be DJETS_F32 or DJETS_F64");
+    REQUIRE(nbrow >= 1 && nbcol >= 1, DJETS_ERR_INVALID, "op_create: the operator needs at least one block");
+    REQUIRE(n1 >= 1 && n2 >= 1 && n1 <= nbrow && n2 <= nbcol && n1 * n2 <= ctx->world, DJETS_ERR_INVALID,
+            "op_create: process grid does not fit the blocks / the job");
+    REQUIRE(n1 <= kMaxParts && n2 <= kMaxParts, DJETS_ERR_INVALID, "op_create: grid too large");
+    if (isdiag) {
+      REQUIRE(n2 == 1, DJETS_ERR_INVALID, "block diagonal jets must define distribution along rows.");  // src:481
+      REQUIRE(nbrow == nbcol, DJETS_ERR_INVALID, "block diagonal operator must be square in blocks");
+    }
+    auto op = std::make_unique<djets_op_s>();
+    op->ctx = ctx;
+    op->dtype = dtype;
+    op->nbrow = nbrow;
+    op->nbcol = nbcol;
+    op->row_len.assign(row_len, row_len + nbrow);
+    op->col_len.assign(col_len, col_len + nbcol);
+    for (int64_t v : op->row_len) REQUIRE(v >= 0 && v < (1LL << 31), DJETS_ERR_INVALID, "bad block row length");
+    for (int64_t v : op->col_len) REQUIRE(v >= 0 && v < (1LL << 31), DJETS_ERR_INVALID, "bad block column length");
+    op->n1 = n1;
+    op->n2 = n2;
+    op->isdiag = isdiag != 0;
+    op->grid.resize((size_t)n1 * n2);
+    std::vector<char> seen(ctx->world, 0);
+    for (int k = 0; k < n1 * n2; ++k) {
+      op->grid[k] = grid_ranks ? grid_ranks[k] : k;
+      REQUIRE(op->grid[k] >= 0 && op->grid[k] < ctx->world && !seen[op->grid[k]], DJETS_ERR_INVALID,
+              "op_create: bad or repeated rank in the process grid");
+      seen[op->grid[k]] = 1;
+    }
+    op->row_cuts.resize(n1 + 1);
+    op->col_cuts.resize(n2 + 1);
+    if (row_cuts)
+      std::copy(row_cuts, row_cuts + n1 + 1, op->row_cuts.begin());
+    else
+      djets_even_cuts(nbrow, n1, op->row_cuts.data());
+    if (col_cuts)
+      std::copy(col_cuts, col_cuts + n2 + 1, op->col_cuts.begin());
+    else
+      djets_even_cuts(nbcol, n2, op->col_cuts.data());
+    REQUIRE(op->row_cuts[0] == 0 && op->row_cuts[n1] == nbrow && op->col_cuts[0] == 0 && op->col_cuts[n2] == nbcol,
+            DJETS_ERR_INVALID, "op_create: cuts must start at 0 and end at the block count");
+    for (int r = 0; r < n1; ++r) REQUIRE(op->row_cuts[r] <= op->row_cuts[r + 1], DJETS_ERR_INVALID, "row cuts decrease");
+    for (int c = 0; c < n2; ++c) REQUIRE(op->col_cuts[c] <= op->col_cuts[c + 1], DJETS_ERR_INVALID, "col cuts decrease");
+    op->blocks.resize((size_t)nbrow * nbcol);
+    op->cells.resize((size_t)n1 * n2);
+    for (int c = 0; c < n2; ++c)
+      for (int r = 0; r < n1; ++r) {
+        Cell& cell = op->cell(r, c);
+        cell.r = r;
+        cell.c = c;
+        cell.rank = op->rank_at(r, c);
+      }
+    // element offsets of every block row inside its range part, of every block column inside its domain part
+    op->row_off.resize(nbrow);
+    op->rowpart_len.assign(n1, 0);
+    for (int r = 0; r < n1; ++r) {
+      int64_t o = 0;
+      for (int64_t i = op->row_cuts[r]; i < op->row_cuts[r + 1]; ++i) {
+        op->row_off[i] = o;
+        o += op->row_len[i];
+      }
+      op->rowpart_len[r] = o;
+    }
+    op->col_off.resize(nbcol);
+    const int ndp = op->ndom_parts();
+    const std::vector<int64_t>& dcuts = op->isdiag ? op->row_cuts : op->col_cuts;
+    op->colpart_len.assign(ndp, 0);
+    for (int c = 0; c < ndp; ++c) {
+      int64_t o = 0;
+      for (int64_t j = dcuts[c]; j < dcuts[c + 1]; ++j) {
+        op->col_off[j] = o;
+        o += op->col_len[j];
+      }
+      op->colpart_len[c] = o;
+    }
+    *out = op.release();
+  });
+}
+
+static RankCtx* block_owner_ctx(djets_op op, int64_t i, int64_t j, int* rr, int* cc) {
+  REQUIRE(op, DJETS_ERR_INVALID, "null operator");
+  REQUIRE(i >= 0 && i < op->nbrow && j >= 0 && j < op->nbcol, DJETS_ERR_INVALID, "block index outside the operator");
+  const int r = op->row_cell(i), c = op->col_cell(j);
+  if (rr) *rr = r;
+  if (cc) *cc = c;
+  return op->ctx->local(op->rank_at(r, c));
+}
+
+static void release_block(Block& b) {
+  if (b.d) cudaFree(b.d);
+  b = Block();
+}
+
+int32_t djets_op_set_dense(djets_op op, int64_t i, int64_t j, const void* host, int64_t ld) {
+  return guard([&] {
+    RankCtx* rc = block_owner_ctx(op, i, j, nullptr, nullptr);
+    if (!rc) return;
+    REQUIRE(!op->finalized, DJETS_ERR_INVALID, "op_set_dense after the operator was finalised");
+    const int64_t m = op->row_len[i], n = op->col_len[j];
+    REQUIRE(host || m * n == 0, DJETS_ERR_INVALID, "op_set_dense: null payload");
+    REQUIRE(ld >= std::max<int64_t>(m, 1), DJETS_ERR_INVALID, "op_set_dense: leading dimension smaller than the block");
+    use(*rc);
+    Block& b = op->block(i, j);
+    release_block(b);
+    const int es = elem_size(op->dtype);
+    b.kind = DJETS_BLOCK_DENSE;
+    b.ld = round_up(std::max<int64_t>(m, 1), vec_elems(op->dtype));
+    const size_t bytes = (size_t)b.ld * std::max<int64_t>(n, 1) * es;
+    CK(cudaMalloc(&b.d, bytes + 256));
+    if (b.ld != m) CK(cudaMemsetAsync(b.d, 0, bytes + 256, rc->stream));
+    if (m * n > 0)
+      CK(cudaMemcpy2DAsync(b.d, (size_t)b.ld * es, host, (size_t)ld * es, (size_t)m * es, (size_t)n,
+                           cudaMemcpyHostToDevice, rc->stream));
+    CK(cudaStreamSynchronize(rc->stream));
+  });
+}
+
+int32_t djets_op_set_diag(djets_op op, int64_t i, int64_t j, const void* host) {
+  return guard([&] {
+    RankCtx* rc = block_owner_ctx(op, i, j, nullptr, nullptr);
+    REQUIRE(op->row_len[i] == op->col_len[j], DJETS_ERR_MISMATCH, "op_set_diag: diagonal block must be square");
+    if (!rc) return;
+    REQUIRE(!op->finalized, DJETS_ERR_INVALID, "op_set_diag after the operator was finalised");
+    const int64_t n = op->row_len[i];
+    REQUIRE(host || n == 0, DJETS_ERR_INVALID, "op_set_diag: null payload");
+    use(*rc);
+    Block& b = op->block(i, j);
+    release_block(b);
+    const int es = elem_size(op->dtype);
+    b.kind = DJETS_BLOCK_DIAG;
+    b.ld = n;
+    CK(cudaMalloc(&b.d, (size_t)std::max<int64_t>(n, 1) * es + 256));
+    if (n > 0) CK(cudaMemcpyAsync(b.d, host, (size_t)n * es, cudaMemcpyHostToDevice, rc->stream));
+    CK(cudaStreamSynchronize(rc->stream));
+  });
+}
+
+int32_t djets_op_finalize(djets_op op) {
+  return guard([&] {
+    REQUIRE(op, DJETS_ERR_INVALID, "null operator");
+    finalize_op(op);
+  });
+}
+
+int32_t djets_op_destroy(djets_op op) {
+  return guard([&] {
+    if (!op) return;
+    std::lock_guard<std::mutex> lock(op->ctx->mu);
+    for (Cell& c : op->cells) {
+      RankCtx* rc = op->ctx->local(c.rank);
+      if (!rc) continue;
+      cudaSetDevice(rc->device);
+      cudaStreamSynchronize(rc->stream);
+      free_plan(c.fwd);
+      free_plan(c.adj);
+    }
+    for (int64_t i = 0; i < op->nbrow; ++i)
+      for (int64_t j = 0; j < op->nbcol; ++j) {
+        Block& b = op->block(i, j);
+        if (!b.d) continue;
+        RankCtx* rc = op->ctx->local(op->rank_at(op->row_cell(i), op->col_cell(j)));
+        if (rc) cudaSetDevice(rc->device);
+        release_block(b);
+      }
+    delete op;
+  });
+}
+
+int32_t djets_op_new_vec(djets_op op, int32_t which, djets_vec* out) {
+  return guard([&] {
+    REQUIRE(op && out, DJETS_ERR_INVALID, "op_new_vec: null argument");
+    REQUIRE(which == 0 || which == 1, DJETS_ERR_INVALID, "op_new_vec: which is 0 (domain) or 1 (range)");
+    const bool is_range = which == 1;
+    const int np = is_range ? op->n1 : op->ndom_parts();
+    const std::vector<int64_t>& cuts = (is_range || op->isdiag) ? op->row_cuts : op->col_cuts;
+    std::vector<int32_t> ranks(np);
+    std::vector<int64_t> nb(np);
+    for (int p = 0; p < np; ++p) {
+      ranks[p] = (is_range || op->isdiag) ? op->rank_at(p, 0) : op->rank_at(0, p);
+      nb[p] = cuts[p + 1] - cuts[p];
+    }
+    *out = make_vec(op->ctx, op->dtype, np, ranks.data(), nb.data(),
+                    is_range ? op->row_len.data() : op->col_len.data());
+  });
+}
+
+int32_t djets_op_mul(djets_op op, djets_vec y, djets_vec x) {
+  return guard([&] {
+    REQUIRE(op && y && x, DJETS_ERR_INVALID, "op_mul: null argument");
+    apply(op, y, x, false);
+  });
+}
+
+int32_t djets_op_mul_adjoint(djets_op op, djets_vec x, djets_vec y) {
+  return guard([&] {
+    REQUIRE(op && y && x, DJETS_ERR_INVALID, "op_mul_adjoint: null argument");
+    apply(op, x, y, true);
+  });
+}
+
+int32_t djets_op_blockmap(djets_op op, int32_t r, int32_t c, int64_t* row_first, int64_t* row_count,
+                          int64_t* col_first, int64_t* col_count) {
+  return guard([&] {
+    REQUIRE(op && r >= 0 && r < op->n1 && c >= 0 && c < op->n2, DJETS_ERR_INVALID, "blockmap: cell outside the grid");
+    if (row_first) *row_first = op->row_cuts[r];
+    if (row_count) *row_count = op->row_cuts[r + 1] - op->row_cuts[r];
+    if (col_first) *col_first = op->col_cuts[c];
+    if (col_count) *col_count = op->col_cuts[c + 1] - op->col_cuts[c];
+  });
+}
+
+int32_t djets_op_block_owner(djets_op op, int64_t i, int64_t j, int32_t* r, int32_t* c, int32_t* rank) {
+  return guard([&] {
+    int rr = 0, cc = 0;
+    block_owner_ctx(op, i, j, &rr, &cc);
+    if (r) *r = rr;
+    if (c) *c = cc;
+    if (rank) *rank = op->rank_at(rr, cc);
+  });
+}
+
+int32_t djets_op_getblock(djets_op op, int64_t i, int64_t j, int32_t* kind, void* host_dst, int64_t ld) {
+  return guard([&] {
+    RankCtx* rc = block_owner_ctx(op, i, j, nullptr, nullptr);
+    REQUIRE(rc, DJETS_ERR_NOT_LOCAL, "getblock(A,i,j): block is owned by a rank of another process");
+    Block& b = op->block(i, j);
+    if (kind) *kind = b.kind;
+    if (!host_dst || b.kind == DJETS_BLOCK_ZERO) return;
+    use(*rc);
+    const int es = elem_size(op->dtype);
+    const int64_t m = op->row_len[i], n = op->col_len[j];
+    if (b.kind == DJETS_BLOCK_DENSE) {
+      REQUIRE(ld >= std::max<int64_t>(m, 1), DJETS_ERR_INVALID, "op_getblock: leading dimension smaller than the block");
+      if (m * n > 0)
+        CK(cudaMemcpy2DAsync(host_dst, (size_t)ld * es, b.d, (size_t)b.ld * es, (size_t)m * es, (size_t)n,
+                             cudaMemcpyDeviceToHost, rc->stream));
+    } else if (m > 0) {
+      CK(cudaMemcpyAsync(host_dst, b.d, (size_t)m * es, cudaMemcpyDeviceToHost, rc->stream));
+    }
+    CK(cudaStreamSynchronize(rc->stream));
+  });
+}
+
+int32_t djets_op_algorithmic_bytes(djets_op op, int64_t* bytes) {
+  return guard([&] {
+    REQUIRE(op && bytes, DJETS_ERR_INVALID, "null argument");
+    const int es = elem_size(op->dtype);
+    int64_t total = 0;
+    for (int64_t i = 0; i < op->nbrow; ++i)
+      for (int64_t j = 0; j < op->nbcol; ++j) {
+        if (op->isdiag && i != j) continue;
+        const Block& b = op->block(i, j);
+        if (!b.d) continue;  // payloads exist only on the ranks this process drives
+        if (b.kind == DJETS_BLOCK_DENSE) total += op->row_len[i] * op->col_len[j] * es;
+        if (b.kind == DJETS_BLOCK_DIAG) total += op->row_len[i] * es;
+      }
+    for (int r = 0; r < op->n1; ++r)
+      if (op->ctx->local(op->rank_at(r, 0))) total += op->rowpart_len[r] * es;
+    for (int c = 0; c < op->ndom_parts(); ++c)
+      if (op->ctx->local(op->isdiag ? op->rank_at(c, 0) : op->rank_at(0, c))) total += op->colpart_len[c] * es;
+    *bytes = total;
+  });
+}
+
+int32_t djets_op_schedule_info(djets_op op, int32_t adjoint, int64_t* ntiles, int64_t* nitems) {
+  return guard([&] {
+    REQUIRE(op, DJETS_ERR_INVALID, "null operator");
+    finalize_op(op);
+    int64_t t = 0, it = 0;
+    for (Cell& c : op->cells) {
+      if (!op->ctx->local(c.rank)) continue;
+      const DirPlan& p = adjoint ? c.adj : c.fwd;
+      t += p.ntiles;
+      it += p.nitems;
+    }
+    if (ntiles) *ntiles = t;
+    if (nitems) *nitems = it;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,719 @@
+// sm_100a kernels of libdjets_b200: batched block GEMV (forward / adjoint) over a tile table,
+// segmented block-row / block-column sum with fused diagonal blocks, deterministic reductions and
+// streaming elementwise kernels.  Everything here is HBM-bound CUDA-core work: 128-bit streaming
+// loads of the block matrices, the x / y slice of a tile staged in shared memory (1-D TMA bulk copy
+// when 16-byte aligned), warp-shuffle reductions, no tensor cores, no floating-point atomics.
+//
+// Reference arithmetic being replaced (ChevronETC/DistributedJets.jl, src/DistributedJets.jl):
+//   forward  d_i  = sum_j A_ij m_j     src:629-639 (inner loop), src:641-654 (row loop)
+//   adjoint  m_j  = sum_i A_ij' d_i    src:676-686, src:688-701
+//   diagonal d_i  = diag .* m_i        test/runtests.jl:8-12 (JopFoo), dense A*m test/runtests.jl:30-36 (JopBaz)
+//   dot/norm/extrema/mapreduce/mean/var partials  src:189-283; fill!/broadcast src:332-376
+#include "djets_kernels.h"
+
+#include <math.h>
+
+namespace djets {
+
+// ------------------------------------------------------------------------------------------------
+// 128-bit streaming loads of read-only block payloads.  L1 is bypassed (no reuse inside an SM);
+// POLICY 1 additionally tags the lines evict-first in L2 so the small vectors / workspace stay
+// resident while the matrices stream through.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct VecT;
+template <>
+struct VecT<float> {
+  using type = float4;
+  static constexpr int N = 4;
+};
+template <>
+struct VecT<double> {
+  using type = double2;
+  static constexpr int N = 2;
+};
+
+__device__ __forceinline__ uint64_t make_evict_first_policy() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+template <int POLICY>
+__device__ __forceinline__ float4 ld_stream(const float4* p, uint64_t pol) {
+  float4 r;
+  if (POLICY == 1) {
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(p), "l"(pol));
+  } else {
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(p));
+  }
+  return r;
+}
+template <int POLICY>
+__device__ __forceinline__ double2 ld_stream(const double2* p, uint64_t pol) {
+  double2 r;
+  if (POLICY == 1) {
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+        : "=d"(r.x), "=d"(r.y)
+        : "l"(p), "l"(pol));
+  } else {
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  }
+  return r;
+}
+
+__device__ __forceinline__ void fma_vec(float (&acc)[4], const float4& a, float x) {
+  acc[0] = fmaf(a.x, x, acc[0]);
+  acc[1] = fmaf(a.y, x, acc[1]);
+  acc[2] = fmaf(a.z, x, acc[2]);
+  acc[3] = fmaf(a.w, x, acc[3]);
+}
+__device__ __forceinline__ void fma_vec(double (&acc)[2], const double2& a, double x) {
+  acc[0] = fma(a.x, x, acc[0]);
+  acc[1] = fma(a.y, x, acc[1]);
+}
+__device__ __forceinline__ void dot_vec(float& acc, const float4& a, const float4& y) {
+  acc = fmaf(a.x, y.x, acc);
+  acc = fmaf(a.y, y.y, acc);
+  acc = fmaf(a.z, y.z, acc);
+  acc = fmaf(a.w, y.w, acc);
+}
+__device__ __forceinline__ void dot_vec(double& acc, const double2& a, const double2& y) {
+  acc = fma(a.x, y.x, acc);
+  acc = fma(a.y, y.y, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Staging a contiguous slice of a vector into shared memory.  When source and length are 16-byte
+// aligned the copy is one 1-D TMA bulk transfer (cp.async.bulk -> SASS UBLKCP) completing on an
+// mbarrier; otherwise the CTA copies it with plain loads.  `pad_to` elements past `n` are zeroed.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <typename T>
+__device__ __forceinline__ void stage_vector(T* __restrict__ dst, const T* __restrict__ src, int n, int pad_to,
+                                             uint64_t* bar) {
+  const int tid = threadIdx.x;
+  const uint32_t bytes = (uint32_t)n * (uint32_t)sizeof(T);
+  const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0) && bytes >= 512;
+  if (bulk) {
+    const uint32_t b = smem_u32(bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(dst)),
+          "l"(src), "r"(bytes), "r"(b)
+          : "memory");
+    }
+    for (int i = n + tid; i < pad_to; i += blockDim.x) dst[i] = T(0);
+    // all threads wait for the bytes to land (phase 0)
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(b)
+          : "memory");
+    }
+    __syncthreads();
+  } else {
+    for (int i = tid; i < pad_to; i += blockDim.x) dst[i] = (i < n) ? src[i] : T(0);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward dense tiles: partial[r] = sum_c A[r,c] x[c].  A is column-major, so a thread owns VEC
+// consecutive rows (one 128-bit load per column) and walks the columns; the CTA is TX threads wide
+// along the rows and TY = 256/TX column groups deep; the TY partial strips are summed in shared
+// memory in a fixed order.  U independent 128-bit loads are in flight per thread.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int TX, int POLICY>
+__global__ void __launch_bounds__(kThreads) gemv_n_kernel(const DenseTile* __restrict__ tiles,
+                                                          const T* __restrict__ in, T* __restrict__ W,
+                                                          T* __restrict__ out) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  constexpr int TY = kThreads / TX;
+  constexpr int TR = TX * VEC;
+  constexpr int U = 8;
+  __shared__ __align__(128) T xs[kFwdMaxTC];
+  __shared__ __align__(16) T red[(TY > 1) ? TY * TR : 1];
+  __shared__ __align__(8) uint64_t bar;
+
+  const DenseTile t = tiles[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int rows = t.rows, cols = t.cols;
+  stage_vector<T>(xs, in + t.vin, cols, cols, &bar);
+
+  uint64_t pol = 0;
+  if (POLICY == 1) pol = make_evict_first_policy();
+
+  const int tx = tid % TX, ty = tid / TX;
+  const int r0 = tx * VEC;
+  T acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = T(0);
+
+  if (r0 < rows) {
+    const long long ld = t.ld;
+    const T* a = reinterpret_cast<const T*>(t.A) + r0 + (long long)ty * ld;
+    const long long cstep = (long long)TY * ld;
+    int c = ty;
+    for (; c + (U - 1) * TY < cols; c += U * TY) {
+      V v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = ld_stream<POLICY>(reinterpret_cast<const V*>(a + u * cstep), pol);
+#pragma unroll
+      for (int u = 0; u < U; ++u) fma_vec(acc, v[u], xs[c + u * TY]);
+      a += U * cstep;
+    }
+    for (; c < cols; c += TY) {
+      V v = ld_stream<POLICY>(reinterpret_cast<const V*>(a), pol);
+      fma_vec(acc, v, xs[c]);
+      a += cstep;
+    }
+  }
+
+  T* dst = (t.direct ? out : W) + t.wout;
+  if (TY > 1) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) red[ty * TR + r0 + k] = acc[k];
+    __syncthreads();
+    for (int r = tid; r < rows; r += kThreads) {  // rows <= TR
+      T s = red[r];
+#pragma unroll
+      for (int y = 1; y < TY; ++y) s += red[y * TR + r];
+      dst[r] = s;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if (r0 + k < rows) dst[r0 + k] = acc[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adjoint dense tiles: partial[c] = sum_r A[r,c] y[r].  A warp owns kAdjCW columns at a time and
+// streams down them with 128-bit loads (each lane VEC rows, 32 lanes = 512 contiguous bytes per
+// column), RU row chunks unrolled -> kAdjCW*RU independent loads in flight per lane; the y slice is
+// staged once per CTA in shared memory and each 128-bit LDS of y is reused for the kAdjCW columns;
+// the per-lane sums are combined with a shuffle butterfly.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int RU, int POLICY>
+__global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __restrict__ tiles,
+                                                             const T* __restrict__ in, T* __restrict__ W,
+                                                             T* __restrict__ out) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  constexpr int CW = kAdjCW;
+  constexpr int S = 32 * VEC;  // rows one warp covers with one load per lane
+  __shared__ __align__(128) T ys[kAdjMaxTRBytes / sizeof(T)];
+  __shared__ __align__(8) uint64_t bar;
+
+  const DenseTile t = tiles[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rows = t.rows, cols = t.cols;
+  const int rowsv = (rows + VEC - 1) / VEC * VEC;  // pad rows of A are zero; pad y with zeros too
+  stage_vector<T>(ys, in + t.vin, rows, rowsv, &bar);
+
+  uint64_t pol = 0;
+  if (POLICY == 1) pol = make_evict_first_policy();
+
+  const long long ld = t.ld;
+  const T* A = reinterpret_cast<const T*>(t.A);
+  T* dst = (t.direct ? out : W) + t.wout;
+  const int ngroups = (cols + CW - 1) / CW;
+
+  for (int g = warp; g < ngroups; g += kThreads / 32) {
+    const int c0 = g * CW;
+    const T* col[CW];
+#pragma unroll
+    for (int k = 0; k < CW; ++k) col[k] = A + (long long)min(c0 + k, cols - 1) * ld + lane * VEC;
+    T acc[CW];
+#pragma unroll
+    for (int k = 0; k < CW; ++k) acc[k] = T(0);
+
+    int rb = 0;
+    for (; rb + RU * S <= rowsv; rb += RU * S) {
+      V a[RU][CW];
+#pragma unroll
+      for (int u = 0; u < RU; ++u)
+#pragma unroll
+        for (int k = 0; k < CW; ++k)
+          a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(col[k] + rb + u * S), pol);
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
+#pragma unroll
+        for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[u][k], y);
+      }
+    }
+    for (; rb < rowsv; rb += S) {
+      if (rb + lane * VEC < rowsv) {
+        V a[CW];
+#pragma unroll
+        for (int k = 0; k < CW; ++k) a[k] = ld_stream<POLICY>(reinterpret_cast<const V*>(col[k] + rb), pol);
+        const V y = *reinterpret_cast<const V*>(ys + rb + lane * VEC);
+#pragma unroll
+        for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[k], y);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CW; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    T mine = acc[0];
+#pragma unroll
+    for (int k = 1; k < CW; ++k)
+      if (lane == k) mine = acc[k];
+    if (lane < CW && c0 + lane < cols) dst[c0 + lane] = mine;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Segmented sum of the partial planes of one output chunk, with the planes pushed by peer ranks
+// and the diagonal blocks of the block row (column) fused in.  Sums run in a fixed order, in
+// double for Float32 vectors.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) finish_kernel(const FinishItem* __restrict__ items,
+                                                          const DiagTerm* __restrict__ diags,
+                                                          const T* __restrict__ in, const T* __restrict__ W,
+                                                          const T* __restrict__ R, T* __restrict__ out) {
+  const FinishItem it = items[blockIdx.x];
+  for (int e = threadIdx.x; e < it.len; e += kThreads) {
+    double s = 0.0;
+    const T* w = W + it.w0 + e;
+    int p = 0;
+    for (; p + 4 <= it.nplanes; p += 4) {
+      const T a0 = w[0], a1 = w[it.wstride], a2 = w[2 * it.wstride], a3 = w[3 * it.wstride];
+      s += (double)a0;
+      s += (double)a1;
+      s += (double)a2;
+      s += (double)a3;
+      w += 4 * it.wstride;
+    }
+    for (; p < it.nplanes; ++p) {
+      s += (double)w[0];
+      w += it.wstride;
+    }
+    for (int q = 0; q < it.nremote; ++q) s += (double)R[it.r0 + q * it.rstride + e];
+    for (int d = it.diag_begin; d < it.diag_end; ++d) {
+      const T* dd = reinterpret_cast<const T*>(diags[d].d);
+      s += (double)(dd[e] * in[diags[d].vin + e]);
+    }
+    out[it.out + e] = (T)s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reductions (dot, norms, extrema, sums): stage 1 = one partial per CTA, stage 2 = one CTA folds
+// the partials.  Grid shape depends only on n, the combine order is fixed -> deterministic.
+// ------------------------------------------------------------------------------------------------
+enum { K_SUM = 0, K_MIN, K_MAX, K_ABSSUM, K_ABSMAX, K_ABSMIN, K_SUMSQ, K_NNZ, K_SUMPOW, K_SUMSQ_SHIFT, K_DOT };
+
+template <int KIND>
+__device__ __forceinline__ double red_identity() {
+  if (KIND == K_MIN || KIND == K_ABSMIN) return INFINITY;
+  if (KIND == K_MAX) return -INFINITY;
+  if (KIND == K_ABSMAX) return 0.0;
+  return 0.0;
+}
+template <int KIND>
+__device__ __forceinline__ double red_combine(double a, double b) {
+  if (KIND == K_MIN || KIND == K_ABSMIN) return fmin(a, b);
+  if (KIND == K_MAX || KIND == K_ABSMAX) return fmax(a, b);
+  return a + b;
+}
+template <int KIND>
+__device__ __forceinline__ double red_map(double x, double y, double param) {
+  switch (KIND) {
+    case K_SUM:
+    case K_MIN:
+    case K_MAX: return x;
+    case K_ABSSUM:
+    case K_ABSMAX:
+    case K_ABSMIN: return fabs(x);
+    case K_SUMSQ: return x * x;
+    case K_NNZ: return x != 0.0 ? 1.0 : 0.0;
+    case K_SUMPOW: return pow(fabs(x), param);
+    case K_SUMSQ_SHIFT: return (x - param) * (x - param);
+    case K_DOT: return x * y;
+  }
+  return 0.0;
+}
+
+template <int KIND>
+__device__ __forceinline__ double block_fold(double v) {
+  __shared__ double sh[kThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = red_combine<KIND>(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = red_identity<KIND>();
+  if (threadIdx.x == 0) {
+    r = sh[0];
+    for (int w = 1; w < kThreads / 32; ++w) r = red_combine<KIND>(r, sh[w]);
+  }
+  return r;
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kThreads) reduce_stage1(const T* __restrict__ x, const T* __restrict__ y,
+                                                          long long n, double param,
+                                                          double* __restrict__ partials) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  constexpr int U = 4;
+  const long long nvec = n / VEC;
+  const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long gstride = (long long)gridDim.x * kThreads;
+  double acc = red_identity<KIND>();
+  const V* xv = reinterpret_cast<const V*>(x);
+  const V* yv = reinterpret_cast<const V*>(y);
+  long long i = gtid;
+  for (; i + (U - 1) * gstride < nvec; i += U * gstride) {
+    V a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      a[u] = ld_stream<0>(xv + i + u * gstride, 0);
+      if (KIND == K_DOT) b[u] = ld_stream<0>(yv + i + u * gstride, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const T* ae = reinterpret_cast<const T*>(&a[u]);
+      const T* be = reinterpret_cast<const T*>(&b[u]);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        acc = red_combine<KIND>(acc, red_map<KIND>((double)ae[k], KIND == K_DOT ? (double)be[k] : 0.0, param));
+    }
+  }
+  for (; i < nvec; i += gstride) {
+    V a = ld_stream<0>(xv + i, 0), b;
+    if (KIND == K_DOT) b = ld_stream<0>(yv + i, 0);
+    const T* ae = reinterpret_cast<const T*>(&a);
+    const T* be = reinterpret_cast<const T*>(&b);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      acc = red_combine<KIND>(acc, red_map<KIND>((double)ae[k], KIND == K_DOT ? (double)be[k] : 0.0, param));
+  }
+  for (long long j = nvec * VEC + gtid; j < n; j += gstride)
+    acc = red_combine<KIND>(acc, red_map<KIND>((double)x[j], KIND == K_DOT ? (double)y[j] : 0.0, param));
+  const double r = block_fold<KIND>(acc);
+  if (threadIdx.x == 0) partials[blockIdx.x] = r;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) reduce_stage2(const double* __restrict__ partials, int np,
+                                                          double* __restrict__ result) {
+  double acc = red_identity<KIND>();
+  for (int i = threadIdx.x; i < np; i += kThreads) acc = red_combine<KIND>(acc, partials[i]);
+  const double r = block_fold<KIND>(acc);
+  if (threadIdx.x == 0) result[0] = r;
+}
+
+int reduce_max_ctas() { return 148 * 8; }
+
+template <typename T, int KIND>
+static cudaError_t launch_reduce_k(const void* x, const void* y, long long n, double param, double* partials,
+                                   double* result, cudaStream_t stream) {
+  constexpr int VEC = VecT<T>::N;
+  long long want = (n / VEC + (long long)kThreads * 4 - 1) / ((long long)kThreads * 4);
+  int grid = (int)(want < 1 ? 1 : (want > reduce_max_ctas() ? reduce_max_ctas() : want));
+  reduce_stage1<T, KIND><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(y),
+                                                        n, param, partials);
+  reduce_stage2<KIND><<<1, kThreads, 0, stream>>>(partials, grid, result);
+  return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_reduce_t(int kind, const void* x, const void* y, long long n, double param,
+                                   double* partials, double* result, cudaStream_t stream) {
+  switch (kind) {
+    case 0: return launch_reduce_k<T, K_SUM>(x, y, n, param, partials, result, stream);
+    case 1: return launch_reduce_k<T, K_MIN>(x, y, n, param, partials, result, stream);
+    case 2: return launch_reduce_k<T, K_MAX>(x, y, n, param, partials, result, stream);
+    case 3: return launch_reduce_k<T, K_ABSSUM>(x, y, n, param, partials, result, stream);
+    case 4: return launch_reduce_k<T, K_ABSMAX>(x, y, n, param, partials, result, stream);
+    case 5: return launch_reduce_k<T, K_ABSMIN>(x, y, n, param, partials, result, stream);
+    case 6: return launch_reduce_k<T, K_SUMSQ>(x, y, n, param, partials, result, stream);
+    case 7: return launch_reduce_k<T, K_NNZ>(x, y, n, param, partials, result, stream);
+    case 8: return launch_reduce_k<T, K_SUMPOW>(x, y, n, param, partials, result, stream);
+    case 9: return launch_reduce_k<T, K_SUMSQ_SHIFT>(x, y, n, param, partials, result, stream);
+    case RED_DOT: return launch_reduce_k<T, K_DOT>(x, y, n, param, partials, result, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_reduce(int dtype, int kind, const void* x, const void* y, long long n, double param,
+                          double* partials, double* result, cudaStream_t stream) {
+  return dtype == 0 ? launch_reduce_t<float>(kind, x, y, n, param, partials, result, stream)
+                    : launch_reduce_t<double>(kind, x, y, n, param, partials, result, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming elementwise kernels.  Products and sums use the non-contracting intrinsics so that
+// `dest .= c0*x0 .+ c1*x1 ...` rounds exactly like the reference's unfused broadcast (src:363-368).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+struct LincombDev {
+  const void* x[4];
+  double coef[4];
+  int xdtype[4];
+  int nterms;
+  int unit0;  // coef[0] == 1 and nterms == 1: plain copy / convert
+};
+
+template <typename ACC>
+__device__ __forceinline__ ACC load_as(const void* p, int dtype, long long i) {
+  return dtype == 0 ? (ACC) reinterpret_cast<const float*>(p)[i] : (ACC) reinterpret_cast<const double*>(p)[i];
+}
+
+// generic path: any mix of operand element types
+template <typename TD, typename ACC>
+__global__ void __launch_bounds__(kThreads) lincomb_generic(TD* __restrict__ dest, LincombDev a, long long n) {
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    ACC s;
+    if (a.unit0) {
+      s = load_as<ACC>(a.x[0], a.xdtype[0], i);
+    } else {
+      s = mul_rn((ACC)a.coef[0], load_as<ACC>(a.x[0], a.xdtype[0], i));
+      for (int k = 1; k < a.nterms; ++k)
+        s = add_rn(s, mul_rn((ACC)a.coef[k], load_as<ACC>(a.x[k], a.xdtype[k], i)));
+    }
+    dest[i] = (TD)s;
+  }
+}
+
+// fast path: all operands and dest share one element type; 128-bit loads / stores
+template <typename T, typename ACC, int NT>
+__global__ void __launch_bounds__(kThreads) lincomb_vec(T* __restrict__ dest, LincombDev a, long long n) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  const long long nvec = n / VEC;
+  const long long stride = (long long)gridDim.x * kThreads;
+  const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  ACC c[NT];
+#pragma unroll
+  for (int k = 0; k < NT; ++k) c[k] = (ACC)a.coef[k];
+  for (long long i = gtid; i < nvec; i += stride) {
+    V v[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) v[k] = reinterpret_cast<const V*>(a.x[k])[i];
+    V o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      ACC s = mul_rn(c[0], (ACC) reinterpret_cast<const T*>(&v[0])[e]);
+#pragma unroll
+      for (int k = 1; k < NT; ++k) s = add_rn(s, mul_rn(c[k], (ACC) reinterpret_cast<const T*>(&v[k])[e]));
+      oe[e] = (T)s;
+    }
+    reinterpret_cast<V*>(dest)[i] = o;
+  }
+  for (long long j = nvec * VEC + gtid; j < n; j += stride) {
+    ACC s = mul_rn(c[0], (ACC) reinterpret_cast<const T*>(a.x[0])[j]);
+#pragma unroll
+    for (int k = 1; k < NT; ++k) s = add_rn(s, mul_rn(c[k], (ACC) reinterpret_cast<const T*>(a.x[k])[j]));
+    dest[j] = (T)s;
+  }
+}
+
+static int stream_grid(long long nvec) {
+  long long want = (nvec + kThreads - 1) / kThreads;
+  const long long cap = 148LL * 16;
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+template <typename T, typename ACC>
+static void launch_lincomb_vec(T* dest, const LincombDev& d, long long n, cudaStream_t stream) {
+  const int grid = stream_grid(n / VecT<T>::N);
+  switch (d.nterms) {
+    case 1: lincomb_vec<T, ACC, 1><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
+    case 2: lincomb_vec<T, ACC, 2><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
+    case 3: lincomb_vec<T, ACC, 3><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
+    default: lincomb_vec<T, ACC, 4><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
+  }
+}
+
+cudaError_t launch_lincomb(int ddtype, void* dest, const LincombArgs& a, long long n, int wide, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  LincombDev d;
+  bool same = true;
+  for (int k = 0; k < 4; ++k) {
+    d.x[k] = k < a.nterms ? a.x[k] : nullptr;
+    d.coef[k] = k < a.nterms ? a.coef[k] : 0.0;
+    d.xdtype[k] = k < a.nterms ? a.xdtype[k] : ddtype;
+    if (k < a.nterms && a.xdtype[k] != ddtype) same = false;
+  }
+  d.nterms = a.nterms;
+  d.unit0 = (a.nterms == 1 && a.coef[0] == 1.0) ? 1 : 0;
+  if (same && !d.unit0) {
+    if (ddtype == 1)
+      launch_lincomb_vec<double, double>(reinterpret_cast<double*>(dest), d, n, stream);
+    else if (wide)
+      launch_lincomb_vec<float, double>(reinterpret_cast<float*>(dest), d, n, stream);
+    else
+      launch_lincomb_vec<float, float>(reinterpret_cast<float*>(dest), d, n, stream);
+  } else {
+    const int grid = stream_grid(n);
+    if (ddtype == 1)
+      lincomb_generic<double, double><<<grid, kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), d, n);
+    else if (wide || !same)
+      lincomb_generic<float, double><<<grid, kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), d, n);
+    else
+      lincomb_generic<float, float><<<grid, kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), d, n);
+  }
+  return cudaGetLastError();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) fill_kernel(T* __restrict__ dest, T a, long long n) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  const long long nvec = n / VEC;
+  const long long stride = (long long)gridDim.x * kThreads;
+  const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  V v;
+  T* ve = reinterpret_cast<T*>(&v);
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) ve[e] = a;
+  for (long long i = gtid; i < nvec; i += stride) reinterpret_cast<V*>(dest)[i] = v;
+  for (long long j = nvec * VEC + gtid; j < n; j += stride) dest[j] = a;
+}
+
+cudaError_t launch_fill(int dtype, void* dest, double a, long long n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (dtype == 0)
+    fill_kernel<float><<<stream_grid(n / 4), kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), (float)a, n);
+  else
+    fill_kernel<double><<<stream_grid(n / 2), kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), a, n);
+  return cudaGetLastError();
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(kThreads) binary_kernel(T* __restrict__ dest, const T* __restrict__ a,
+                                                          const T* __restrict__ b, long long n) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  const long long nvec = n / VEC;
+  const long long stride = (long long)gridDim.x * kThreads;
+  const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  for (long long i = gtid; i < nvec; i += stride) {
+    V va = reinterpret_cast<const V*>(a)[i], vb = reinterpret_cast<const V*>(b)[i], o;
+    const T* ae = reinterpret_cast<const T*>(&va);
+    const T* be = reinterpret_cast<const T*>(&vb);
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) oe[e] = OP == 0 ? mul_rn(ae[e], be[e]) : ae[e] / be[e];
+    reinterpret_cast<V*>(dest)[i] = o;
+  }
+  for (long long j = nvec * VEC + gtid; j < n; j += stride) dest[j] = OP == 0 ? mul_rn(a[j], b[j]) : a[j] / b[j];
+}
+
+cudaError_t launch_binary(int dtype, int op, void* dest, const void* a, const void* b, long long n,
+                          cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (op != 0 && op != 1) return cudaErrorInvalidValue;
+#define DJ_BIN(T, OP)                                                                                              \
+  binary_kernel<T, OP><<<stream_grid(n / VecT<T>::N), kThreads, 0, stream>>>(                                      \
+      reinterpret_cast<T*>(dest), reinterpret_cast<const T*>(a), reinterpret_cast<const T*>(b), n)
+  if (dtype == 0) {
+    if (op == 0) DJ_BIN(float, 0); else DJ_BIN(float, 1);
+  } else {
+    if (op == 0) DJ_BIN(double, 0); else DJ_BIN(double, 1);
+  }
+#undef DJ_BIN
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch dispatch for the tile kernels
+// ------------------------------------------------------------------------------------------------
+template <typename T, int POLICY>
+static cudaError_t launch_gemv_n_t(int fwd_tx, const DenseTile* tiles, int ntiles, const void* in, void* W, void* out,
+                                   cudaStream_t stream) {
+  const T* i = reinterpret_cast<const T*>(in);
+  T* w = reinterpret_cast<T*>(W);
+  T* o = reinterpret_cast<T*>(out);
+  switch (fwd_tx) {
+    case 32: gemv_n_kernel<T, 32, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
+    case 64: gemv_n_kernel<T, 64, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
+    case 128: gemv_n_kernel<T, 128, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
+    case 256: gemv_n_kernel<T, 256, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
+                          void* W, void* out, cudaStream_t stream) {
+  if (ntiles <= 0) return cudaSuccess;
+  if (dtype == 0)
+    return ld_policy ? launch_gemv_n_t<float, 1>(fwd_tx, tiles, ntiles, in, W, out, stream)
+                     : launch_gemv_n_t<float, 0>(fwd_tx, tiles, ntiles, in, W, out, stream);
+  return ld_policy ? launch_gemv_n_t<double, 1>(fwd_tx, tiles, ntiles, in, W, out, stream)
+                   : launch_gemv_n_t<double, 0>(fwd_tx, tiles, ntiles, in, W, out, stream);
+}
+
+template <typename T, int POLICY>
+static cudaError_t launch_gemv_t_t(int adj_ru, const DenseTile* tiles, int ntiles, const void* in, void* W, void* out,
+                                   cudaStream_t stream) {
+  const T* i = reinterpret_cast<const T*>(in);
+  T* w = reinterpret_cast<T*>(W);
+  T* o = reinterpret_cast<T*>(out);
+  switch (adj_ru) {
+    case 1: gemv_t_kernel<T, 1, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
+    case 2: gemv_t_kernel<T, 2, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
+    case 4: gemv_t_kernel<T, 4, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemv_t(int dtype, int adj_ru, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
+                          void* W, void* out, cudaStream_t stream) {
+  if (ntiles <= 0) return cudaSuccess;
+  if (dtype == 0)
+    return ld_policy ? launch_gemv_t_t<float, 1>(adj_ru, tiles, ntiles, in, W, out, stream)
+                     : launch_gemv_t_t<float, 0>(adj_ru, tiles, ntiles, in, W, out, stream);
+  return ld_policy ? launch_gemv_t_t<double, 1>(adj_ru, tiles, ntiles, in, W, out, stream)
+                   : launch_gemv_t_t<double, 0>(adj_ru, tiles, ntiles, in, W, out, stream);
+}
+
+cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,
+                          const void* W, const void* R, void* out, cudaStream_t stream) {
+  if (nitems <= 0) return cudaSuccess;
+  if (dtype == 0)
+    finish_kernel<float><<<nitems, kThreads, 0, stream>>>(items, diags, reinterpret_cast<const float*>(in),
+                                                          reinterpret_cast<const float*>(W),
+                                                          reinterpret_cast<const float*>(R),
+                                                          reinterpret_cast<float*>(out));
+  else
+    finish_kernel<double><<<nitems, kThreads, 0, stream>>>(items, diags, reinterpret_cast<const double*>(in),
+                                                           reinterpret_cast<const double*>(W),
+                                                           reinterpret_cast<const double*>(R),
+                                                           reinterpret_cast<double*>(out));
+  return cudaGetLastError();
+}
+
+}  // namespace djets

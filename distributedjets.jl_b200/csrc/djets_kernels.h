@@ -1,0 +1,81 @@
+// Device-side work descriptors and launcher prototypes shared by the host scheduler
+// (djets_api.cu) and the sm_100a kernels (djets_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace djets {
+
+// One dense tile of one block: a rows x cols window of a column-major block.
+//   forward (gemv_n):  partial[r] = sum_c A[r,c] * in[vin + c]      r < rows
+//   adjoint (gemv_t):  partial[c] = sum_r A[r,c] * in[vin + r]      c < cols
+// The partial goes to workspace plane `wout` or, when this tile is the only contribution to its
+// output strip (`direct`), straight into the output vector at element offset `wout`.
+struct DenseTile {
+  const void* A;      // tile origin (16-byte aligned: row0 % VEC == 0, ld % VEC == 0)
+  long long ld;       // leading dimension in elements (padded to a 16-byte multiple, pad rows are 0)
+  long long vin;      // element offset of the tile's slice of the input vector
+  long long wout;     // element offset into the workspace (or the output vector when direct)
+  int rows, cols;     // tile extents
+  int direct;
+  int pad_;
+};
+
+// One term of a diagonal block inside a finish item: out[e] += d[e] * in[vin + e].
+struct DiagTerm {
+  const void* d;      // diagonal, already offset to the item's first row
+  long long vin;      // element offset into the input vector, already offset likewise
+};
+
+// Segmented sum of one output chunk: out[out+e] = sum_p W[w0 + p*wstride + e]
+//                                               + sum_q R[r0 + q*rstride + e]     (planes received from peers)
+//                                               + sum_t d_t[e] * in[vin_t + e]    (diagonal blocks)
+struct FinishItem {
+  long long out;
+  long long w0, wstride;
+  long long r0, rstride;
+  int nplanes, nremote;
+  int diag_begin, diag_end;
+  int len;
+  int pad_;
+};
+
+// ---- launchers (all asynchronous on `stream`) ------------------------------------------------
+// dtype: 0 = float, 1 = double.  fwd_tx in {32,64,128,256}; adj_ru in {2,4,8}.
+cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
+                          void* W, void* out, cudaStream_t stream);
+cudaError_t launch_gemv_t(int dtype, int adj_ru, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
+                          void* W, void* out, cudaStream_t stream);
+cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,
+                          const void* W, const void* R, void* out, cudaStream_t stream);
+
+// Elementwise: dest[i] = sum_k coef[k] * x_k[i]; dtypes per operand; compute in double if wide.
+struct LincombArgs {
+  const void* x[4];
+  double coef[4];
+  int xdtype[4];
+  int nterms;
+};
+cudaError_t launch_lincomb(int ddtype, void* dest, const LincombArgs& a, long long n, int wide, cudaStream_t stream);
+cudaError_t launch_fill(int dtype, void* dest, double a, long long n, cudaStream_t stream);
+cudaError_t launch_binary(int dtype, int op, void* dest, const void* a, const void* b, long long n,
+                          cudaStream_t stream);
+
+// Reductions: two deterministic stages.  `partials` holds at least reduce_max_ctas() doubles;
+// `result` is one double (device).  kind: DJETS_RED_* or RED_DOT (100).
+enum { RED_DOT = 100 };
+int reduce_max_ctas();
+cudaError_t launch_reduce(int dtype, int kind, const void* x, const void* y, long long n, double param,
+                          double* partials, double* result, cudaStream_t stream);
+
+// geometry helpers shared with the scheduler
+inline int vec_elems(int dtype) { return dtype == 0 ? 4 : 2; }
+inline int elem_size(int dtype) { return dtype == 0 ? 4 : 8; }
+constexpr int kThreads = 256;
+constexpr int kFwdMaxTC = 1024;   // columns of x staged in shared memory by a forward tile
+constexpr int kAdjMaxTRBytes = 32768;  // bytes of y staged in shared memory by an adjoint tile
+constexpr int kAdjCW = 4;         // columns a warp handles at once in the adjoint kernel
+constexpr int kFinishChunk = 2048;
+inline int adj_max_rows(int dtype) { return kAdjMaxTRBytes / elem_size(dtype); }
+
+}  // namespace djets

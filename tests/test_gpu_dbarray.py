@@ -1,0 +1,203 @@
+"""GPU port of the reference's DBArray / JetDSpace testsets (test/runtests.jl:55-363), through the
+C ABI, with the oracle as the checker.  Index metadata, getblock / setblock! / collect are bit-exact
+(SURVEY.md 8a rows a1-a12)."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PI = math.pi
+
+
+def diag_op(dj, ctx, shape, nblk, pids, dist=None):
+    """``@blockop DArray(I->[JopFoo(rand(shape)) ...], (nblk,1), pids[, dist])`` (test:8-12)."""
+    rng = np.random.default_rng(nblk)
+    return dj.JopDBlock(lambda i, j: dj.JopDiagonal(rng.random(shape)), dims=(nblk, 1), pids=pids, dist=dist, ctx=ctx)
+
+
+def test_jetdspace_construction_1d_2d(dj, ctx4):
+    """test:65-93."""
+    A = diag_op(dj, ctx4, (2,), 2, [0, 1])
+    R = A.range()
+    assert R.size() == (4,) and len(R) == 4 and R.eltype == np.float64
+    assert R.indices == [range(1, 3), range(3, 5)]
+    assert R.procs() == [0, 1] and R.nprocs() == 2 and A.nprocs() == 2 and R.nblocks() == 2
+    A = diag_op(dj, ctx4, (2, 3), 2, [0, 1])
+    R = A.range()
+    assert R.size() == (12,) and R.indices == [range(1, 7), range(7, 13)] and R.nblocks() == 2
+    assert R == dj.rand(R).space()                                   # test:95-103
+
+
+@pytest.mark.parametrize("shape,nblk", [((2,), 2), ((2, 3), 4)])
+def test_jetdspace_operations(dj, ctx4, shape, nblk):
+    """test:105-170: zeros/ones/Array/rand layout, similar, local indices, pi round trips."""
+    A = diag_op(dj, ctx4, shape, nblk, [0, 1])
+    R = A.range()
+    n = nblk * int(np.prod(shape))
+    assert np.array_equal(dj.zeros(R).to_array(), np.zeros(n))
+    assert np.array_equal(dj.ones(R).to_array(), np.ones(n))
+    d = dj.Array(R)
+    assert d.size() == (n,)
+    assert d.indices == [range(1, n // 2 + 1), range(n // 2 + 1, n + 1)]
+    assert d.blockmap() == [range(1, nblk // 2 + 1), range(nblk // 2 + 1, nblk + 1)]
+    y = d.similar()
+    assert isinstance(y, dj.DBArray) and y.dtype == np.float64
+    z = d.similar(np.float32)
+    assert isinstance(z, dj.DBArray) and z.dtype == np.float32
+    assert isinstance(d.similar(np.float32, len(y)), dj.DBArray)
+    assert isinstance(d.similar(np.float32, (len(y),)), dj.DBArray)
+    assert isinstance(d.similar(np.float32, len(y) + 1), np.ndarray)      # src:186
+    assert R.localindices(0) == range(1, n // 2 + 1) and R.localindices(1) == range(n // 2 + 1, n + 1)
+    assert R.localblockindices(0) == range(1, nblk // 2 + 1)
+    assert R.localblockindices(1) == range(nblk // 2 + 1, nblk + 1)
+    x = dj.getblock(d, 1)
+    assert x.shape == shape
+    x[...] = PI
+    dj.setblock(d, 1, x)
+    m = int(np.prod(shape))
+    assert [d[i] for i in range(1, m + 1)] == [PI] * m                   # bit-exact
+    x[...] = 0
+    assert np.array_equal(dj.getblock_into(d, 1, x), np.full(shape, PI))
+
+
+def test_dbarray_construction_known_answers(dj, ctx4):
+    """test:172-221: f(i) = i*pi*ones(2 or 3), 7 blocks on 4 workers."""
+    foo = lambda i: i * PI * np.ones(2 if i % 2 == 0 else 3)
+    A = dj.DBArray(foo, (7,), dj.workers(), [4])
+    B = dj.DBArray(foo, (7,), dj.workers())
+    Cc = dj.DBArray(foo, (7,))
+    D = dj.DBArray(foo, dj.blockmap(A))
+    E = dj.DBArray(foo, [range(1, 2), range(2, 3), range(3, 4), range(4, 8)])
+    assert A.blkindices == [range(1, 3), range(3, 5), range(5, 7), range(7, 8)]
+    assert A.blkindices == B.blkindices == Cc.blkindices == D.blkindices != E.blkindices
+    assert A.indices == B.indices == Cc.indices == D.indices != E.indices
+    assert A.indices == [range(1, 6), range(6, 11), range(11, 16), range(16, 19)]
+    assert len(A) == 18
+    for v in (B, Cc, D, E):
+        assert np.array_equal(A.to_array(), v.to_array())
+    for i in range(1, 19):
+        assert A[i] == E[i]
+    for ib in range(1, 8):
+        m = 2 if ib % 2 == 0 else 3
+        for v in (A, B, Cc, D, E):
+            b = dj.getblock(v, ib)
+            assert b.shape == (m,) and np.array_equal(b, ib * PI * np.ones(m))
+    with pytest.raises(IndexError):
+        A[19]
+    with pytest.raises(IndexError):
+        dj.getblock(A, 8)
+
+
+def test_collect_rebases_blocks(dj, O, ctx4):
+    """collect (src:310-323): blocks in worker order, each in its own shape; bit-exact."""
+    rng = np.random.default_rng(1)
+    shapes = [(2, 3), (4,), (1, 5), (3, 3), (7,)]
+    data = {i + 1: np.asfortranarray(rng.random(s)) for i, s in enumerate(shapes)}
+    x = dj.DBArray(lambda i: data[i], [range(1, 3), range(3, 4), range(4, 6)], [0, 1, 2])
+    ox = O.ODBArray.from_function(lambda i: data[i], [range(1, 3), range(3, 4), range(4, 6)], [0, 1, 2])
+    got = dj.collect(x)
+    want = ox.collect()
+    assert len(got) == 5
+    for g, w in zip(got, want.arrays):
+        assert g.shape == w.shape and np.array_equal(g, w)
+    assert np.array_equal(x.to_array(), ox.to_array())
+    assert x.indices == ox.indices and x.blkindices == ox.blkindices
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_reductions_match_oracle(dj, O, ctx4, dtype):
+    """test:223-304: dot, norm(p), mapreduce(abs,+), maximum/minimum, extrema, mean, var."""
+    rng = np.random.default_rng(42)
+    shapes = [(2, 3)] * 4 + [(1001,), (37, 5)]
+    blkidx = [range(1, 3), range(3, 5), range(5, 6), range(6, 7)]
+    data = {i + 1: np.asfortranarray((rng.random(s) - 0.3).astype(dtype)) for i, s in enumerate(shapes)}
+    data2 = {i + 1: np.asfortranarray(rng.random(s).astype(dtype)) for i, s in enumerate(shapes)}
+    x, y = dj.DBArray(lambda i: data[i], blkidx, [0, 1, 2, 3]), dj.DBArray(lambda i: data2[i], blkidx, [0, 1, 2, 3])
+    ox = O.ODBArray.from_function(lambda i: data[i], blkidx, [0, 1, 2, 3])
+    oy = O.ODBArray.from_function(lambda i: data2[i], blkidx, [0, 1, 2, 3])
+    rt = 1e-12 if dtype == np.float64 else 2e-6
+    assert type(x.dot(y)) == dtype
+    np.testing.assert_allclose(x.dot(y), ox.dot(oy), rtol=rt)
+    np.testing.assert_allclose(float(x.dot(y)), float(np.dot(ox.to_array().astype(np.longdouble),
+                                                             oy.to_array().astype(np.longdouble))), rtol=rt)
+    for p in (2, 0, 1, math.inf, -math.inf, 0.5, 3):
+        np.testing.assert_allclose(x.norm(p), ox.norm(p), rtol=rt * 10, err_msg=f"norm p={p}")
+        assert type(x.norm(p)) == dtype                                   # test:237-239
+    np.testing.assert_allclose(x.mapreduce(abs, "+"), ox.mapreduce(np.abs, np.add), rtol=rt)
+    assert x.maximum() == ox.extrema()[1] and x.minimum() == ox.extrema()[0]        # exact
+    assert x.extrema() == ox.extrema()
+    assert x.maximum(abs) == np.abs(ox.to_array()).max() and x.minimum(abs) == np.abs(ox.to_array()).min()
+    np.testing.assert_allclose(x.mean(), ox.mean(), rtol=rt * 10)
+    np.testing.assert_allclose(x.var(), ox.var(), rtol=rt * 100)
+    np.testing.assert_allclose(x.var(mean=100.0), ox.var(mean=100.0), rtol=rt * 10)
+    np.testing.assert_allclose(x.var(corrected=False), ox.var(corrected=False), rtol=rt * 100)
+    parts = x.reduce_parts(6)                                             # the reference's z[ipid] vector
+    want = [float(np.sum(p.flat().astype(np.float64) ** 2)) for p in ox.parts]
+    np.testing.assert_allclose(parts, want, rtol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(2,), (2, 3)])
+def test_broadcasting(dj, ctx4, shape):
+    """test:306-363: 7 blocks on 2 workers with dist [2,1] (4 + 3 blocks)."""
+    A = diag_op(dj, ctx4, shape, 7, [0, 1], [2, 1])
+    R = A.range()
+    assert R.blkindices == [range(1, 5), range(5, 8)]
+    d1, d2, d3, d = dj.ones(R), dj.ones(R), dj.ones(R), dj.ones(R)
+    a1, a2, a3 = np.random.default_rng(9).random(3)
+    d = a3 * d3                                                           # allocates like Julia's similar(bc)
+    assert np.array_equal(d.to_array(), np.full(len(R), a3))
+    d.assign(dj.dotted(a1, d1) + dj.dotted(a2, d2) + dj.dotted(a3, d3))   # d .= a1.*d1 .+ a2.*d2 .+ a3.*d3
+    want = (a1 * 1.0 + a2 * 1.0) + a3 * 1.0
+    assert np.array_equal(d.to_array(), np.full(len(R), want))            # unfused rounding, bit-exact
+    d.assign(a1 * d1 + a2 * d2 + a3 * d3)                                 # test:322 as written (temporaries)
+    assert np.array_equal(d.to_array(), np.full(len(R), want))
+    d1.assign(3.14)
+    assert all(d1[i] == 3.14 for i in range(1, len(d1) + 1))
+    # element-type conversion `_d .= d` (test:237-238)
+    x = dj.rand(R, np.random.default_rng(4))
+    x32 = x.similar(np.float32).assign(x)
+    assert np.array_equal(x32.to_array(), x.to_array().astype(np.float32))
+    # elementwise product / quotient
+    y = dj.rand(R, np.random.default_rng(5))
+    assert np.array_equal(x.similar().mul_(x, y).to_array(), x.to_array() * y.to_array())
+    assert np.array_equal(x.similar().div_(x, y).to_array(), x.to_array() / y.to_array())
+    with pytest.raises(dj.DimensionMismatch):
+        d.assign(dj.DBArray(lambda i: np.ones(3), (2,), [0, 1]))
+
+
+def test_lincomb_random_bit_exact_vs_numpy(dj, ctx4):
+    rng = np.random.default_rng(77)
+    for dtype in (np.float64, np.float32):
+        n = [1003, 517, 64, 2049]
+        xs = [dj.DBArray(lambda i: rng.random(n[i - 1]).astype(dtype), (4,), [0, 1, 2, 3]) for _ in range(4)]
+        c = rng.random(4)
+        ref = [v.to_array() for v in xs]
+        out = xs[0].similar()
+        for k in range(1, 5):
+            out.lincomb_(c[:k], xs[:k], wide=True)
+            acc = c[0] * ref[0].astype(np.float64)
+            for t in range(1, k):
+                acc = acc + c[t] * ref[t].astype(np.float64)
+            assert np.array_equal(out.to_array(), acc.astype(dtype)), (dtype, k)
+        if dtype == np.float32:
+            out.lincomb_(c[:3], xs[:3], wide=False)
+            c32 = c.astype(np.float32)
+            acc = (c32[0] * ref[0] + c32[1] * ref[1]) + c32[2] * ref[2]
+            assert np.array_equal(out.to_array(), acc)
+
+
+def test_large_vector_reductions_and_axpy(dj, ctx4):
+    """2^24 elements in 16 blocks over 4 ranks: checksum-style properties at size."""
+    nb, bl = 16, 1 << 20
+    x = dj.DBArray(lambda i: np.full(bl, float(i)), (nb,), [0, 1, 2, 3])
+    y = x.similar().fill(2.0)
+    s = sum(range(1, nb + 1))
+    assert x.sum() == s * bl
+    assert x.dot(y) == 2.0 * s * bl
+    assert x.norm(math.inf) == nb and x.norm(-math.inf) == 1.0 and x.norm(0) == nb * bl
+    np.testing.assert_allclose(x.norm(2), math.sqrt(bl * sum(i * i for i in range(1, nb + 1))), rtol=1e-14)
+    y.lincomb_([0.5, 1.0], [x, y])                                        # y .= 0.5.*x .+ y
+    assert y.sum() == 0.5 * s * bl + 2.0 * nb * bl
+    assert y[1] == 2.5 and y[nb * bl] == 0.5 * nb + 2.0

@@ -1,0 +1,155 @@
+"""GPU parity of mul! / adjoint against the oracle.
+
+Every case feeds identical seeded blocks and vectors to the oracle (reference-ordered arithmetic,
+src:582-721) and to the CUDA backend through the C ABI, and measures both against a higher-precision
+ground truth with the tolerance BASELINE.json states (1e-12 Float64, 1e-5 Float32, norm-wise per block).
+"""
+import numpy as np
+import pytest
+
+from helpers import build_pair, load_like, tol_for
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(dj, O, oop, gop, oblocks, rng, dtype):
+    tol = tol_for(dtype)
+    # forward
+    xo = oop.dom.rand(rng)
+    xg = load_like(gop.domain().zeros(), xo)
+    yo = oop.mul(oop.rng.zeros(), xo)
+    yg = gop.mul(gop.range().zeros(), xg)
+    truth = O.ground_truth_mul(oblocks, xo.to_array()) if not oop.isdiag else None
+    if oop.isdiag:
+        dblocks = [[oblocks[i][j] if i == j else O.OZero(dtype, oblocks[i][0].rng_shape, oblocks[j][j].dom_shape)
+                    for j in range(len(oblocks))] for i in range(len(oblocks))]
+        truth = O.ground_truth_mul(dblocks, xo.to_array())
+    lens = [int(np.prod(s)) for s in gop.row_shapes]
+    err_g = O.blockwise_relerr(yg.to_array(), truth, lens)
+    err_o = O.blockwise_relerr(yo.to_array(), truth, lens)
+    assert err_o <= tol, f"oracle itself off: {err_o}"
+    assert err_g <= tol, f"forward: gpu {err_g} (oracle {err_o}) > {tol}"
+    # the reference's own check: distributed == serial block operator under isapprox (test:418-428)
+    np.testing.assert_allclose(yg.to_array(), yo.to_array(), rtol=1.5e-8 if dtype == np.float64 else 1e-4)
+    # adjoint
+    do = oop.rng.rand(rng)
+    dg = load_like(gop.range().zeros(), do)
+    mo = oop.mul_adjoint(oop.dom.zeros(), do)
+    mg = gop.mul_adjoint(gop.domain().zeros(), dg)
+    if oop.isdiag:
+        truth_t = O.ground_truth_mul(dblocks, do.to_array(), adjoint=True)
+    else:
+        truth_t = O.ground_truth_mul(oblocks, do.to_array(), adjoint=True)
+    clens = [int(np.prod(s)) for s in gop.col_shapes]
+    err_g = O.blockwise_relerr(mg.to_array(), truth_t, clens)
+    err_o = O.blockwise_relerr(mo.to_array(), truth_t, clens)
+    assert err_o <= tol
+    assert err_g <= tol, f"adjoint: gpu {err_g} (oracle {err_o}) > {tol}"
+    # results land in the caller's vectors (mul! returns its first argument)
+    assert yg.nblocks() == oop.rng.nblocks() and mg.nblocks() == oop.dom.nblocks()
+
+
+CASES = [
+    # name, row sizes, col sizes, kind, pids, dist, isdiag
+    ("3x4 mixed on [2,1] (test:377-436 shape)", [10] * 3, [10] * 4,
+     lambda i, j: "diag" if (i + j) % 3 == 0 else ("zero" if (i, j) == (2, 2) else "dense"), [0, 1], [2, 1], False),
+    ("3x5 mixed on [2,2] (test:529-591 shape)", [10] * 3, [10] * 5,
+     lambda i, j: "diag" if (i % 2 == 0 and j % 2 == 1) else "dense", [0, 1, 2, 3], [2, 2], False),
+    ("4x4 block-diagonal dense 10x5 on 4 workers (test:496-512)", [10] * 4, [5] * 4,
+     lambda i, j: "dense" if i == j else "zero", [0, 1, 2, 3], [4, 1], True),
+    ("10x10 block-diagonal on 4 workers, 3,3,2,2 split (test:514-527)", [10] * 10, [10] * 10,
+     lambda i, j: "diag" if (i == j and i % 2) else ("dense" if i == j else "zero"), [0, 1, 2, 3], [4, 1], True),
+    ("misaligned sizes 5/7/3 x 9/1/6/2 on [2,2]", [5, 7, 3], [9, 1, 6, 2],
+     lambda i, j: "dense", [0, 1, 2, 3], [2, 2], False),
+    ("all-zero block row and column on [1,2] (extension F6)", [6, 4, 8], [4, 6, 5, 8],
+     lambda i, j: "zero" if (i == 2 or j == 3) else ("diag" if (i, j) in ((1, 2), (3, 4)) else "dense"),
+     [0, 1], [1, 2], False),
+    ("single worker 2x3 (extension F6)", [33, 65], [17, 129, 64], lambda i, j: "dense", [0], [1, 1], False),
+    ("tall blocks spanning several row strips / column panels on [2,2]", [300, 1100], [1300, 70, 2500],
+     lambda i, j: "dense", [0, 1, 2, 3], [2, 2], False),
+    ("4x1 grid column vector of blocks", [40, 50, 60, 70, 80], [30], lambda i, j: "dense", [0, 1, 2, 3], [4, 1], False),
+    ("1x4 grid", [50], [40, 50, 60, 70, 80], lambda i, j: "dense", [0, 1, 2, 3], [1, 4], False),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_mul_and_adjoint_match_oracle(dj, O, ctx4, case, dtype):
+    name, rs, cs, kind, pids, dist, isdiag = case
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    oop, gop, oblocks = build_pair(dj, O, rng, rs, cs, kind, dtype, pids, dist, isdiag, ctx=ctx4)
+    _check(dj, O, oop, gop, oblocks, rng, dtype)
+
+
+def test_config1_shape_4x4_dense_f64_1000(dj, O, ctx4):
+    """BASELINE config 1: 4x4 dense Float64 1000x1000 blocks on a [2,2] grid of 4 workers."""
+    rng = np.random.default_rng(20241)
+    oop, gop, oblocks = build_pair(dj, O, rng, [1000] * 4, [1000] * 4, lambda i, j: "dense", np.float64,
+                                   [0, 1, 2, 3], [2, 2], ctx=ctx4)
+    _check(dj, O, oop, gop, oblocks, rng, np.float64)
+
+
+def test_irregular_chunks(dj, O, ctx4):
+    """Caller-prescribed block ranges per grid row / column (src:8-38, test:39-52)."""
+    rng = np.random.default_rng(7)
+    rr, cr = [range(1, 2), range(2, 5)], [range(1, 4), range(4, 5)]
+    oop, gop, oblocks = build_pair(dj, O, rng, [12, 8, 9, 20], [7, 16, 5, 11], lambda i, j: "dense", np.float64,
+                                   [0, 1, 2, 3], None, ctx=ctx4, row_ranges=rr, col_ranges=cr)
+    assert gop.blockmap()[1][0] == (range(2, 5), range(1, 4))
+    _check(dj, O, oop, gop, oblocks, rng, np.float64)
+
+
+def test_operator_metadata_and_getblock(dj, O, ctx4):
+    """blockmap / procs / localblockindices / getblock(A,i,j) (src:805-852; test:381-385, 533-551)."""
+    rng = np.random.default_rng(3)
+    kind = lambda i, j: "diag" if (i % 2 == 0 and j % 2 == 1) else ("zero" if (i, j) == (1, 5) else "dense")
+    oop, gop, oblocks = build_pair(dj, O, rng, [10] * 3, [10] * 5, kind, np.float64, [0, 1, 2, 3], [2, 2], ctx=ctx4)
+    assert gop.nblocks() == (3, 5) == oop.nblocks()
+    assert gop.procs() == oop.procs() == [[0, 2], [1, 3]]                  # column-major grid, test:543
+    assert gop.blockmap() == oop.blockmap
+    assert gop.blockmap()[0][0] == (range(1, 3), range(1, 4))               # test:536-539
+    assert gop.blockmap()[1][1] == (range(3, 4), range(4, 6))
+    for pid in range(4):
+        assert gop.localblockindices(pid) == oop.localblockindices(pid)
+        assert gop.localblockindices(pid, 1) == oop.localblockindices(pid, 1)
+    assert gop.range().indices == oop.rng.indices and gop.domain().indices == oop.dom.indices
+    assert gop.domain().indices == [range(1, 31), range(31, 51)]            # test:568-571
+    for i in range(1, 4):
+        for j in range(1, 6):
+            g, o = gop.getblock(i, j), oop.getblock(i, j)
+            assert {"dense": dj.BLOCK_DENSE, "diag": dj.BLOCK_DIAG, "zero": dj.BLOCK_ZERO}[o.kind] == g.kind
+            if o.kind == "dense":
+                assert np.array_equal(g.A, o.A)                             # bit-exact round trip
+            elif o.kind == "diag":
+                assert np.array_equal(g.diag, o.d)
+
+
+def test_mismatched_vectors_raise(dj, O, ctx4):
+    rng = np.random.default_rng(5)
+    _, gop, _ = build_pair(dj, O, rng, [8, 8], [6, 6, 6], lambda i, j: "dense", np.float64, [0, 1, 2, 3], [2, 2],
+                           ctx=ctx4)
+    with pytest.raises(dj.DimensionMismatch):
+        gop.mul(gop.domain().zeros(), gop.domain().zeros())
+    with pytest.raises(dj.DimensionMismatch):
+        gop.mul_adjoint(gop.domain().zeros(), gop.domain().zeros())
+    x32 = gop.domain().zeros().similar(np.float32)
+    with pytest.raises(dj.DimensionMismatch):
+        gop.mul(gop.range().zeros(), x32)
+    with pytest.raises(dj.DJetsError):
+        dj.JopDBlock([[dj.JopZeroBlock(np.float64, 3, 3)] * 2] * 2, pids=[0, 1, 2, 3], dist=[2, 2], isdiag=True,
+                     ctx=ctx4)                                              # src:481
+
+
+def test_deterministic_run_to_run(dj, O, ctx4):
+    rng = np.random.default_rng(11)
+    _, gop, _ = build_pair(dj, O, rng, [700, 900], [1500, 600], lambda i, j: "dense", np.float32, [0, 1, 2, 3],
+                           [2, 2], ctx=ctx4)
+    x = gop.domain().rand(np.random.default_rng(1))
+    a = (gop @ x).to_array()
+    for _ in range(3):
+        assert np.array_equal(a, (gop @ x).to_array())
+    d = gop.range().rand(np.random.default_rng(2))
+    b = (gop.T @ d).to_array()
+    for _ in range(3):
+        assert np.array_equal(b, (gop.T @ d).to_array())
