@@ -92,6 +92,7 @@ SIGNATURES = {
     "djets_op_set_dense": [vp, i64, i64, vp, i64],
     "djets_op_set_diag": [vp, i64, i64, vp],
     "djets_op_finalize": [vp],
+    "djets_op_replan": [vp],
     "djets_op_destroy": [vp],
     "djets_op_new_vec": [vp, i32, p_vp],
     "djets_op_mul": [vp, vp, vp],

@@ -875,6 +875,10 @@ class JopDBlock:
         _lib.call("djets_op_algorithmic_bytes", self.h, C.byref(out))
         return int(out.value)
 
+    def replan(self) -> None:
+        """Rebuild the tile schedules after ``ctx.set_param`` (tuning only)."""
+        _lib.call("djets_op_replan", self.h)
+
     def schedule_info(self, adjoint: bool = False) -> Tuple[int, int]:
         nt, ni = C.c_int64(), C.c_int64()
         _lib.call("djets_op_schedule_info", self.h, 1 if adjoint else 0, C.byref(nt), C.byref(ni))

@@ -100,7 +100,7 @@ struct djets_ctx_s {
   std::vector<int> local_of_rank;
   bool has_nccl = false;
   bool timing = false;
-  int64_t fwd_tx = 32, fwd_tc = 512, adj_ru = 4, adj_tc = 32, ld_policy = 0;
+  int64_t fwd_tx = 64, fwd_tc = 512, adj_ru = 4, adj_tc = 64, ld_policy = 1;
   std::mutex mu;
 
   RankCtx* local(int rank) {
@@ -383,8 +383,9 @@ struct Block {
 struct DirPlan {
   DenseTile* d_tiles = nullptr;
   int ntiles = 0;
-  FinishItem* d_items = nullptr;
-  int nitems = 0;
+  FinishItem* d_items = nullptr;  // loose items first (finish_kernel), then the fused ones
+  int nitems = 0, nloose = 0;
+  unsigned* d_tickets = nullptr;  // one per item
   DiagTerm* d_diags = nullptr;
   char* W = nullptr;
   char* stage_in = nullptr;   // input slice received from its owner
@@ -411,7 +412,7 @@ struct djets_op_s {
   std::vector<int64_t> row_off, col_off;         // element offset of block row / column inside its part
   std::vector<int64_t> rowpart_len, colpart_len;  // elements per range / domain part
   bool finalized = false;
-  int64_t p_fwd_tx = 32, p_adj_ru = 4, p_ld_policy = 0;
+  int64_t p_fwd_tx = 64, p_adj_ru = 4, p_ld_policy = 1;
 
   int rank_at(int r, int c) const { return grid[r + c * n1]; }
   Cell& cell(int r, int c) { return cells[r + c * n1]; }
@@ -430,6 +431,7 @@ namespace {
 void free_plan(DirPlan& p) {
   cudaFree(p.d_tiles);
   cudaFree(p.d_items);
+  cudaFree(p.d_tickets);
   cudaFree(p.d_diags);
   cudaFree(p.W);
   cudaFree(p.stage_in);
@@ -507,9 +509,12 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
                                    : op->rowpart_len[cell.r];
 
   std::vector<DenseTile> tiles;
-  std::vector<FinishItem> items;
+  std::vector<FinishItem> loose, fused;
   std::vector<DiagTerm> diags;
   int64_t wtotal = 0;
+  // A cell that sums planes received from peers finishes in a separate kernel after the receive;
+  // everywhere else the last tile CTA of a strip does the sum inside the GEMV kernel.
+  const bool can_fuse = (nremote == 0);
 
   for (int64_t o = o0; o < o1; ++o) {
     const int64_t olen = out_len[o];
@@ -534,8 +539,50 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
       }
     }
     const bool direct = (nplanes == 1 && diag.empty() && nremote == 0);
+    const bool fuse = can_fuse && !direct && !dense.empty();
     const int64_t wbase = wtotal;
     if (!direct) wtotal += nplanes * olen;
+
+    // segmented-sum items of this output block, in chunks of `chunk` elements
+    auto emit_items = [&](std::vector<FinishItem>& dst, int64_t chunk) {
+      const int first = (int)dst.size();
+      for (int64_t e0 = 0; e0 < olen; e0 += chunk) {
+        FinishItem it;
+        it.out = out_off[o] + e0;
+        it.w0 = wbase + e0;
+        it.wstride = olen;
+        it.r0 = out_off[o] + e0;
+        it.rstride = part_len;
+        it.nplanes = (int)nplanes;
+        it.nremote = nremote;
+        it.diag_begin = (int)diags.size();
+        for (const Contribution& cb : diag) {
+          DiagTerm d;
+          d.d = cb.b->d + e0 * es;
+          d.vin = in_off[cb.in] + e0;
+          diags.push_back(d);
+        }
+        it.diag_end = (int)diags.size();
+        it.len = (int)std::min<int64_t>(chunk, olen - e0);
+        it.pad_ = 0;
+        dst.push_back(it);
+      }
+      return first;
+    };
+
+    int fused_first = -1;
+    int64_t strip = 0;  // strip length along the output dimension (identical for every block of the row/column)
+    if (fuse) {
+      const Contribution& cb = dense.front();
+      const int64_t i = adjoint ? cb.in : o, j = adjoint ? o : cb.in;
+      const TileShape sh = plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, op->p_fwd_tx, ctx->fwd_tc,
+                                      ctx->adj_tc);
+      strip = adjoint ? sh.tile_cols : sh.tile_rows;
+      fused_first = emit_items(fused, strip);
+    } else if (!direct) {
+      emit_items(loose, kFinishChunk);
+    }
+
     int64_t plane = 0;
     for (const Contribution& cb : dense) {
       const int64_t i = adjoint ? cb.in : o, j = adjoint ? o : cb.in;
@@ -552,7 +599,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
             t.cols = (int)std::min<int64_t>(sh.tile_cols, n - col0);
             t.direct = direct ? 1 : 0;
             t.wout = direct ? out_off[o] + row0 : wbase + (plane + p) * olen + row0;
-            t.pad_ = 0;
+            t.fin = fuse ? fused_first + (int)(row0 / strip) : -1;
             tiles.push_back(t);
           }
         }
@@ -567,40 +614,26 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
             t.cols = (int)std::min<int64_t>(sh.tile_cols, n - col0);
             t.direct = direct ? 1 : 0;
             t.wout = direct ? out_off[o] + col0 : wbase + (plane + p) * olen + col0;
-            t.pad_ = 0;
+            t.fin = fuse ? fused_first + (int)(col0 / strip) : -1;
             tiles.push_back(t);
           }
         }
       }
       plane += sh.nplanes;
     }
-    if (direct) continue;
-    for (int64_t e0 = 0; e0 < olen; e0 += kFinishChunk) {
-      FinishItem it;
-      it.out = out_off[o] + e0;
-      it.w0 = wbase + e0;
-      it.wstride = olen;
-      it.r0 = out_off[o] + e0;
-      it.rstride = part_len;
-      it.nplanes = (int)nplanes;
-      it.nremote = nremote;
-      it.diag_begin = (int)diags.size();
-      for (const Contribution& cb : diag) {
-        DiagTerm d;
-        d.d = cb.b->d + e0 * es;
-        d.vin = in_off[cb.in] + e0;
-        diags.push_back(d);
-      }
-      it.diag_end = (int)diags.size();
-      it.len = (int)std::min<int64_t>(kFinishChunk, olen - e0);
-      it.pad_ = 0;
-      items.push_back(it);
-    }
   }
+  // loose items first, fused items after them; tiles index the concatenated table
+  const int nloose = (int)loose.size();
+  for (DenseTile& t : tiles)
+    if (t.fin >= 0) t.fin += nloose;
+  std::vector<FinishItem> items(loose);
+  items.insert(items.end(), fused.begin(), fused.end());
+  plan.nloose = nloose;
   plan.ntiles = (int)tiles.size();
   plan.nitems = (int)items.size();
   plan.d_tiles = upload(tiles);
   plan.d_items = upload(items);
+  plan.d_tickets = reinterpret_cast<unsigned*>(dalloc(items.size() * sizeof(unsigned)));
   plan.d_diags = upload(diags);
   plan.W = dalloc((size_t)wtotal * es);
   // exchange buffers
@@ -686,17 +719,17 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
         if (!adjoint)
           launch_counted(ctx, *rc, DJETS_K_GEMV_N, [&] {
             return launch_gemv_n(op->dtype, (int)op->p_fwd_tx, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles, inp,
-                                 plan.W, outp, rc->stream);
+                                 plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets}, rc->stream);
           });
         else
           launch_counted(ctx, *rc, DJETS_K_GEMV_T, [&] {
             return launch_gemv_t(op->dtype, (int)op->p_adj_ru, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles, inp,
-                                 plan.W, outp, rc->stream);
+                                 plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets}, rc->stream);
           });
       }
-      if (!owner && plan.nitems > 0)
+      if (!owner && plan.nloose > 0)
         launch_counted(ctx, *rc, DJETS_K_FINISH, [&] {
-          return launch_finish(op->dtype, plan.d_items, plan.nitems, plan.d_diags, inp, plan.W, nullptr, outp,
+          return launch_finish(op->dtype, plan.d_items, plan.nloose, plan.d_diags, inp, plan.W, nullptr, outp,
                                rc->stream);
         });
     }
@@ -731,13 +764,13 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
       if (!rc) continue;
       use(*rc);
       DirPlan& plan = adjoint ? cell.adj : cell.fwd;
-      if (plan.nitems == 0) continue;
+      if (plan.nloose == 0) continue;
       const int ip = op->isdiag ? r : (adjoint ? r : c);
       const int opart = op->isdiag ? r : (adjoint ? c : r);
       const bool in_owner = op->isdiag || (adjoint ? (c == 0) : (r == 0));
       const char* inp = in_owner ? in->parts[ip].d : plan.stage_in;
       launch_counted(ctx, *rc, DJETS_K_FINISH, [&] {
-        return launch_finish(op->dtype, plan.d_items, plan.nitems, plan.d_diags, inp, plan.W, plan.R,
+        return launch_finish(op->dtype, plan.d_items, plan.nloose, plan.d_diags, inp, plan.W, plan.R,
                              out->parts[opart].d, rc->stream);
       });
     }
@@ -1433,6 +1466,19 @@ int32_t djets_op_finalize(djets_op op) {
   });
 }
 
+int32_t djets_op_replan(djets_op op) {
+  return guard([&] {
+    REQUIRE(op, DJETS_ERR_INVALID, "null operator");
+    for (Cell& c : op->cells)
+      if (RankCtx* rc = op->ctx->local(c.rank)) {
+        use(*rc);
+        CK(cudaStreamSynchronize(rc->stream));
+      }
+    op->finalized = false;
+    finalize_op(op);
+  });
+}
+
 int32_t djets_op_destroy(djets_op op) {
   return guard([&] {
     if (!op) return;
@@ -1562,7 +1608,7 @@ int32_t djets_op_schedule_info(djets_op op, int32_t adjoint, int64_t* ntiles, in
       if (!op->ctx->local(c.rank)) continue;
       const DirPlan& p = adjoint ? c.adj : c.fwd;
       t += p.ntiles;
-      it += p.nitems;
+      it += p.nloose;
     }
     if (ntiles) *ntiles = t;
     if (nitems) *nitems = it;

@@ -135,6 +135,67 @@ __device__ __forceinline__ void stage_vector(T* __restrict__ dst, const T* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Segmented sum of the partial planes of one output chunk, with the planes pushed by peer ranks
+// and the diagonal blocks of the block row (column) fused in.  Sums run in a fixed order, in
+// double for Float32 vectors.  COHERENT: the planes were written by other CTAs of this launch, so
+// they are read with ld.global.cg (L2), never from this SM's L1.
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool COHERENT>
+__device__ __forceinline__ T ld_plane(const T* p) {
+  return COHERENT ? __ldcg(p) : *p;
+}
+
+template <typename T, bool COHERENT>
+__device__ __forceinline__ void finish_item(const FinishItem& it, const DiagTerm* __restrict__ diags,
+                                            const T* __restrict__ in, const T* W, const T* __restrict__ R,
+                                            T* __restrict__ out) {
+  for (int e = threadIdx.x; e < it.len; e += kThreads) {
+    double s = 0.0;
+    const T* w = W + it.w0 + e;
+    int p = 0;
+    for (; p + 4 <= it.nplanes; p += 4) {
+      const T a0 = ld_plane<T, COHERENT>(w), a1 = ld_plane<T, COHERENT>(w + it.wstride),
+              a2 = ld_plane<T, COHERENT>(w + 2 * it.wstride), a3 = ld_plane<T, COHERENT>(w + 3 * it.wstride);
+      s += (double)a0;
+      s += (double)a1;
+      s += (double)a2;
+      s += (double)a3;
+      w += 4 * it.wstride;
+    }
+    for (; p < it.nplanes; ++p) {
+      s += (double)ld_plane<T, COHERENT>(w);
+      w += it.wstride;
+    }
+    for (int q = 0; q < it.nremote; ++q) s += (double)R[it.r0 + q * it.rstride + e];
+    for (int d = it.diag_begin; d < it.diag_end; ++d) {
+      const T* dd = reinterpret_cast<const T*>(diags[d].d);
+      s += (double)(dd[e] * in[diags[d].vin + e]);
+    }
+    out[it.out + e] = (T)s;
+  }
+}
+
+// Ticket protocol of a fused strip: every contributing CTA publishes its plane (fence), takes a
+// ticket, and the CTA holding the last ticket sums all planes and rearms the ticket for the next apply.
+template <typename T>
+__device__ __forceinline__ void fused_finish(const DenseTile& t, const FusedFinish& ff, const T* __restrict__ in,
+                                             const T* W, T* __restrict__ out) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned old = atomicAdd(ff.tickets + t.fin, 1u);
+    s_last = (old + 1u == (unsigned)ff.items[t.fin].nplanes) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    finish_item<T, true>(ff.items[t.fin], ff.diags, in, W, nullptr, out);
+    if (threadIdx.x == 0) ff.tickets[t.fin] = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Forward dense tiles: partial[r] = sum_c A[r,c] x[c].  A is column-major, so a thread owns VEC
 // consecutive rows (one 128-bit load per column) and walks the columns; the CTA is TX threads wide
 // along the rows and TY = 256/TX column groups deep; the TY partial strips are summed in shared
@@ -142,8 +203,8 @@ __device__ __forceinline__ void stage_vector(T* __restrict__ dst, const T* __res
 // ------------------------------------------------------------------------------------------------
 template <typename T, int TX, int POLICY>
 __global__ void __launch_bounds__(kThreads) gemv_n_kernel(const DenseTile* __restrict__ tiles,
-                                                          const T* __restrict__ in, T* __restrict__ W,
-                                                          T* __restrict__ out) {
+                                                          const T* __restrict__ in, T* W, T* __restrict__ out,
+                                                          FusedFinish ff) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   constexpr int TY = kThreads / TX;
@@ -203,6 +264,7 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(const DenseTile* __res
     for (int k = 0; k < VEC; ++k)
       if (r0 + k < rows) dst[r0 + k] = acc[k];
   }
+  if (t.fin >= 0) fused_finish<T>(t, ff, in, W, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -214,8 +276,8 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(const DenseTile* __res
 // ------------------------------------------------------------------------------------------------
 template <typename T, int RU, int POLICY>
 __global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __restrict__ tiles,
-                                                             const T* __restrict__ in, T* __restrict__ W,
-                                                             T* __restrict__ out) {
+                                                             const T* __restrict__ in, T* W, T* __restrict__ out,
+                                                             FusedFinish ff) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   constexpr int CW = kAdjCW;
@@ -282,42 +344,17 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __
       if (lane == k) mine = acc[k];
     if (lane < CW && c0 + lane < cols) dst[c0 + lane] = mine;
   }
+  if (t.fin >= 0) fused_finish<T>(t, ff, in, W, out);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Segmented sum of the partial planes of one output chunk, with the planes pushed by peer ranks
-// and the diagonal blocks of the block row (column) fused in.  Sums run in a fixed order, in
-// double for Float32 vectors.
-// ------------------------------------------------------------------------------------------------
+// Loose items: block rows / columns with no dense tile on this rank (diagonal-only: the fused
+// streaming `d .= diag .* m`), and every item of a rank that also sums planes received from peers.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) finish_kernel(const FinishItem* __restrict__ items,
                                                           const DiagTerm* __restrict__ diags,
                                                           const T* __restrict__ in, const T* __restrict__ W,
                                                           const T* __restrict__ R, T* __restrict__ out) {
-  const FinishItem it = items[blockIdx.x];
-  for (int e = threadIdx.x; e < it.len; e += kThreads) {
-    double s = 0.0;
-    const T* w = W + it.w0 + e;
-    int p = 0;
-    for (; p + 4 <= it.nplanes; p += 4) {
-      const T a0 = w[0], a1 = w[it.wstride], a2 = w[2 * it.wstride], a3 = w[3 * it.wstride];
-      s += (double)a0;
-      s += (double)a1;
-      s += (double)a2;
-      s += (double)a3;
-      w += 4 * it.wstride;
-    }
-    for (; p < it.nplanes; ++p) {
-      s += (double)w[0];
-      w += it.wstride;
-    }
-    for (int q = 0; q < it.nremote; ++q) s += (double)R[it.r0 + q * it.rstride + e];
-    for (int d = it.diag_begin; d < it.diag_end; ++d) {
-      const T* dd = reinterpret_cast<const T*>(diags[d].d);
-      s += (double)(dd[e] * in[diags[d].vin + e]);
-    }
-    out[it.out + e] = (T)s;
-  }
+  finish_item<T, false>(items[blockIdx.x], diags, in, W, R, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -651,53 +688,53 @@ cudaError_t launch_binary(int dtype, int op, void* dest, const void* a, const vo
 // ------------------------------------------------------------------------------------------------
 template <typename T, int POLICY>
 static cudaError_t launch_gemv_n_t(int fwd_tx, const DenseTile* tiles, int ntiles, const void* in, void* W, void* out,
-                                   cudaStream_t stream) {
+                                   FusedFinish ff, cudaStream_t stream) {
   const T* i = reinterpret_cast<const T*>(in);
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
   switch (fwd_tx) {
-    case 32: gemv_n_kernel<T, 32, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
-    case 64: gemv_n_kernel<T, 64, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
-    case 128: gemv_n_kernel<T, 128, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
-    case 256: gemv_n_kernel<T, 256, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
+    case 32: gemv_n_kernel<T, 32, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
+    case 64: gemv_n_kernel<T, 64, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
+    case 128: gemv_n_kernel<T, 128, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
+    case 256: gemv_n_kernel<T, 256, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
-                          void* W, void* out, cudaStream_t stream) {
+                          void* W, void* out, FusedFinish ff, cudaStream_t stream) {
   if (ntiles <= 0) return cudaSuccess;
   if (dtype == 0)
-    return ld_policy ? launch_gemv_n_t<float, 1>(fwd_tx, tiles, ntiles, in, W, out, stream)
-                     : launch_gemv_n_t<float, 0>(fwd_tx, tiles, ntiles, in, W, out, stream);
-  return ld_policy ? launch_gemv_n_t<double, 1>(fwd_tx, tiles, ntiles, in, W, out, stream)
-                   : launch_gemv_n_t<double, 0>(fwd_tx, tiles, ntiles, in, W, out, stream);
+    return ld_policy ? launch_gemv_n_t<float, 1>(fwd_tx, tiles, ntiles, in, W, out, ff, stream)
+                     : launch_gemv_n_t<float, 0>(fwd_tx, tiles, ntiles, in, W, out, ff, stream);
+  return ld_policy ? launch_gemv_n_t<double, 1>(fwd_tx, tiles, ntiles, in, W, out, ff, stream)
+                   : launch_gemv_n_t<double, 0>(fwd_tx, tiles, ntiles, in, W, out, ff, stream);
 }
 
 template <typename T, int POLICY>
 static cudaError_t launch_gemv_t_t(int adj_ru, const DenseTile* tiles, int ntiles, const void* in, void* W, void* out,
-                                   cudaStream_t stream) {
+                                   FusedFinish ff, cudaStream_t stream) {
   const T* i = reinterpret_cast<const T*>(in);
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
   switch (adj_ru) {
-    case 1: gemv_t_kernel<T, 1, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
-    case 2: gemv_t_kernel<T, 2, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
-    case 4: gemv_t_kernel<T, 4, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o); break;
+    case 1: gemv_t_kernel<T, 1, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
+    case 2: gemv_t_kernel<T, 2, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
+    case 4: gemv_t_kernel<T, 4, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_gemv_t(int dtype, int adj_ru, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
-                          void* W, void* out, cudaStream_t stream) {
+                          void* W, void* out, FusedFinish ff, cudaStream_t stream) {
   if (ntiles <= 0) return cudaSuccess;
   if (dtype == 0)
-    return ld_policy ? launch_gemv_t_t<float, 1>(adj_ru, tiles, ntiles, in, W, out, stream)
-                     : launch_gemv_t_t<float, 0>(adj_ru, tiles, ntiles, in, W, out, stream);
-  return ld_policy ? launch_gemv_t_t<double, 1>(adj_ru, tiles, ntiles, in, W, out, stream)
-                   : launch_gemv_t_t<double, 0>(adj_ru, tiles, ntiles, in, W, out, stream);
+    return ld_policy ? launch_gemv_t_t<float, 1>(adj_ru, tiles, ntiles, in, W, out, ff, stream)
+                     : launch_gemv_t_t<float, 0>(adj_ru, tiles, ntiles, in, W, out, ff, stream);
+  return ld_policy ? launch_gemv_t_t<double, 1>(adj_ru, tiles, ntiles, in, W, out, ff, stream)
+                   : launch_gemv_t_t<double, 0>(adj_ru, tiles, ntiles, in, W, out, ff, stream);
 }
 
 cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,

@@ -18,7 +18,7 @@ struct DenseTile {
   long long wout;     // element offset into the workspace (or the output vector when direct)
   int rows, cols;     // tile extents
   int direct;
-  int pad_;
+  int fin;            // >= 0: finish item this tile's strip belongs to (fused segmented sum), else -1
 };
 
 // One term of a diagonal block inside a finish item: out[e] += d[e] * in[vin + e].
@@ -30,6 +30,9 @@ struct DiagTerm {
 // Segmented sum of one output chunk: out[out+e] = sum_p W[w0 + p*wstride + e]
 //                                               + sum_q R[r0 + q*rstride + e]     (planes received from peers)
 //                                               + sum_t d_t[e] * in[vin_t + e]    (diagonal blocks)
+// An item is either "loose" (run by finish_kernel) or "fused": the last of the `nplanes` tile CTAs
+// that contribute to the strip (counted with an atomic ticket) performs the sum inside the GEMV
+// kernel, always in plane order, so the result does not depend on which CTA came last.
 struct FinishItem {
   long long out;
   long long w0, wstride;
@@ -42,10 +45,15 @@ struct FinishItem {
 
 // ---- launchers (all asynchronous on `stream`) ------------------------------------------------
 // dtype: 0 = float, 1 = double.  fwd_tx in {32,64,128,256}; adj_ru in {2,4,8}.
+struct FusedFinish {
+  const FinishItem* items;
+  const DiagTerm* diags;
+  unsigned* tickets;  // one per item, zero between launches
+};
 cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
-                          void* W, void* out, cudaStream_t stream);
+                          void* W, void* out, FusedFinish ff, cudaStream_t stream);
 cudaError_t launch_gemv_t(int dtype, int adj_ru, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
-                          void* W, void* out, cudaStream_t stream);
+                          void* W, void* out, FusedFinish ff, cudaStream_t stream);
 cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,
                           const void* W, const void* R, void* out, cudaStream_t stream);
 
@@ -75,7 +83,7 @@ constexpr int kThreads = 256;
 constexpr int kFwdMaxTC = 1024;   // columns of x staged in shared memory by a forward tile
 constexpr int kAdjMaxTRBytes = 32768;  // bytes of y staged in shared memory by an adjoint tile
 constexpr int kAdjCW = 4;         // columns a warp handles at once in the adjoint kernel
-constexpr int kFinishChunk = 2048;
+constexpr int kFinishChunk = 1024;
 inline int adj_max_rows(int dtype) { return kAdjMaxTRBytes / elem_size(dtype); }
 
 }  // namespace djets

@@ -186,6 +186,8 @@ int32_t djets_op_set_dense(djets_op op, int64_t i, int64_t j, const void* host, 
 int32_t djets_op_set_diag(djets_op op, int64_t i, int64_t j, const void* host);
 /* Build the tile schedules (after the last set_*; implicit on first apply). */
 int32_t djets_op_finalize(djets_op op);
+/* Rebuild the tile schedules with the context's current tuning parameters (payloads stay put). */
+int32_t djets_op_replan(djets_op op);
 int32_t djets_op_destroy(djets_op op);
 /* zeros(range(A)) / zeros(domain(A)) (src:378-381 over the spaces of src:502-503). which: 0 = domain, 1 = range. */
 int32_t djets_op_new_vec(djets_op op, int32_t which, djets_vec* out);
@@ -205,7 +207,7 @@ int32_t djets_op_getblock(djets_op op, int64_t i, int64_t j, int32_t* kind, void
  * domain + range elements. */
 int32_t djets_op_algorithmic_bytes(djets_op op, int64_t* bytes);
 /* Size of the finalised schedule on the ranks this process drives: dense tiles (one CTA each) and
- * segmented-sum items of the forward (adjoint = 0) or adjoint (1) apply. */
+ * segmented-sum items left to the separate finish kernel (the others are fused into the GEMV kernel). */
 int32_t djets_op_schedule_info(djets_op op, int32_t adjoint, int64_t* ntiles, int64_t* nitems);
 
 #ifdef __cplusplus
