@@ -6,7 +6,7 @@ root) under the module name ``djets_b200``; see INTEGRATION.md.
 from ._lib import (DJetsError, DimensionMismatch, NotLocal, LIB_PATH, F32, F64, BLOCK_ZERO, BLOCK_DENSE,
                    BLOCK_DIAG)
 from .partition import (urange, even_cuts, even_ranges, default_grid, cuts_from_ranges, ranges_from_cuts,
-                        grid_of)
+                        grid_of, plan_exchange)
 from .core import (Context, init, set_default_context, context, workers, nworkers, nccl_unique_id,
                    PinnedBuffer, JetDSpace, DBArray, LinExpr, dotted, zeros, ones, rand, Array, getblock,
                    getblock_into, setblock, collect, dot, norm, blockmap, localblockindices, procs, nprocs,

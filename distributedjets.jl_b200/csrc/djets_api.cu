@@ -645,6 +645,39 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   if (nremote > 0) plan.R = dalloc((size_t)nremote * part_len * es);
 }
 
+// The cross-rank traffic of one apply as a list of point-to-point messages between grid cells.
+//   phase 0 (before the tile kernels): the owner of an input part -- grid row 0 for the domain
+//     (forward), grid column 0 for the range (adjoint) -- sends it to the other cells of its grid
+//     column / row (one message per apply instead of the reference's per-(i,j) remote getblock,
+//     src:588,635,682).
+//   phase 1 (after them): every cell that does not own its output part sends its reduced partial to
+//     the owner on grid column 0 (forward) / grid row 0 (adjoint), which stores it in receive slot
+//     `slot` (replaces ArrayFutures + reduce!, src:600-604, 647-651, 694-698).
+// Block-diagonal operators exchange nothing (src:609-614, 656-661, 703-708).
+struct Message {
+  int src_r, src_c, dst_r, dst_c;
+  int part;  // index of the vector part being moved (input part in phase 0, output part in phase 1)
+  int slot;  // phase 1: receive plane on the owner; phase 0: -1
+};
+
+std::vector<Message> plan_exchange(int n1, int n2, bool isdiag, bool adjoint, int phase) {
+  std::vector<Message> out;
+  if (isdiag) return out;
+  for (int c = 0; c < n2; ++c)
+    for (int r = 0; r < n1; ++r) {
+      if (phase == 0) {
+        const bool in_owner = adjoint ? (c == 0) : (r == 0);
+        if (in_owner) continue;
+        out.push_back(adjoint ? Message{r, 0, r, c, r, -1} : Message{0, c, r, c, c, -1});
+      } else {
+        const bool owner = adjoint ? (r == 0) : (c == 0);
+        if (owner) continue;
+        out.push_back(adjoint ? Message{r, c, 0, c, c, r - 1} : Message{r, c, r, 0, r, c - 1});
+      }
+    }
+  return out;
+}
+
 void check_vec(djets_op op, djets_vec v, bool is_range, const char* what) {
   REQUIRE(v && v->ctx == op->ctx, DJETS_ERR_INVALID, std::string(what) + ": vector of another context");
   REQUIRE(v->dtype == op->dtype, DJETS_ERR_MISMATCH, std::string(what) + ": element type differs from the operator's");
@@ -684,22 +717,14 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   const int n1 = op->n1, n2 = op->isdiag ? 1 : op->n2;
 
   // phase A: every cell gets the input blocks of its block columns (forward) / block rows (adjoint)
-  // from the cell of grid row 0 / grid column 0 that owns them (replaces the per-(i,j) remote
-  // getblock(m, icol) of src:588,635 and getblock(d, irow) of src:682).
   std::vector<Transfer> ts;
-  if (!op->isdiag) {
-    for (int c = 0; c < n2; ++c)
-      for (int r = 0; r < n1; ++r) {
-        const bool in_owner = adjoint ? (c == 0) : (r == 0);
-        if (in_owner) continue;
-        Cell& cell = op->cell(r, c);
-        DirPlan& plan = adjoint ? cell.adj : cell.fwd;
-        const int ip = adjoint ? r : c;
-        const VecPart& part = in->parts[ip];
-        ts.push_back({part.rank, part.d, cell.rank, plan.stage_in, (size_t)part.elem_count * es});
-      }
-    run_transfers(ctx, ts);
+  for (const Message& msg : plan_exchange(n1, n2, op->isdiag, adjoint, 0)) {
+    Cell& cell = op->cell(msg.dst_r, msg.dst_c);
+    DirPlan& plan = adjoint ? cell.adj : cell.fwd;
+    const VecPart& part = in->parts[msg.part];
+    ts.push_back({part.rank, part.d, cell.rank, plan.stage_in, (size_t)part.elem_count * es});
   }
+  run_transfers(ctx, ts);
 
   // phase B: tile kernels, then the segmented sum on cells that do not own the output part
   for (int c = 0; c < n2; ++c)
@@ -734,25 +759,18 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
         });
     }
 
-  // phase C: partials of the other cells of a grid row (forward) / grid column (adjoint) go to the
-  // owner (replaces ArrayFutures + reduce! of src:600-604, 647-651, 694-698)
-  if (!op->isdiag && (adjoint ? n1 : n2) > 1) {
-    ts.clear();
-    for (int c = 0; c < n2; ++c)
-      for (int r = 0; r < n1; ++r) {
-        const bool owner = adjoint ? (r == 0) : (c == 0);
-        if (owner) continue;
-        Cell& cell = op->cell(r, c);
-        Cell& own = adjoint ? op->cell(0, c) : op->cell(r, 0);
-        DirPlan& plan = adjoint ? cell.adj : cell.fwd;
-        DirPlan& oplan = adjoint ? own.adj : own.fwd;
-        const int64_t part_len = adjoint ? op->colpart_len[c] : op->rowpart_len[r];
-        const int q = (adjoint ? r : c) - 1;
-        ts.push_back({cell.rank, plan.stage_out, own.rank, oplan.R ? oplan.R + (size_t)q * part_len * es : nullptr,
-                      (size_t)part_len * es});
-      }
-    run_transfers(ctx, ts);
+  // phase C: partials of the other cells of a grid row (forward) / grid column (adjoint) go to the owner
+  ts.clear();
+  for (const Message& msg : plan_exchange(n1, n2, op->isdiag, adjoint, 1)) {
+    Cell& cell = op->cell(msg.src_r, msg.src_c);
+    Cell& own = op->cell(msg.dst_r, msg.dst_c);
+    DirPlan& plan = adjoint ? cell.adj : cell.fwd;
+    DirPlan& oplan = adjoint ? own.adj : own.fwd;
+    const int64_t part_len = adjoint ? op->colpart_len[msg.part] : op->rowpart_len[msg.part];
+    ts.push_back({cell.rank, plan.stage_out, own.rank,
+                  oplan.R ? oplan.R + (size_t)msg.slot * part_len * es : nullptr, (size_t)part_len * es});
   }
+  run_transfers(ctx, ts);
 
   // phase D: owners sum their planes, the received planes and their diagonal blocks
   for (int c = 0; c < n2; ++c)
@@ -814,6 +832,22 @@ int32_t djets_plan_tiles(int32_t dtype, int64_t m, int64_t n, int32_t adjoint, i
     if (tile_rows) *tile_rows = s.tile_rows;
     if (tile_cols) *tile_cols = s.tile_cols;
     if (ntiles) *ntiles = s.ntiles;
+  });
+}
+
+int32_t djets_plan_exchange(int32_t n1, int32_t n2, int32_t isdiag, int32_t adjoint, int32_t phase, int32_t* out6,
+                            int32_t capacity, int32_t* count) {
+  return guard([&] {
+    REQUIRE(n1 >= 1 && n2 >= 1 && (phase == 0 || phase == 1) && count, DJETS_ERR_INVALID, "plan_exchange: bad arguments");
+    const std::vector<Message> msgs = plan_exchange(n1, n2, isdiag != 0, adjoint != 0, phase);
+    *count = (int32_t)msgs.size();
+    if (!out6) return;
+    REQUIRE(capacity >= (int32_t)msgs.size(), DJETS_ERR_INVALID, "plan_exchange: output too small");
+    for (size_t k = 0; k < msgs.size(); ++k) {
+      const Message& m = msgs[k];
+      const int32_t v[6] = {m.src_r, m.src_c, m.dst_r, m.dst_c, m.part, m.slot};
+      memcpy(out6 + 6 * k, v, sizeof(v));
+    }
   });
 }
 

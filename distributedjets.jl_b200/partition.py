@@ -79,3 +79,13 @@ def grid_of(pids: Sequence[int], n1: int, n2: int) -> List[List[int]]:
     if len(pids) < n1 * n2:
         raise ValueError(f"need {n1 * n2} workers for a {n1}x{n2} grid, have {len(pids)}")
     return [[pids[r + c * n1] for c in range(n2)] for r in range(n1)]
+
+
+def plan_exchange(n1: int, n2: int, isdiag: bool, adjoint: bool, phase: int) -> List[Tuple[int, int, int, int, int, int]]:
+    """The messages of one apply as (src_r, src_c, dst_r, dst_c, part, slot), 0-based grid
+    coordinates: exactly the list the library executes (include/djets.h djets_plan_exchange)."""
+    n = C.c_int32()
+    _lib.call("djets_plan_exchange", n1, n2, int(isdiag), int(adjoint), phase, None, 0, C.byref(n))
+    buf = (C.c_int32 * max(6 * n.value, 1))()
+    _lib.call("djets_plan_exchange", n1, n2, int(isdiag), int(adjoint), phase, buf, n.value, C.byref(n))
+    return [tuple(buf[6 * k:6 * k + 6]) for k in range(n.value)]

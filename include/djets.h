@@ -86,6 +86,15 @@ int32_t djets_grid_rank(int32_t n1, int32_t n2, int32_t r, int32_t c, const int3
 int32_t djets_plan_tiles(int32_t dtype, int64_t m, int64_t n, int32_t adjoint, int64_t* tile_rows,
                          int64_t* tile_cols, int64_t* ntiles);
 
+/* The point-to-point messages of one apply on an n1 x n2 grid (0-based grid coordinates), six
+ * int32 per message: src_r, src_c, dst_r, dst_c, part, slot.  phase 0: input parts from their owner
+ * (grid row 0 for mul!, grid column 0 for the adjoint) to the other cells of the grid column / row
+ * (replaces the remote getblock of src:588,635,682); phase 1: reduced partials to the owner of the
+ * output part, receive slot `slot` (replaces ArrayFutures + reduce! of src:600-604,647-651,694-698).
+ * out6 may be NULL to query the count.  This is the list djets_op_mul / djets_op_mul_adjoint execute. */
+int32_t djets_plan_exchange(int32_t n1, int32_t n2, int32_t isdiag, int32_t adjoint, int32_t phase, int32_t* out6,
+                            int32_t capacity, int32_t* count);
+
 /* ---- context ------------------------------------------------------------------------------ */
 int32_t djets_device_count(int32_t* n);
 /* 128-byte NCCL unique id, to be generated on one process and handed to every process'
