@@ -153,7 +153,7 @@ def run_reference(args):
         "note": "restated reference (NumPy/OpenBLAS port of src/DistributedJets.jl:656-661,703-708), not Julia: "
                 "Julia is absent from the image; omits Distributed.jl RPC cost, so it flatters the reference",
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=args.out, flush=True)
     return 0
 
 
@@ -340,11 +340,20 @@ def run_cuda(args):
             "clocks": clocks, "host_cores": os.cpu_count(), "parity_relerr_block1": parity, "build_s": t_build,
             "schedule": {"fwd_tiles_items": A.schedule_info(False), "adj_tiles_items": A.schedule_info(True)},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=args.out, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def quiet_stdout():
+    """Keep stdout for the ONE JSON line: libraries that print to fd 1 (NCCL's version banner, for
+    instance) are sent to stderr; returns a file object on the original stdout."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
 
 
 def main():
@@ -361,6 +370,7 @@ def main():
         ap.add_argument(f"--{name}", type=int, default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.out = quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_cuda(args)

@@ -324,8 +324,10 @@ void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_
                            rc->stream);
     });
   }
-  if (any_remote) {
-    REQUIRE(ctx->has_nccl, DJETS_ERR_NCCL, "vector has parts in other processes but the context has no NCCL");
+  // Every process of a multi-process job makes the same calls, so the decision to exchange must not
+  // depend on which parts happen to be local: with NCCL up, always all-reduce.
+  const bool multi_process = (int)ctx->ranks.size() < ctx->world;
+  if (multi_process && ctx->has_nccl) {
     const char* why = nullptr;
     const NcclApi* api = nccl_api(&why);
     REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
@@ -336,6 +338,8 @@ void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_
       NCK(api, api->AllReduce(rc.d_result, rc.d_result, np, ncclDouble, ncclSum, rc.comm, rc.stream));
     }
     NCK(api, api->GroupEnd());
+  } else {
+    REQUIRE(!any_remote, DJETS_ERR_NCCL, "vector has parts in other processes but the context has no NCCL");
   }
   for (RankCtx& rc : ctx->ranks) {
     use(rc);
