@@ -885,17 +885,37 @@ class JopDBlock:
         return int(nt.value), int(ni.value)
 
     # apply (src:582-721) ------------------------------------------------------------------------------------------
-    def mul(self, d: DBArray, m: DBArray) -> DBArray:
-        """``mul!(d, A, m)``."""
+    def _replicated_domain(self) -> DBArray:
+        """Device-side home of a replicated (plain-array) model: the tall-and-skinny case n2 == 1, where
+        the reference's domain is a local JetBSpace on the master and ``m`` is broadcast to every worker
+        (src:510-557).  Here it is the single domain part on grid cell (1,1); phase 0 of the exchange
+        plan forwards it to the other grid rows."""
+        if self.n2 != 1 or self.isdiag:
+            raise DimensionMismatch(_lib.ERR_MISMATCH, "a plain-array model needs a tall-and-skinny operator "
+                                                       "(grid n x 1, not block diagonal): src:523-557")
+        if getattr(self, "_mrep", None) is None:
+            self._mrep = self._domain.zeros()
+        return self._mrep
+
+    def mul(self, d: DBArray, m) -> DBArray:
+        """``mul!(d, A, m)``; ``m`` may be a plain array when the domain is replicated (src:544-557)."""
+        if isinstance(m, np.ndarray):
+            m = self._replicated_domain().scatter(np.ascontiguousarray(m.reshape(-1, order="F"), dtype=self.dtype))
         _lib.call("djets_op_mul", self.h, d.h, m.h)
         return d
 
-    def mul_adjoint(self, m: DBArray, d: DBArray) -> DBArray:
-        """``mul!(m, A', d)``."""
+    def mul_adjoint(self, m, d: DBArray):
+        """``mul!(m, A', d)``; a plain-array ``m`` receives the sum over workers (src:565-580)."""
+        if isinstance(m, np.ndarray):
+            rep = self._replicated_domain()
+            _lib.call("djets_op_mul_adjoint", self.h, rep.h, d.h)
+            flat = rep.to_array()
+            m[...] = flat.reshape(m.shape, order="F")
+            return m
         _lib.call("djets_op_mul_adjoint", self.h, m.h, d.h)
         return m
 
-    def __matmul__(self, m: DBArray) -> DBArray:
+    def __matmul__(self, m) -> DBArray:
         """``A*m = mul!(zeros(range(A)), A, m)``."""
         return self.mul(self._range.zeros(), m)
 

@@ -315,14 +315,34 @@ mutable struct DBlockOp{T}
     pids::Matrix{Int}
     blockmap::Matrix{Tuple{UnitRange{Int},UnitRange{Int}}}
     isdiag::Bool
+    mrep::Any                              # DBArray home of a replicated (plain-array) model, made on demand
     function DBlockOp{T}(h, pids, bm, isdiag) where {T}
-        op = new{T}(h, pids, bm, isdiag)
+        op = new{T}(h, pids, bm, isdiag, nothing)
         finalizer(o -> (o.h == C_NULL || ccall((:djets_op_destroy, libdjets[]), Int32, (Ptr{Cvoid},), o.h); o.h = C_NULL), op)
     end
 end
 
 JetDBlock_df!(d::DBArray, m::DBArray; op, kwargs...) = (@dj djets_op_mul (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}) op.h d.h m.h; d)           # src:663-674
 JetDBlock_df′!(m::DBArray, d::DBArray; op, kwargs...) = (@dj djets_op_mul_adjoint (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}) op.h m.h d.h; m)  # src:710-721
+
+# replicated domain (tall and skinny, grid n x 1): `m` is a plain array on the master, broadcast forward
+# (src:544-557) and tree-summed in the adjoint (src:565-580).  Its device-side home is the single
+# domain part on grid cell (1,1); phase 0 of the exchange plan forwards it to the other grid rows.
+function replicated!(op, dom::JetDSpace)
+    op.mrep === nothing && (op.mrep = zeros(dom))
+    op.mrep
+end
+function JetDBlock_df!(d::DBArray, m::Array{T}; op, dom, kwargs...) where {T}
+    x = replicated!(op, dom)
+    GC.@preserve m @dj djets_vec_scatter (Ptr{Cvoid}, Ptr{Cvoid}) x.h pointer(m)
+    JetDBlock_df!(d, x; op=op)
+end
+function JetDBlock_df′!(m::Array{T}, d::DBArray; op, dom, kwargs...) where {T}
+    x = replicated!(op, dom)
+    JetDBlock_df′!(x, d; op=op)
+    GC.@preserve m @dj djets_vec_collect (Ptr{Cvoid}, Ptr{Cvoid}) x.h pointer(m)
+    m
+end
 
 """
     JopBlock(blocks::Matrix{<:B200Block}; pids=workers(), dist=[n1,n2], isdiag=false)
@@ -361,7 +381,9 @@ function Jets.JopBlock(blocks::Matrix{<:B200Block{T}}; pids=workers(), dist=noth
     dom = isdiag ? JetDSpace(T, [colshapes[rcuts[r]+1:rcuts[r+1]] for r in 1:n1], grid[:, 1]) :
                    JetDSpace(T, [colshapes[ccuts[c]+1:ccuts[c+1]] for c in 1:n2], grid[1, :])                       # src:491-493
     op = DBlockOp{T}(h[], grid, bm, isdiag)
-    JopLn(dom = dom, rng = rng, df! = JetDBlock_df!, df′! = JetDBlock_df′!, s = (op=op, blockmap=bm, isdiag=isdiag))
+    # like the reference (src:459-462) a single domain worker means a plain local space: with n2 == 1 the
+    # operator also accepts `m::Array`; the DBArray form of the domain stays available as `state(A).dom`.
+    JopLn(dom = dom, rng = rng, df! = JetDBlock_df!, df′! = JetDBlock_df′!, s = (op=op, dom=dom, blockmap=bm, isdiag=isdiag))
 end
 
 # accessors (src:805-852) ------------------------------------------------------------------------------------------

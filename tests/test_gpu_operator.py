@@ -153,3 +153,68 @@ def test_deterministic_run_to_run(dj, O, ctx4):
     b = (gop.T @ d).to_array()
     for _ in range(3):
         assert np.array_equal(b, (gop.T @ d).to_array())
+
+
+def test_replicated_domain_tall_and_skinny(dj, O, ctx4):
+    """The reference's most used shape (test:377-470, docs:200-208): grid [n,1], the model a plain array
+    on the master, broadcast forward (src:544-557), tree-summed adjoint (src:565-580)."""
+    rng = np.random.default_rng(21)
+    kind = lambda i, j: "diag" if (i, j) in ((1, 1), (3, 2)) else ("zero" if (i, j) == (2, 3) else "dense")
+    oop, gop, oblocks = build_pair(dj, O, rng, [10, 10, 10], [10] * 4, kind, np.float64, [0, 1], [2, 1], ctx=ctx4)
+    assert gop.blockmap()[0][0] == (range(1, 3), range(1, 5)) and gop.blockmap()[1][0] == (range(3, 4), range(1, 5))
+    assert gop.range().indices == [range(1, 21), range(21, 31)]           # cuts [1,21,31], test:411-414
+    m = rng.random(40)
+    d = gop @ m
+    want = oop.mul_replicated(oop.rng.zeros(), m).to_array()
+    truth = O.ground_truth_mul(oblocks, m)
+    assert O.blockwise_relerr(d.to_array(), truth, [10] * 3) <= 1e-12
+    np.testing.assert_allclose(d.to_array(), want, rtol=1.5e-8)
+    dd = oop.rng.rand(rng)
+    dg = load_like(gop.range().zeros(), dd)
+    got = gop.mul_adjoint(np.zeros(40), dg)
+    want = oop.mul_adjoint_replicated(np.zeros(40), dd)
+    assert O.blockwise_relerr(got, O.ground_truth_mul(oblocks, dd.to_array(), adjoint=True), [10] * 4) <= 1e-12
+    np.testing.assert_allclose(got, want, rtol=1.5e-8)
+    _, g22, _ = build_pair(dj, O, rng, [4, 4], [4, 4], lambda i, j: "dense", np.float64, [0, 1, 2, 3], [2, 2], ctx=ctx4)
+    with pytest.raises(dj.DimensionMismatch):
+        g22 @ np.zeros(8)
+
+
+@pytest.mark.parametrize("dtype,m,n", [(np.float64, 9001, 70), (np.float32, 17003, 45), (np.float64, 6, 5000)])
+def test_blocks_taller_than_one_stage(dj, O, ctx4, dtype, m, n):
+    """Blocks taller than the 32 KB y stage of an adjoint tile (several row panels -> several planes per
+    output strip) and wider than one x stage of a forward tile."""
+    rng = np.random.default_rng(m)
+    oop, gop, oblocks = build_pair(dj, O, rng, [m, 33], [n, 17], lambda i, j: "dense", dtype, [0, 1], [1, 2], ctx=ctx4)
+    _check(dj, O, oop, gop, oblocks, rng, dtype)
+
+
+def test_empty_blocks_and_scalar_blocks(dj, O, ctx4):
+    """Zero-length and one-element blocks (ragged inputs)."""
+    rng = np.random.default_rng(5)
+    oop, gop, oblocks = build_pair(dj, O, rng, [1, 7, 1], [1, 3], lambda i, j: "dense", np.float64, [0, 1, 2, 3], [2, 2],
+                                   ctx=ctx4)
+    _check(dj, O, oop, gop, oblocks, rng, np.float64)
+    x = dj.DBArray(lambda i: np.zeros(0) if i == 2 else np.full(3, float(i)), (3,), [0, 1, 2])
+    assert len(x) == 6 and x.indices == [range(1, 4), range(4, 4), range(4, 7)]
+    assert dj.getblock(x, 2).shape == (0,) and x.sum() == 12.0 and np.array_equal(x.to_array(), [1, 1, 1, 3, 3, 3])
+
+
+def test_adjoint_dot_test_full_size_config2_shard(dj, ctx1):
+    """Size-independent property at the benchmark's block shape: <A x, y> == <x, A' y> on 8 dense Float32
+    4096x4096 diagonal blocks (one GPU's shard of BASELINE config 2 at N=8), plus a rank-one known answer."""
+    rng = np.random.default_rng(8)
+    u = [rng.random(4096, dtype=np.float32) for _ in range(8)]
+    v = [rng.random(4096, dtype=np.float32) for _ in range(8)]
+    A = dj.JopDBlock(lambda i, j: dj.JopDense(np.asfortranarray(np.outer(u[i - 1], v[i - 1])))
+                     if i == j else dj.JopZeroBlock(np.float32, 4096, 4096), dims=(8, 8), pids=[0], dist=[1, 1],
+                     isdiag=True, shapes=([(4096,)] * 8, [(4096,)] * 8), dtype=np.float32, ctx=ctx1)
+    x = dj.DBArray(lambda i: rng.random(4096, dtype=np.float32), (8,), [0], ctx=ctx1)
+    y = dj.DBArray(lambda i: rng.random(4096, dtype=np.float32), (8,), [0], ctx=ctx1)
+    Ax, Aty = A @ x, A.T @ y
+    lhs, rhs = float(Ax.dot(y)), float(x.dot(Aty))
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    for ib in range(1, 9):                                 # (u v') x = u (v . x)
+        want = np.outer(u[ib - 1], v[ib - 1]).astype(np.float64) @ x.getblock(ib).astype(np.float64)
+        got = Ax.getblock(ib).astype(np.float64)
+        assert np.linalg.norm(got - want) <= 1e-5 * np.linalg.norm(want)
