@@ -318,6 +318,14 @@ def run_cuda(args):
         dom = "gemv_t" if kt["ms"] >= kn["ms"] else "gemv_n"
         kd = kstats[dom]
         ach = per_launch / (kd["ms"] / max(kd["launches"], 1) * 1e-3) / 1e9 if kd["launches"] else None
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic_current.json")
+        if world == 1 and nblk == NBLK and os.path.exists(tpath):     # the ncu capture is of exactly this launch
+            with open(tpath) as f:
+                tj = json.load(f).get(dom + "_kernel")
+            if tj:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch (profiles/traffic_current.json)"
         kernels = {}
         for name, st in kstats.items():
             if st["launches"]:
@@ -331,7 +339,8 @@ def run_cuda(args):
             "applies_per_s": 2.0 / (ms_per_step * 1e-3),
             "frac_of_aggregate_hbm_peak": value / (peak * world),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": per_launch, "kernels": kernels},
             "cpu_baseline": cpu,
             "e2e": {"value": bytes_total / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
