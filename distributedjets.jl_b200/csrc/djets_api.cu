@@ -83,6 +83,7 @@ struct RankCtx {
   int rank = -1, device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev = nullptr;  // scratch event for cross-stream ordering
+  cudaEvent_t ev_fork = nullptr;  // fork / join of a captured apply
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   double* d_partials = nullptr;  // reduce stage-1 partials
   double* d_result = nullptr;    // 2*kMaxParts doubles: per-part results, then the all-reduce buffer
@@ -101,6 +102,14 @@ struct djets_ctx_s {
   bool has_nccl = false;
   bool timing = false;
   int64_t fwd_tx = 64, fwd_tc = 512, adj_ru = 4, adj_tc = 64, ld_policy = 1;
+  int64_t auto_tile = 1;  // shrink tiles of small operators so a launch still fills the SMs
+  int64_t graphs = 1;  // replay multi-launch applies as CUDA graphs
+  int64_t p2p = 1;     // kernels of one rank read / write another local rank's buffers in place
+  std::vector<char> peer;  // peer[a * ndev + b]: device a can address device b's memory
+  int ndev = 0;
+  bool can_address(const RankCtx& a, const RankCtx& b) const {
+    return a.device == b.device || peer[(size_t)a.device * ndev + b.device];
+  }
   std::mutex mu;
 
   RankCtx* local(int rank) {
@@ -417,6 +426,18 @@ struct djets_op_s {
   std::vector<int64_t> rowpart_len, colpart_len;  // elements per range / domain part
   bool finalized = false;
   int64_t p_fwd_tx = 64, p_adj_ru = 4, p_ld_policy = 1;
+  // CUDA-graph replay of whole applies (latency-bound operators: many small launches and copies)
+  struct GraphEntry {
+    std::vector<const void*> key;  // device pointers of the input and output parts
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
+    uint64_t last_use = 0;
+  };
+  std::vector<GraphEntry> graphs[2];
+  std::vector<std::vector<const void*>> seen[2];
+  uint64_t graph_clock = 0;
+  bool graphs_broken = false;
+  int enqueue_ops[2] = {0, 0};  // launches + copies of one apply, counted on the first direct run
 
   int rank_at(int r, int c) const { return grid[r + c * n1]; }
   Cell& cell(int r, int c) { return cells[r + c * n1]; }
@@ -512,6 +533,25 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   const int64_t part_len = adjoint ? (op->isdiag ? op->colpart_len[cell.r] : op->colpart_len[cell.c])
                                    : op->rowpart_len[cell.r];
 
+  // Tile extents of this cell and direction.  The tuned maxima (fwd_tc / adj_tc) apply to large
+  // operators; small ones get smaller tiles so that one launch still fills 148 SMs several times over
+  // (auto_tile).  One value per cell: every block of a block row / column must cut the same strips.
+  int64_t eff_fwd_tc = ctx->fwd_tc, eff_adj_tc = ctx->adj_tc;
+  if (ctx->auto_tile) {
+    int64_t dense_bytes = 0, max_rows = 1;
+    for (int64_t i = r0; i < r1; ++i)
+      for (int64_t j = c0; j < c1; ++j) {
+        if (op->isdiag && i != j) continue;
+        if (op->block(i, j).kind != DJETS_BLOCK_DENSE) continue;
+        dense_bytes += op->row_len[i] * op->col_len[j] * es;
+        max_rows = std::max(max_rows, op->row_len[i]);
+      }
+    const int64_t tile_bytes = std::max<int64_t>(64 * 1024, dense_bytes / (148 * 6));
+    const int64_t tr = op->p_fwd_tx * vec_elems(op->dtype);
+    eff_fwd_tc = std::max<int64_t>(64, std::min<int64_t>(ctx->fwd_tc, round_up(std::max<int64_t>(tile_bytes / (tr * es), 1), 64)));
+    const int64_t rows = std::min<int64_t>(max_rows, adj_max_rows(op->dtype));
+    eff_adj_tc = std::max<int64_t>(32, std::min<int64_t>(ctx->adj_tc, round_up(std::max<int64_t>(tile_bytes / (rows * es), 1), 32)));
+  }
   std::vector<DenseTile> tiles;
   std::vector<FinishItem> loose, fused;
   std::vector<DiagTerm> diags;
@@ -535,8 +575,8 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
       Block& b = op->block(i, j);
       if (b.kind == DJETS_BLOCK_DENSE && op->row_len[i] > 0 && op->col_len[j] > 0) {
         dense.push_back({in, &b});
-        nplanes += plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, op->p_fwd_tx, ctx->fwd_tc,
-                              ctx->adj_tc)
+        nplanes += plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, op->p_fwd_tx, eff_fwd_tc,
+                              eff_adj_tc)
                        .nplanes;
       } else if (b.kind == DJETS_BLOCK_DIAG) {
         diag.push_back({in, &b});
@@ -579,8 +619,8 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     if (fuse) {
       const Contribution& cb = dense.front();
       const int64_t i = adjoint ? cb.in : o, j = adjoint ? o : cb.in;
-      const TileShape sh = plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, op->p_fwd_tx, ctx->fwd_tc,
-                                      ctx->adj_tc);
+      const TileShape sh = plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, op->p_fwd_tx, eff_fwd_tc,
+                                      eff_adj_tc);
       strip = adjoint ? sh.tile_cols : sh.tile_rows;
       fused_first = emit_items(fused, strip);
     } else if (!direct) {
@@ -591,7 +631,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     for (const Contribution& cb : dense) {
       const int64_t i = adjoint ? cb.in : o, j = adjoint ? o : cb.in;
       const int64_t m = op->row_len[i], n = op->col_len[j];
-      const TileShape sh = plan_shape(op->dtype, m, n, adjoint, op->p_fwd_tx, ctx->fwd_tc, ctx->adj_tc);
+      const TileShape sh = plan_shape(op->dtype, m, n, adjoint, op->p_fwd_tx, eff_fwd_tc, eff_adj_tc);
       if (!adjoint) {
         for (int64_t col0 = 0, p = 0; col0 < n; col0 += sh.tile_cols, ++p) {
           for (int64_t row0 = 0; row0 < m; row0 += sh.tile_rows) {
@@ -710,15 +750,27 @@ void finalize_op(djets_op op) {
   op->finalized = true;
 }
 
-// mul!(out, A, in) (adjoint = false) or mul!(out, A', in) (adjoint = true)
-void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
+// Enqueues one apply on the ranks' streams: exchange phase 0, tile kernels (+ fused sums), exchange
+// phase 1, owners' segmented sums.  Returns the number of enqueued operations.
+int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   djets_ctx ctx = op->ctx;
-  check_vec(op, out, !adjoint, adjoint ? "mul!(m, A', d): m" : "mul!(d, A, m): d");
-  check_vec(op, in, adjoint, adjoint ? "mul!(m, A', d): d" : "mul!(d, A, m): m");
-  REQUIRE(out != in, DJETS_ERR_INVALID, "mul!: output aliases input");
-  finalize_op(op);
+  int nops = 0;
   const int es = elem_size(op->dtype);
   const int n1 = op->n1, n2 = op->isdiag ? 1 : op->n2;
+
+  // When both ends of a message are ranks of this process whose GPUs can address each other, no
+  // copy is made: the consumer's kernels read the owner's input part in place (peer loads over
+  // NVLink), and a non-owner's kernels store their reduced partial straight into the owner's receive
+  // plane (peer stores) -- the transfer is part of the compute kernel.  Streams are ordered with events.
+  auto in_place = [&](int rank_a, int rank_b) {
+    RankCtx* a = ctx->local(rank_a);
+    RankCtx* b = ctx->local(rank_b);
+    return ctx->p2p && a && b && ctx->can_address(*a, *b) && ctx->can_address(*b, *a);
+  };
+  const int ncell = n1 * n2;
+  std::vector<const char*> in_direct(ncell, nullptr);  // input part read in place from its owner
+  std::vector<char*> out_direct(ncell, nullptr);       // receive plane of the owner written in place
+  std::vector<int> in_from(ncell, -1), out_to(ncell, -1);
 
   // phase A: every cell gets the input blocks of its block columns (forward) / block rows (adjoint)
   std::vector<Transfer> ts;
@@ -726,11 +778,33 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
     Cell& cell = op->cell(msg.dst_r, msg.dst_c);
     DirPlan& plan = adjoint ? cell.adj : cell.fwd;
     const VecPart& part = in->parts[msg.part];
-    ts.push_back({part.rank, part.d, cell.rank, plan.stage_in, (size_t)part.elem_count * es});
+    const int k = msg.dst_r + msg.dst_c * n1;
+    if (in_place(part.rank, cell.rank)) {
+      in_direct[k] = part.d;
+      in_from[k] = part.rank;
+      stream_after(*ctx->local(part.rank), *ctx->local(cell.rank));  // the part is complete before it is read
+    } else {
+      ts.push_back({part.rank, part.d, cell.rank, plan.stage_in, (size_t)part.elem_count * es});
+    }
   }
   run_transfers(ctx, ts);
+  nops += (int)ts.size();
 
-  // phase B: tile kernels, then the segmented sum on cells that do not own the output part
+  std::vector<Message> phase1 = plan_exchange(n1, n2, op->isdiag, adjoint, 1);
+  for (const Message& msg : phase1) {
+    Cell& cell = op->cell(msg.src_r, msg.src_c);
+    Cell& own = op->cell(msg.dst_r, msg.dst_c);
+    DirPlan& oplan = adjoint ? own.adj : own.fwd;
+    if (in_place(cell.rank, own.rank)) {
+      const int64_t part_len = adjoint ? op->colpart_len[msg.part] : op->rowpart_len[msg.part];
+      const int k = msg.src_r + msg.src_c * n1;
+      out_direct[k] = oplan.R + (size_t)msg.slot * part_len * es;
+      out_to[k] = own.rank;
+      stream_after(*ctx->local(own.rank), *ctx->local(cell.rank));  // the owner's previous sum has read the plane
+    }
+  }
+
+  // phase B: tile kernels (with the fused segmented sums), loose sums on cells that do not own the output part
   for (int c = 0; c < n2; ++c)
     for (int r = 0; r < n1; ++r) {
       Cell& cell = op->cell(r, c);
@@ -738,13 +812,15 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
       if (!rc) continue;
       use(*rc);
       DirPlan& plan = adjoint ? cell.adj : cell.fwd;
+      const int k = r + c * n1;
       const bool in_owner = op->isdiag || (adjoint ? (c == 0) : (r == 0));
       const bool owner = op->isdiag || (adjoint ? (r == 0) : (c == 0));
       const int ip = op->isdiag ? r : (adjoint ? r : c);
       const int opart = op->isdiag ? r : (adjoint ? c : r);
-      const char* inp = in_owner ? in->parts[ip].d : plan.stage_in;
-      char* outp = owner ? out->parts[opart].d : plan.stage_out;
+      const char* inp = in_owner ? in->parts[ip].d : (in_direct[k] ? in_direct[k] : plan.stage_in);
+      char* outp = owner ? out->parts[opart].d : (out_direct[k] ? out_direct[k] : plan.stage_out);
       if (plan.ntiles > 0) {
+        ++nops;
         if (!adjoint)
           launch_counted(ctx, *rc, DJETS_K_GEMV_N, [&] {
             return launch_gemv_n(op->dtype, (int)op->p_fwd_tx, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles, inp,
@@ -756,16 +832,23 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
                                  plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets}, rc->stream);
           });
       }
-      if (!owner && plan.nloose > 0)
+      if (!owner && plan.nloose > 0) {
+        ++nops;
         launch_counted(ctx, *rc, DJETS_K_FINISH, [&] {
           return launch_finish(op->dtype, plan.d_items, plan.nloose, plan.d_diags, inp, plan.W, nullptr, outp,
                                rc->stream);
         });
+      }
+      // later writes to the input part (on its owner's stream) wait for this cell's reads; the owner's
+      // segmented sum waits for this cell's stores
+      if (in_from[k] >= 0) stream_after(*rc, *ctx->local(in_from[k]));
+      if (out_to[k] >= 0) stream_after(*rc, *ctx->local(out_to[k]));
     }
 
   // phase C: partials of the other cells of a grid row (forward) / grid column (adjoint) go to the owner
   ts.clear();
-  for (const Message& msg : plan_exchange(n1, n2, op->isdiag, adjoint, 1)) {
+  for (const Message& msg : phase1) {
+    if (out_direct[msg.src_r + msg.src_c * n1]) continue;
     Cell& cell = op->cell(msg.src_r, msg.src_c);
     Cell& own = op->cell(msg.dst_r, msg.dst_c);
     DirPlan& plan = adjoint ? cell.adj : cell.fwd;
@@ -775,6 +858,7 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
                   oplan.R ? oplan.R + (size_t)msg.slot * part_len * es : nullptr, (size_t)part_len * es});
   }
   run_transfers(ctx, ts);
+  nops += (int)ts.size();
 
   // phase D: owners sum their planes, the received planes and their diagonal blocks
   for (int c = 0; c < n2; ++c)
@@ -790,12 +874,145 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
       const int ip = op->isdiag ? r : (adjoint ? r : c);
       const int opart = op->isdiag ? r : (adjoint ? c : r);
       const bool in_owner = op->isdiag || (adjoint ? (c == 0) : (r == 0));
-      const char* inp = in_owner ? in->parts[ip].d : plan.stage_in;
+      const int k = r + c * n1;
+      const char* inp = in_owner ? in->parts[ip].d : (in_direct[k] ? in_direct[k] : plan.stage_in);
+      ++nops;
       launch_counted(ctx, *rc, DJETS_K_FINISH, [&] {
         return launch_finish(op->dtype, plan.d_items, plan.nloose, plan.d_diags, inp, plan.W, plan.R,
                              out->parts[opart].d, rc->stream);
       });
+      if (in_from[k] >= 0) stream_after(*rc, *ctx->local(in_from[k]));  // diagonal terms read the input in place
     }
+  return nops;
+}
+
+void clear_graphs(djets_op op) {
+  for (int d = 0; d < 2; ++d) {
+    for (auto& g : op->graphs[d])
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    op->graphs[d].clear();
+    op->seen[d].clear();
+  }
+}
+
+// The distinct local ranks an operator runs on, the first one being the capture origin.
+std::vector<RankCtx*> op_ranks(djets_op op) {
+  std::vector<RankCtx*> out;
+  for (Cell& c : op->cells)
+    if (RankCtx* rc = op->ctx->local(c.rank))
+      if (std::find(out.begin(), out.end(), rc) == out.end()) out.push_back(rc);
+  return out;
+}
+
+// mul!(out, A, in) (adjoint = false) or mul!(out, A', in) (adjoint = true)
+void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
+  djets_ctx ctx = op->ctx;
+  check_vec(op, out, !adjoint, adjoint ? "mul!(m, A', d): m" : "mul!(d, A, m): d");
+  check_vec(op, in, adjoint, adjoint ? "mul!(m, A', d): d" : "mul!(d, A, m): m");
+  REQUIRE(out != in, DJETS_ERR_INVALID, "mul!: output aliases input");
+  finalize_op(op);
+  const int dir = adjoint ? 1 : 0;
+  // Graph replay pays when an apply is a chain of many small launches and copies (grids on few GPUs,
+  // small blocks).  It needs every rank of the operator in this process (NCCL stays outside graphs)
+  // and per-launch timing off.  A (vectors, direction) pair is captured the second time it is seen.
+  const bool all_local = (int)ctx->ranks.size() == ctx->world;
+  const bool eligible = ctx->graphs && !ctx->timing && all_local && !op->graphs_broken &&
+                        (op->enqueue_ops[dir] == 0 || op->enqueue_ops[dir] >= 3);
+  if (!eligible) {
+    op->enqueue_ops[dir] = apply_enqueue(op, out, in, adjoint);
+    return;
+  }
+  std::vector<const void*> key;
+  for (const VecPart& p : in->parts) key.push_back(p.d);
+  for (const VecPart& p : out->parts) key.push_back(p.d);
+  std::vector<RankCtx*> ranks = op_ranks(op);
+  RankCtx* origin = ranks.front();
+
+  auto replay = [&](djets_op_s::GraphEntry& g) {
+    for (size_t k = 1; k < ranks.size(); ++k) stream_after(*ranks[k], *origin);  // earlier work of the other ranks
+    use(*origin);
+    CK(cudaGraphLaunch(g.exec, origin->stream));
+    if (ranks.size() > 1) {
+      CK(cudaEventRecord(origin->ev_fork, origin->stream));
+      for (size_t k = 1; k < ranks.size(); ++k) {
+        use(*ranks[k]);
+        CK(cudaStreamWaitEvent(ranks[k]->stream, origin->ev_fork, 0));
+      }
+    }
+    for (int k = 0; k < DJETS_K_COUNT; ++k) origin->launches[k] += g.launches[k];
+    g.last_use = ++op->graph_clock;
+  };
+
+  for (auto& g : op->graphs[dir])
+    if (g.key == key) {
+      replay(g);
+      return;
+    }
+  auto& seen = op->seen[dir];
+  if (std::find(seen.begin(), seen.end(), key) == seen.end()) {
+    if (seen.size() >= 16) seen.erase(seen.begin());
+    seen.push_back(key);
+    op->enqueue_ops[dir] = apply_enqueue(op, out, in, adjoint);
+    return;
+  }
+
+  // capture: fork every other rank's stream from the origin, enqueue, join back
+  std::vector<std::vector<int64_t>> before;  // the capture launches nothing: counters are restored after it
+  for (RankCtx* rc : ranks) before.emplace_back(rc->launches, rc->launches + DJETS_K_COUNT);
+  auto restore_counters = [&](int64_t* captured) {
+    for (size_t r = 0; r < ranks.size(); ++r)
+      for (int k = 0; k < DJETS_K_COUNT; ++k) {
+        if (captured) captured[k] += ranks[r]->launches[k] - before[r][k];
+        ranks[r]->launches[k] = before[r][k];
+      }
+  };
+  use(*origin);
+  CK(cudaStreamBeginCapture(origin->stream, cudaStreamCaptureModeRelaxed));
+  cudaGraph_t graph = nullptr;
+  try {
+    CK(cudaEventRecord(origin->ev_fork, origin->stream));
+    for (size_t k = 1; k < ranks.size(); ++k) {
+      use(*ranks[k]);
+      CK(cudaStreamWaitEvent(ranks[k]->stream, origin->ev_fork, 0));
+    }
+    apply_enqueue(op, out, in, adjoint);
+    for (size_t k = 1; k < ranks.size(); ++k) {
+      use(*ranks[k]);
+      CK(cudaEventRecord(ranks[k]->ev_fork, ranks[k]->stream));
+      use(*origin);
+      CK(cudaStreamWaitEvent(origin->stream, ranks[k]->ev_fork, 0));
+    }
+    use(*origin);
+    CK(cudaStreamEndCapture(origin->stream, &graph));
+  } catch (...) {
+    use(*origin);
+    cudaStreamEndCapture(origin->stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    (void)cudaGetLastError();
+    op->graphs_broken = true;  // fall back to direct launches for this operator from now on
+    restore_counters(nullptr);
+    apply_enqueue(op, out, in, adjoint);
+    return;
+  }
+  djets_op_s::GraphEntry g;
+  g.key = key;
+  restore_counters(g.launches);
+  cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    op->graphs_broken = true;
+    apply_enqueue(op, out, in, adjoint);
+    return;
+  }
+  if (op->graphs[dir].size() >= 8) {  // evict the least recently used
+    auto lru = std::min_element(op->graphs[dir].begin(), op->graphs[dir].end(),
+                                [](const auto& a, const auto& b) { return a.last_use < b.last_use; });
+    cudaGraphExecDestroy(lru->exec);
+    op->graphs[dir].erase(lru);
+  }
+  op->graphs[dir].push_back(g);
+  replay(op->graphs[dir].back());
 }
 
 }  // namespace
@@ -914,13 +1131,17 @@ int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ran
               std::string("device ") + prop.name + " is not sm_100-class: libdjets_b200 carries sm_100a code only");
       CK(cudaStreamCreateWithFlags(&rc.stream, cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&rc.ev, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&rc.ev_fork, cudaEventDisableTiming));
       CK(cudaEventCreate(&rc.t0));
       CK(cudaEventCreate(&rc.t1));
       CK(cudaMalloc(&rc.d_partials, sizeof(double) * reduce_max_ctas()));
       CK(cudaMalloc(&rc.d_result, sizeof(double) * 2 * kMaxParts));
       CK(cudaHostAlloc(&rc.h_result, sizeof(double) * 2 * kMaxParts, cudaHostAllocPortable));
     }
-    // peer access between the GPUs this process drives (local->local exchange is a peer copy)
+    // peer access between the GPUs this process drives: local->local exchange is in-place peer
+    // loads / stores from the kernels (or a peer copy when p2p is off)
+    ctx->ndev = ndev;
+    ctx->peer.assign((size_t)ndev * ndev, 0);
     for (RankCtx& a : ctx->ranks)
       for (RankCtx& b : ctx->ranks) {
         if (a.device == b.device) continue;
@@ -931,6 +1152,7 @@ int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ran
           cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
           if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
           (void)cudaGetLastError();
+          ctx->peer[(size_t)a.device * ndev + b.device] = 1;
         }
       }
     if (nccl_uid) {
@@ -968,6 +1190,7 @@ int32_t djets_ctx_destroy(djets_ctx ctx) {
       cudaFree(rc.d_result);
       cudaFreeHost(rc.h_result);
       cudaEventDestroy(rc.ev);
+      cudaEventDestroy(rc.ev_fork);
       cudaEventDestroy(rc.t0);
       cudaEventDestroy(rc.t1);
       cudaStreamDestroy(rc.stream);
@@ -1087,6 +1310,15 @@ int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
     } else if (n == "ld_policy") {
       REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "ld_policy in {0,1}");
       ctx->ld_policy = value;
+    } else if (n == "auto_tile") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "auto_tile in {0,1}");
+      ctx->auto_tile = value;
+    } else if (n == "p2p") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "p2p in {0,1}");
+      ctx->p2p = value;
+    } else if (n == "graphs") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "graphs in {0,1}");
+      ctx->graphs = value;
     } else {
       fail(DJETS_ERR_INVALID, "unknown parameter " + n);
     }
@@ -1512,6 +1744,8 @@ int32_t djets_op_replan(djets_op op) {
         use(*rc);
         CK(cudaStreamSynchronize(rc->stream));
       }
+    clear_graphs(op);
+    op->enqueue_ops[0] = op->enqueue_ops[1] = 0;
     op->finalized = false;
     finalize_op(op);
   });
@@ -1526,6 +1760,12 @@ int32_t djets_op_destroy(djets_op op) {
       if (!rc) continue;
       cudaSetDevice(rc->device);
       cudaStreamSynchronize(rc->stream);
+    }
+    clear_graphs(op);
+    for (Cell& c : op->cells) {
+      RankCtx* rc = op->ctx->local(c.rank);
+      if (!rc) continue;
+      cudaSetDevice(rc->device);
       free_plan(c.fwd);
       free_plan(c.adj);
     }

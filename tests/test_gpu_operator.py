@@ -218,3 +218,42 @@ def test_adjoint_dot_test_full_size_config2_shard(dj, ctx1):
         want = np.outer(u[ib - 1], v[ib - 1]).astype(np.float64) @ x.getblock(ib).astype(np.float64)
         got = Ax.getblock(ib).astype(np.float64)
         assert np.linalg.norm(got - want) <= 1e-5 * np.linalg.norm(want)
+
+
+def test_graph_replay_matches_direct_launches(dj, O, ctx4):
+    """Whole applies replayed as CUDA graphs (second sighting of a (vectors, direction) pair) give the
+    same bits as direct launches, read fresh input data on every replay, and count their launches."""
+    rng = np.random.default_rng(31)
+    kind = lambda i, j: "diag" if (i, j) == (2, 2) else "dense"
+    oop, gop, oblocks = build_pair(dj, O, rng, [300, 300, 120], [300, 300, 80, 64], kind, np.float64, [0, 1, 2, 3],
+                                   [2, 2], ctx=ctx4)
+    x, y = gop.domain().zeros(), gop.range().zeros()
+    d, m = gop.range().zeros(), gop.domain().zeros()
+    results = {}
+    for graphs, p2p in ((0, 0), (0, 1), (1, 1), (1, 0)):
+        ctx4.set_param("graphs", graphs)
+        ctx4.set_param("p2p", p2p)                           # 0: staged copies; 1: in-place peer loads / stores
+        gop.replan()
+        ctx4.reset_stats()
+        out = []
+        for it in range(5):                                  # same vectors every time -> captured at it == 1
+            x.scatter(np.random.default_rng(100 + it).random(len(x)))
+            d.scatter(np.random.default_rng(200 + it).random(len(d)))
+            gop.mul(y, x)
+            gop.mul_adjoint(m, d)
+            out.append((y.to_array().copy(), m.to_array().copy()))
+        results[(graphs, p2p)] = out
+        st = ctx4.kernel_stats()
+        assert st["gemv_n"]["launches"] == 5 * 4 and st["gemv_t"]["launches"] == 5 * 4, st
+    ctx4.set_param("graphs", 1)
+    ctx4.set_param("p2p", 1)
+    for key in ((0, 1), (1, 1), (1, 0)):
+        for a, b in zip(results[(0, 0)], results[key]):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), key
+    xo = oop.dom.zeros()
+    o = 0
+    flat = np.random.default_rng(104).random(len(x))
+    for ib, n in enumerate([300, 300, 80, 64], start=1):
+        xo.setblock(ib, flat[o:o + n]); o += n
+    truth = O.ground_truth_mul(oblocks, flat)
+    assert O.blockwise_relerr(results[(1, 1)][-1][0], truth, [300, 300, 120]) <= 1e-12
