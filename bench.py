@@ -185,7 +185,7 @@ def run_cuda(args):
     else:
         ctx = dj.Context(world=1, devices=[0])
     dj.set_default_context(ctx)
-    for name in ("fwd_tx", "fwd_tc", "adj_ru", "adj_tc", "ld_policy"):
+    for name in ("fwd_tx", "fwd_tc", "adj_ru", "adj_tc", "ld_policy", "pdl", "graphs", "p2p", "auto_tile"):
         v = getattr(args, name)
         if v is not None:
             ctx.set_param(name, v)
@@ -375,7 +375,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: skips the e2e pass, the clock-sampling loop and the CPU baseline")
-    for name in ("fwd_tx", "fwd_tc", "adj_ru", "adj_tc", "ld_policy"):
+    for name in ("fwd_tx", "fwd_tc", "adj_ru", "adj_tc", "ld_policy", "pdl", "graphs", "p2p", "auto_tile"):
         ap.add_argument(f"--{name}", type=int, default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -1310,6 +1310,9 @@ int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
     } else if (n == "ld_policy") {
       REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "ld_policy in {0,1}");
       ctx->ld_policy = value;
+    } else if (n == "pdl") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "pdl in {0,1}");
+      set_pdl((int)value);
     } else if (n == "auto_tile") {
       REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "auto_tile in {0,1}");
       ctx->auto_tile = value;

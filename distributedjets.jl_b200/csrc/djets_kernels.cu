@@ -92,6 +92,14 @@ __device__ __forceinline__ void dot_vec(double& acc, const double2& a, const dou
 // aligned the copy is one 1-D TMA bulk transfer (cp.async.bulk -> SASS UBLKCP) completing on an
 // mbarrier; otherwise the CTA copies it with plain loads.  `pad_to` elements past `n` are zeroed.
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a GEMV kernel lets the next kernel of the stream start as soon as its
+// own last CTA is resident (launch_dependents), and itself touches nothing a predecessor may still
+// be writing -- vectors, workspace, tickets -- before griddepcontrol.wait.  The block payloads and the
+// tile tables are immutable, so the first batch of matrix loads is issued ahead of the wait: launch
+// latency, the predecessor's tail and the x staging are hidden behind HBM traffic.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <typename T>
@@ -214,10 +222,10 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(const DenseTile* __res
   __shared__ __align__(16) T red[(TY > 1) ? TY * TR : 1];
   __shared__ __align__(8) uint64_t bar;
 
+  griddep_launch_dependents();
   const DenseTile t = tiles[blockIdx.x];
   const int tid = threadIdx.x;
   const int rows = t.rows, cols = t.cols;
-  stage_vector<T>(xs, in + t.vin, cols, cols, &bar);
 
   uint64_t pol = 0;
   if (POLICY == 1) pol = make_evict_first_policy();
@@ -228,11 +236,27 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(const DenseTile* __res
 #pragma unroll
   for (int k = 0; k < VEC; ++k) acc[k] = T(0);
 
+  const long long ld = t.ld;
+  const T* a = reinterpret_cast<const T*>(t.A) + r0 + (long long)ty * ld;
+  const long long cstep = (long long)TY * ld;
+  int c = ty;
+  // first batch of matrix loads goes out before the input vector is even looked at
+  const bool pre = (r0 < rows) && (c + (U - 1) * TY < cols);
+  V v0[U];
+  if (pre) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) v0[u] = ld_stream<POLICY>(reinterpret_cast<const V*>(a + u * cstep), pol);
+  }
+  griddep_wait();
+  stage_vector<T>(xs, in + t.vin, cols, cols, &bar);
+
   if (r0 < rows) {
-    const long long ld = t.ld;
-    const T* a = reinterpret_cast<const T*>(t.A) + r0 + (long long)ty * ld;
-    const long long cstep = (long long)TY * ld;
-    int c = ty;
+    if (pre) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) fma_vec(acc, v0[u], xs[c + u * TY]);
+      a += U * cstep;
+      c += U * TY;
+    }
     for (; c + (U - 1) * TY < cols; c += U * TY) {
       V v[U];
 #pragma unroll
@@ -285,10 +309,12 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __
   __shared__ __align__(128) T ys[kAdjMaxTRBytes / sizeof(T)];
   __shared__ __align__(8) uint64_t bar;
 
+  griddep_launch_dependents();
   const DenseTile t = tiles[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rows = t.rows, cols = t.cols;
   const int rowsv = (rows + VEC - 1) / VEC * VEC;  // pad rows of A are zero; pad y with zeros too
+  griddep_wait();
   stage_vector<T>(ys, in + t.vin, rows, rowsv, &bar);
 
   uint64_t pol = 0;
@@ -464,6 +490,9 @@ __global__ void __launch_bounds__(kThreads) reduce_stage2(const double* __restri
 }
 
 int reduce_max_ctas() { return 148 * 8; }
+
+static int g_pdl = 1;
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
 template <typename T, int KIND>
 static cudaError_t launch_reduce_k(const void* x, const void* y, long long n, double param, double* partials,
@@ -686,6 +715,21 @@ cudaError_t launch_binary(int dtype, int op, void* dest, const void* a, const vo
 // ------------------------------------------------------------------------------------------------
 // launch dispatch for the tile kernels
 // ------------------------------------------------------------------------------------------------
+template <typename... Args>
+static cudaError_t launch_tiles(void (*kernel)(Args...), int grid, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <typename T, int POLICY>
 static cudaError_t launch_gemv_n_t(int fwd_tx, const DenseTile* tiles, int ntiles, const void* in, void* W, void* out,
                                    FusedFinish ff, cudaStream_t stream) {
@@ -693,10 +737,10 @@ static cudaError_t launch_gemv_n_t(int fwd_tx, const DenseTile* tiles, int ntile
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
   switch (fwd_tx) {
-    case 32: gemv_n_kernel<T, 32, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
-    case 64: gemv_n_kernel<T, 64, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
-    case 128: gemv_n_kernel<T, 128, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
-    case 256: gemv_n_kernel<T, 256, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
+    case 32: return launch_tiles(gemv_n_kernel<T, 32, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+    case 64: return launch_tiles(gemv_n_kernel<T, 64, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+    case 128: return launch_tiles(gemv_n_kernel<T, 128, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+    case 256: return launch_tiles(gemv_n_kernel<T, 256, POLICY>, ntiles, stream, tiles, i, w, o, ff);
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -719,9 +763,9 @@ static cudaError_t launch_gemv_t_t(int adj_ru, const DenseTile* tiles, int ntile
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
   switch (adj_ru) {
-    case 1: gemv_t_kernel<T, 1, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
-    case 2: gemv_t_kernel<T, 2, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
-    case 4: gemv_t_kernel<T, 4, POLICY><<<ntiles, kThreads, 0, stream>>>(tiles, i, w, o, ff); break;
+    case 1: return launch_tiles(gemv_t_kernel<T, 1, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+    case 2: return launch_tiles(gemv_t_kernel<T, 2, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+    case 4: return launch_tiles(gemv_t_kernel<T, 4, POLICY>, ntiles, stream, tiles, i, w, o, ff);
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -57,6 +57,9 @@ cudaError_t launch_gemv_t(int dtype, int adj_ru, int ld_policy, const DenseTile*
 cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,
                           const void* W, const void* R, void* out, cudaStream_t stream);
 
+// Programmatic dependent launch of the tile kernels on / off (process-wide tuning switch).
+void set_pdl(int on);
+
 // Elementwise: dest[i] = sum_k coef[k] * x_k[i]; dtypes per operand; compute in double if wide.
 struct LincombArgs {
   const void* x[4];

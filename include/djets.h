@@ -124,7 +124,7 @@ int32_t djets_timer_stop(djets_ctx ctx, float* ms);
 int32_t djets_ctx_kernel_timing(djets_ctx ctx, int32_t enable);
 int32_t djets_ctx_kernel_stats(djets_ctx ctx, int32_t kind, int64_t* launches, double* total_ms);
 int32_t djets_ctx_reset_stats(djets_ctx ctx);
-/* Tuning knob (schedule shapes); name in {"fwd_tx","fwd_tc","adj_ru","adj_tc","ld_policy","graphs","p2p","auto_tile"}.
+/* Tuning knob (schedule shapes); name in {"fwd_tx","fwd_tc","adj_ru","adj_tc","ld_policy","graphs","p2p","auto_tile","pdl"}.
  * Affects operators finalised afterwards. */
 int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value);
 
