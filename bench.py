@@ -137,7 +137,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = 16
+    sample = max(16, min(NBLK, os.cpu_count() or 1))     # at least one block per host core
     steps = max(1, min(args.steps, 10))
     gbs, dt, cores = cpu_reference_run(sample, steps, max(1, min(args.warmup, 2)))
     sample_txt = (f"{sample} of the {NBLK} dense Float32 {BM}x{BN} diagonal blocks, forward+adjoint, "

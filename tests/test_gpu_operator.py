@@ -257,3 +257,31 @@ def test_graph_replay_matches_direct_launches(dj, O, ctx4):
         xo.setblock(ib, flat[o:o + n]); o += n
     truth = O.ground_truth_mul(oblocks, flat)
     assert O.blockwise_relerr(results[(1, 1)][-1][0], truth, [300, 300, 120]) <= 1e-12
+
+
+def test_random_operators_match_oracle(dj, O, ctx4):
+    """Forty seeded random operators: random block counts and sizes (including misaligned and
+    one-element blocks), random grids over 1-4 ranks, random mix of dense / diagonal / zero blocks,
+    random element type; forward and adjoint against ground truth and the oracle."""
+    master = np.random.default_rng(424242)
+    grids = [(1, 1), (2, 1), (1, 2), (2, 2), (4, 1), (1, 4), (3, 1), (1, 3)]
+    for case in range(40):
+        n1, n2 = grids[master.integers(len(grids))]
+        N, M = int(master.integers(n1, n1 + 4)), int(master.integers(n2, n2 + 4))
+        sizes = [1, 2, 3, 5, 8, 17, 33, 64, 100, 129, 257, 600]
+        rs = [int(sizes[master.integers(len(sizes))]) for _ in range(N)]
+        cs = [int(sizes[master.integers(len(sizes))]) for _ in range(M)]
+        dtype = np.float64 if master.integers(2) else np.float32
+        pick = master.random((N, M))
+
+        def kind(i, j, rs=rs, cs=cs, pick=pick):
+            p = pick[i - 1, j - 1]
+            if p < 0.2:
+                return "zero"
+            if p < 0.45 and rs[i - 1] == cs[j - 1]:
+                return "diag"
+            return "dense"
+
+        rng = np.random.default_rng(1000 + case)
+        oop, gop, oblocks = build_pair(dj, O, rng, rs, cs, kind, dtype, list(range(n1 * n2)), [n1, n2], ctx=ctx4)
+        _check(dj, O, oop, gop, oblocks, rng, dtype)
