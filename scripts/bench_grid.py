@@ -1,0 +1,114 @@
+"""BASELINE config 3 across GPUs: the full 32x32 dense Float64 2048x2048 operator on an n1 x n2 grid,
+block columns sharded across GPUs (cross-rank exchange: input parts to the other grid rows, reduced
+partials to the owners of the range parts).
+
+  one process per GPU over NCCL:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 --master-port 29540 \
+        scripts/bench_grid.py --grid 2 P/2
+  one host process driving P GPUs (in-place peer loads / stores, CUDA-graph replay):
+    python scripts/bench_grid.py --grid 2 2 --single-process
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import djets_loader  # noqa: E402
+
+dj = djets_loader.load()
+ap = argparse.ArgumentParser()
+ap.add_argument("--grid", type=int, nargs=2, default=[1, 1])
+ap.add_argument("--nb", type=int, default=32)
+ap.add_argument("--bs", type=int, default=2048)
+ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--single-process", action="store_true")
+args = ap.parse_args()
+n1, n2 = args.grid
+world = n1 * n2
+rank = int(os.environ.get("RANK", "0"))
+dist = None
+if args.single_process:
+    ctx = dj.Context(world=world, devices=list(range(world)))
+else:
+    import torch
+    import torch.distributed as dist
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    assert dist.get_world_size() == world, "launch one process per grid cell"
+    box = [dj.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx = dj.Context.spmd(rank, world, lr, box[0])
+dj.set_default_context(ctx)
+nb, bs = args.nb, args.bs
+rng = np.random.default_rng(20243)
+pool = [np.asfortranarray(rng.random((bs, bs))) for _ in range(8)]
+A = dj.JopDBlock(lambda i, j: dj.JopDense(pool[(3 * i + 5 * j) % 8]), dims=(nb, nb), pids=list(range(world)),
+                 dist=[n1, n2], shapes=([(bs,)] * nb, [(bs,)] * nb), dtype=np.float64, ctx=ctx)
+xs, ys = rng.random(nb * bs), rng.random(nb * bs)          # same on every process
+x, y = A.domain().zeros().scatter(xs), A.range().zeros().scatter(ys)
+yo, xo = A.range().zeros(), A.domain().zeros()
+
+
+def barrier():
+    ctx.sync()
+    if dist is not None:
+        dist.barrier()
+
+
+def reduce_max(v):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(v):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def timed(fn):
+    for _ in range(3):
+        fn()
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.reps):
+        fn()
+    ms = ctx.timer_stop() / args.reps
+    barrier()
+    return reduce_max(ms)
+
+
+tf = timed(lambda: A.mul(yo, x))
+ta = timed(lambda: A.mul_adjoint(xo, y))
+nbytes = reduce_sum(float(A.algorithmic_bytes()))
+# parity on block row 1 / block column 1 (owned by rank 0) against long double
+err_f = err_a = None
+if rank == 0:
+    got = yo.getblock(1)
+    truth = sum(pool[(3 * 1 + 5 * j) % 8].astype(np.longdouble) @ xs[(j - 1) * bs:j * bs].astype(np.longdouble)
+                for j in range(1, nb + 1))
+    err_f = float(np.linalg.norm((got - truth).astype(np.float64)) / np.linalg.norm(truth.astype(np.float64)))
+    got = xo.getblock(1)
+    truth = sum(pool[(3 * i + 5 * 1) % 8].astype(np.longdouble).T @ ys[(i - 1) * bs:i * bs].astype(np.longdouble)
+                for i in range(1, nb + 1))
+    err_a = float(np.linalg.norm((got - truth).astype(np.float64)) / np.linalg.norm(truth.astype(np.float64)))
+    print(json.dumps({"config": 3, "grid": [n1, n2], "n_gpus": world, "mode": "one process" if dist is None else "spmd+nccl",
+                      "blocks": [nb, nb], "block": [bs, bs], "bytes_per_apply": nbytes, "forward_ms": tf, "adjoint_ms": ta,
+                      "GBps_forward": nbytes / tf / 1e6, "GBps_adjoint": nbytes / ta / 1e6,
+                      "GBps_per_gpu": [nbytes / tf / 1e6 / world, nbytes / ta / 1e6 / world],
+                      "relerr_blockrow1": err_f, "relerr_blockcol1": err_a}), flush=True)
+if dist is not None:
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
