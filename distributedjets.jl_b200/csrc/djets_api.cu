@@ -49,8 +49,13 @@ struct Err {
     if (!(cond)) fail(code, msg); \
   } while (0)
 
+// One lock for the whole ABI: the contract is one calling thread per context, but *_destroy may
+// arrive from a finalizer thread (Julia GC) while the master thread is inside another call.
+std::recursive_mutex g_api_mutex;
+
 template <class F>
 int32_t guard(F&& f) {
+  std::lock_guard<std::recursive_mutex> api_lock(g_api_mutex);
   try {
     f();
     return DJETS_OK;
@@ -110,7 +115,6 @@ struct djets_ctx_s {
   bool can_address(const RankCtx& a, const RankCtx& b) const {
     return a.device == b.device || peer[(size_t)a.device * ndev + b.device];
   }
-  std::mutex mu;
 
   RankCtx* local(int rank) {
     if (rank < 0 || rank >= world) return nullptr;
@@ -1353,7 +1357,6 @@ int32_t djets_vec_similar(djets_vec x, int32_t dtype, djets_vec* out) {
 int32_t djets_vec_destroy(djets_vec x) {
   return guard([&] {
     if (!x) return;
-    std::lock_guard<std::mutex> lock(x->ctx->mu);
     free_vec(x);
   });
 }
@@ -1757,7 +1760,6 @@ int32_t djets_op_replan(djets_op op) {
 int32_t djets_op_destroy(djets_op op) {
   return guard([&] {
     if (!op) return;
-    std::lock_guard<std::mutex> lock(op->ctx->mu);
     for (Cell& c : op->cells) {
       RankCtx* rc = op->ctx->local(c.rank);
       if (!rc) continue;

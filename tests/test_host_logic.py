@@ -148,3 +148,30 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".jl")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "djets_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def _build_c_client(tmp_path):
+    import subprocess
+    exe = os.path.join(str(tmp_path), "c_abi_smoke")
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                          os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-ldl", "-lm"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_refuses_without_gpu(dj, tmp_path):
+    """include/djets.h compiles as C99 (-pedantic -Werror); the plain-C client loads the library and,
+    with no GPU, sees djets_ctx_create refuse with DJETS_ERR_CUDA."""
+    import subprocess
+    exe = _build_c_client(tmp_path)
+    out = subprocess.run([exe, dj.LIB_PATH], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "version" in out.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_client_on_gpu(dj, tmp_path):
+    import subprocess
+    exe = _build_c_client(tmp_path)
+    out = subprocess.run([exe, dj.LIB_PATH], capture_output=True, text=True)
+    assert out.returncode == 0 and "c abi ok" in out.stdout, out.stdout + out.stderr
