@@ -102,6 +102,8 @@ SIGNATURES = {
     "djets_op_block_owner": [vp, i64, i64, p_i32, p_i32, p_i32],
     "djets_op_getblock": [vp, i64, i64, p_i32, vp, i64],
     "djets_op_algorithmic_bytes": [vp, p_i64],
+    "djets_op_perfstat_enable": [vp, i32],
+    "djets_op_perfstat": [vp, i32, i32, p_f64],
     "djets_op_schedule_info": [vp, i32, p_i64, p_i64],
 }
 

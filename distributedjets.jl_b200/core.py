@@ -701,9 +701,12 @@ class JopDBlock:
     def __init__(self, blocks, dims: Optional[Tuple[int, int]] = None, pids: Optional[Sequence[int]] = None,
                  dist: Optional[Sequence[int]] = None, isdiag: bool = False,
                  row_ranges: Optional[Sequence[range]] = None, col_ranges: Optional[Sequence[range]] = None,
-                 shapes=None, dtype=None, ctx: Optional[Context] = None):
+                 shapes=None, dtype=None, ctx: Optional[Context] = None, perfstatfile: str = ""):
         ctx = ctx or context()
         self.ctx = ctx
+        self.perfstatfile = perfstatfile
+        if perfstatfile and os.path.exists(perfstatfile):
+            os.remove(perfstatfile)                       # src:505
         if callable(blocks):
             if dims is None:
                 raise ValueError("dims=(N, M) is needed when blocks is a callable")
@@ -789,6 +792,8 @@ class JopDBlock:
                 built.pop((i, j), None)
         built.clear()
         _lib.call("djets_op_finalize", h)
+        if perfstatfile:
+            _lib.call("djets_op_perfstat_enable", h, 1)
         self._range = self._space(True)
         self._domain = self._space(False)
 
@@ -897,11 +902,48 @@ class JopDBlock:
             self._mrep = self._domain.zeros()
         return self._mrep
 
+    def _perfstat(self, operation: str) -> None:
+        """``Jets.perfstat(ops, operation, perfstatfile)`` (src:723-745): append one step to the JSON file,
+        one entry per worker with ``id``, ``hostname``, ``operation`` and ``localblock`` -- here the
+        milliseconds of that worker's share of the apply, split over its local blocks (column-major, like
+        the reference's ``[...][:]``) in proportion to their algorithmic bytes."""
+        if not self.perfstatfile:
+            return
+        import json
+        import socket
+        es = self.dtype.itemsize
+        entries = []
+        for c in range(self.n2):                          # procs(ops) order: column-major grid
+            for r in range(self.n1):
+                if not self.ctx.is_local(self.pids[r][c]):
+                    continue
+                ms = C.c_double()
+                _lib.call("djets_op_perfstat", self.h, r, c, C.byref(ms))
+                rows, cols = self._blockmap[r][c]
+                w = []
+                for j in cols:
+                    for i in rows:
+                        k = self._kinds.get((i, j), _lib.BLOCK_ZERO)
+                        m_, n_ = _size(self.row_shapes[i - 1]), _size(self.col_shapes[j - 1])
+                        w.append(float(m_ * n_ * es) if k == _lib.BLOCK_DENSE else float(n_ * es) if k == _lib.BLOCK_DIAG else 0.0)
+                tot = sum(w) or 1.0
+                entries.append({"id": self.pids[r][c], "hostname": socket.gethostname(), "operation": operation,
+                                "localblock": [ms.value * v / tot for v in w]})
+        if os.path.isfile(self.perfstatfile):
+            with open(self.perfstatfile) as f:
+                doc = json.load(f)
+            doc["step"].append({"pid": entries})
+        else:
+            doc = {"step": [{"pid": entries}]}
+        with open(self.perfstatfile, "w") as f:
+            json.dump(doc, f, indent=1)
+
     def mul(self, d: DBArray, m) -> DBArray:
         """``mul!(d, A, m)``; ``m`` may be a plain array when the domain is replicated (src:544-557)."""
         if isinstance(m, np.ndarray):
             m = self._replicated_domain().scatter(np.ascontiguousarray(m.reshape(-1, order="F"), dtype=self.dtype))
         _lib.call("djets_op_mul", self.h, d.h, m.h)
+        self._perfstat("df")
         return d
 
     def mul_adjoint(self, m, d: DBArray):
@@ -909,10 +951,12 @@ class JopDBlock:
         if isinstance(m, np.ndarray):
             rep = self._replicated_domain()
             _lib.call("djets_op_mul_adjoint", self.h, rep.h, d.h)
+            self._perfstat("df\u2032")
             flat = rep.to_array()
             m[...] = flat.reshape(m.shape, order="F")
             return m
         _lib.call("djets_op_mul_adjoint", self.h, m.h, d.h)
+        self._perfstat("df\u2032")
         return m
 
     def __matmul__(self, m) -> DBArray:

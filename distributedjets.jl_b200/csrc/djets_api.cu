@@ -413,6 +413,8 @@ struct DirPlan {
 struct Cell {
   int r = 0, c = 0, rank = 0;
   DirPlan fwd, adj;
+  cudaEvent_t pt0 = nullptr, pt1 = nullptr;  // perfstat: bracket of this cell's work in the last apply
+  bool ptimed = false;
 };
 
 struct djets_op_s {
@@ -441,6 +443,7 @@ struct djets_op_s {
   std::vector<std::vector<const void*>> seen[2];
   uint64_t graph_clock = 0;
   bool graphs_broken = false;
+  bool perfstat = false;  // time every cell's share of each apply (replaces Jets.perfstat, src:723-745)
   int enqueue_ops[2] = {0, 0};  // launches + copies of one apply, counted on the first direct run
 
   int rank_at(int r, int c) const { return grid[r + c * n1]; }
@@ -756,6 +759,30 @@ void finalize_op(djets_op op) {
 
 // Enqueues one apply on the ranks' streams: exchange phase 0, tile kernels (+ fused sums), exchange
 // phase 1, owners' segmented sums.  Returns the number of enqueued operations.
+void perfstat_mark(djets_op op, bool begin) {
+  if (!op->perfstat) return;
+  for (Cell& cell : op->cells) {
+    RankCtx* rc = op->ctx->local(cell.rank);
+    if (!rc) continue;
+    use(*rc);
+    if (!cell.pt0) {
+      CK(cudaEventCreate(&cell.pt0));
+      CK(cudaEventCreate(&cell.pt1));
+    }
+    CK(cudaEventRecord(begin ? cell.pt0 : cell.pt1, rc->stream));
+    cell.ptimed = !begin;
+  }
+}
+
+int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint);
+
+int apply_enqueue_timed(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
+  perfstat_mark(op, true);
+  const int n = apply_enqueue(op, out, in, adjoint);
+  perfstat_mark(op, false);
+  return n;
+}
+
 int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   djets_ctx ctx = op->ctx;
   int nops = 0;
@@ -920,10 +947,10 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   // small blocks).  It needs every rank of the operator in this process (NCCL stays outside graphs)
   // and per-launch timing off.  A (vectors, direction) pair is captured the second time it is seen.
   const bool all_local = (int)ctx->ranks.size() == ctx->world;
-  const bool eligible = ctx->graphs && !ctx->timing && all_local && !op->graphs_broken &&
+  const bool eligible = ctx->graphs && !ctx->timing && !op->perfstat && all_local && !op->graphs_broken &&
                         (op->enqueue_ops[dir] == 0 || op->enqueue_ops[dir] >= 3);
   if (!eligible) {
-    op->enqueue_ops[dir] = apply_enqueue(op, out, in, adjoint);
+    op->enqueue_ops[dir] = apply_enqueue_timed(op, out, in, adjoint);
     return;
   }
   std::vector<const void*> key;
@@ -1771,6 +1798,8 @@ int32_t djets_op_destroy(djets_op op) {
       RankCtx* rc = op->ctx->local(c.rank);
       if (!rc) continue;
       cudaSetDevice(rc->device);
+      if (c.pt0) cudaEventDestroy(c.pt0);
+      if (c.pt1) cudaEventDestroy(c.pt1);
       free_plan(c.fwd);
       free_plan(c.adj);
     }
@@ -1879,6 +1908,28 @@ int32_t djets_op_algorithmic_bytes(djets_op op, int64_t* bytes) {
     for (int c = 0; c < op->ndom_parts(); ++c)
       if (op->ctx->local(op->isdiag ? op->rank_at(c, 0) : op->rank_at(0, c))) total += op->colpart_len[c] * es;
     *bytes = total;
+  });
+}
+
+int32_t djets_op_perfstat_enable(djets_op op, int32_t enable) {
+  return guard([&] {
+    REQUIRE(op, DJETS_ERR_INVALID, "null operator");
+    op->perfstat = enable != 0;
+  });
+}
+
+int32_t djets_op_perfstat(djets_op op, int32_t r, int32_t c, double* ms) {
+  return guard([&] {
+    REQUIRE(op && ms && r >= 0 && r < op->n1 && c >= 0 && c < op->n2, DJETS_ERR_INVALID, "perfstat: bad arguments");
+    Cell& cell = op->cell(r, c);
+    RankCtx* rc = op->ctx->local(cell.rank);
+    REQUIRE(rc, DJETS_ERR_NOT_LOCAL, "perfstat: the cell is driven by another process");
+    REQUIRE(cell.ptimed, DJETS_ERR_INVALID, "perfstat: no timed apply yet (djets_op_perfstat_enable first)");
+    use(*rc);
+    CK(cudaEventSynchronize(cell.pt1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, cell.pt0, cell.pt1));
+    *ms = t;
   });
 }
 

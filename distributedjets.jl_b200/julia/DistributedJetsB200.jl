@@ -17,7 +17,7 @@
 # (distributedjets.jl_b200/_lib.py, core.py), which is kept 1:1 with this file.
 module DistributedJetsB200
 
-using Jets, LinearAlgebra, Statistics
+using Jets, LinearAlgebra, Statistics, JSON
 import Libdl
 
 export DBArray, JetDSpace, blockmap, localblockindices
@@ -322,8 +322,34 @@ mutable struct DBlockOp{T}
     end
 end
 
-JetDBlock_df!(d::DBArray, m::DBArray; op, kwargs...) = (@dj djets_op_mul (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}) op.h d.h m.h; d)           # src:663-674
-JetDBlock_df′!(m::DBArray, d::DBArray; op, kwargs...) = (@dj djets_op_mul_adjoint (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}) op.h m.h d.h; m)  # src:710-721
+function JetDBlock_df!(d::DBArray, m::DBArray; op, perfstatfile="", kwargs...)                                      # src:663-674
+    @dj djets_op_mul (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}) op.h d.h m.h
+    perfstat(op, "df", perfstatfile)
+    d
+end
+function JetDBlock_df′!(m::DBArray, d::DBArray; op, perfstatfile="", kwargs...)                                     # src:710-721
+    @dj djets_op_mul_adjoint (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}) op.h m.h d.h
+    perfstat(op, "df′", perfstatfile)
+    m
+end
+
+# perfstatfile (src:723-745): one step per apply, one entry per worker; "localblock" holds the worker's
+# elapsed milliseconds, one value per local block (the JSON layout the reference's test:618-651 pins)
+function perfstat(op, operation, perfstatfile)
+    perfstatfile == "" && return nothing
+    entries = Dict{String,Any}[]
+    for c in 1:size(op.pids, 2), r in 1:size(op.pids, 1)
+        ms = Ref{Float64}(0)
+        @dj djets_op_perfstat (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}) op.h Int32(r - 1) Int32(c - 1) ms
+        nloc = length(op.blockmap[r, c][1]) * length(op.blockmap[r, c][2])
+        push!(entries, Dict("id" => op.pids[r, c], "hostname" => gethostname(), "operation" => operation,
+                            "localblock" => fill(ms[] / nloc, nloc)))
+    end
+    doc = isfile(perfstatfile) ? JSON.parse(read(perfstatfile, String)) : Dict("step" => Any[])
+    push!(doc["step"], Dict("pid" => entries))
+    write(perfstatfile, JSON.json(doc, 1))
+    nothing
+end
 
 # replicated domain (tall and skinny, grid n x 1): `m` is a plain array on the master, broadcast forward
 # (src:544-557) and tree-summed in the adjoint (src:565-580).  Its device-side home is the single
@@ -350,7 +376,7 @@ The `@blockop DArray(...) isdiag=...` of the reference (src:414-415, 476-508) fo
 blocks are laid out on an `n1 x n2` grid of ranks (column-major, src:483), payloads are uploaded to
 the owning GPU, and the result is a Jets `JopLn` whose `df!`/`df′!` are `djets_op_mul`/`_adjoint`.
 """
-function Jets.JopBlock(blocks::Matrix{<:B200Block{T}}; pids=workers(), dist=nothing, isdiag=false) where {T}
+function Jets.JopBlock(blocks::Matrix{<:B200Block{T}}; pids=workers(), dist=nothing, isdiag=false, perfstatfile="") where {T}
     N, M = size(blocks)
     dist === nothing && (dist = [min(N, length(pids)), 1])
     n1, n2 = dist
@@ -376,6 +402,10 @@ function Jets.JopBlock(blocks::Matrix{<:B200Block{T}}; pids=workers(), dist=noth
         end
     end
     @dj djets_op_finalize (Ptr{Cvoid},) h[]
+    if perfstatfile != ""                                                                                          # src:505
+        rm(perfstatfile, force=true)
+        @dj djets_op_perfstat_enable (Ptr{Cvoid}, Int32) h[] Int32(1)
+    end
     bm = [(rcuts[r]+1:rcuts[r+1], ccuts[c]+1:ccuts[c+1]) for r in 1:n1, c in 1:n2]                                 # src:507 indices(ops)
     rng = JetDSpace(T, [rowshapes[rcuts[r]+1:rcuts[r+1]] for r in 1:n1], grid[:, 1])                               # src:485
     dom = isdiag ? JetDSpace(T, [colshapes[rcuts[r]+1:rcuts[r+1]] for r in 1:n1], grid[:, 1]) :
@@ -383,7 +413,7 @@ function Jets.JopBlock(blocks::Matrix{<:B200Block{T}}; pids=workers(), dist=noth
     op = DBlockOp{T}(h[], grid, bm, isdiag)
     # like the reference (src:459-462) a single domain worker means a plain local space: with n2 == 1 the
     # operator also accepts `m::Array`; the DBArray form of the domain stays available as `state(A).dom`.
-    JopLn(dom = dom, rng = rng, df! = JetDBlock_df!, df′! = JetDBlock_df′!, s = (op=op, dom=dom, blockmap=bm, isdiag=isdiag))
+    JopLn(dom = dom, rng = rng, df! = JetDBlock_df!, df′! = JetDBlock_df′!, s = (op=op, dom=dom, blockmap=bm, isdiag=isdiag, perfstatfile=perfstatfile))
 end
 
 # accessors (src:805-852) ------------------------------------------------------------------------------------------

@@ -215,6 +215,11 @@ int32_t djets_op_getblock(djets_op op, int64_t i, int64_t j, int32_t* kind, void
 /* Algorithmic bytes of one apply on the ranks this process drives: non-zero block payloads +
  * domain + range elements. */
 int32_t djets_op_algorithmic_bytes(djets_op op, int64_t* bytes);
+/* perfstatfile support (src:723-745: per-worker statistics gathered after every apply).  With it
+ * enabled every grid cell's share of each apply is bracketed by CUDA events on its stream (graph replay
+ * is then bypassed); djets_op_perfstat returns the elapsed milliseconds of cell (r,c) in the last apply. */
+int32_t djets_op_perfstat_enable(djets_op op, int32_t enable);
+int32_t djets_op_perfstat(djets_op op, int32_t r, int32_t c, double* ms);
 /* Size of the finalised schedule on the ranks this process drives: dense tiles (one CTA each) and
  * segmented-sum items left to the separate finish kernel (the others are fused into the GEMV kernel). */
 int32_t djets_op_schedule_info(djets_op op, int32_t adjoint, int64_t* ntiles, int64_t* nitems);

@@ -285,3 +285,27 @@ def test_random_operators_match_oracle(dj, O, ctx4):
         rng = np.random.default_rng(1000 + case)
         oop, gop, oblocks = build_pair(dj, O, rng, rs, cs, kind, dtype, list(range(n1 * n2)), [n1, n2], ctx=ctx4)
         _check(dj, O, oop, gop, oblocks, rng, dtype)
+
+
+def test_perfstatfile_schema(dj, O, ctx4, tmp_path):
+    """perfstatfile (src:723-745; schema pinned by test:618-651): one step per apply, one entry per worker
+    with id / hostname / operation / localblock (8 and 4 local blocks for a 3x4 operator on grid [2,1])."""
+    import json
+    path = str(tmp_path / "stats.json")
+    open(path, "w").write("stale")                       # removed at construction (src:505)
+    rng = np.random.default_rng(1)
+    F = dj.JopDBlock(lambda i, j: dj.JopDense(np.asfortranarray(rng.random((10, 10)))), dims=(3, 4), pids=[0, 1],
+                     dist=[2, 1], perfstatfile=path, ctx=ctx4)
+    assert not (tmp_path / "stats.json").exists()
+    m = F.domain().rand(rng)
+    d = F @ m
+    s = json.load(open(path))
+    assert len(s["step"]) == 1 and len(s["step"][0]["pid"]) == 2
+    assert len(s["step"][0]["pid"][0]["localblock"]) == 8 and len(s["step"][0]["pid"][1]["localblock"]) == 4
+    assert s["step"][0]["pid"][0]["operation"] == "df" and s["step"][0]["pid"][0]["id"] == 0
+    assert all(v > 0 for p in s["step"][0]["pid"] for v in p["localblock"])
+    F.T @ d
+    F @ m
+    s = json.load(open(path))
+    assert [st["pid"][1]["operation"] for st in s["step"]] == ["df", "df′", "df"]
+    assert isinstance(s["step"][1]["pid"][0]["hostname"], str)
