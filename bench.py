@@ -157,10 +157,10 @@ def run_reference(args):
     return 0
 
 
-def workload_config(ngpus: int) -> dict:
-    return {"workload": f"BASELINE configs[1]: block-diagonal JopDBlock, {NBLK} dense Float32 {BM}x{BN} blocks, "
+def workload_config(ngpus: int, nblk: int = NBLK) -> dict:
+    return {"workload": f"BASELINE configs[1]: block-diagonal JopDBlock, {nblk} dense Float32 {BM}x{BN} blocks, "
                         f"isdiag, grid [{ngpus},1], forward mul! + adjoint mul! per step",
-            "blocks": NBLK, "block_shape": [BM, BN], "grid": [ngpus, 1],
+            "blocks": nblk, "block_shape": [BM, BN], "grid": [ngpus, 1],
             "l2": "inputs larger than L2 (operator payload per GPU >= 512 MiB vs 126 MB L2), no flush needed"}
 
 
@@ -213,7 +213,7 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    nblk = args.blocks
+    nblk = args.blocks * (world if args.scaling == "weak" else 1)
     shapes = ([(BM,)] * nblk, [(BN,)] * nblk)
     t_build = time.perf_counter()
     A = dj.JopDBlock(lambda i, j: dj.JopDense(block_payload(i)) if i == j else dj.JopZeroBlock(DTYPE, BM, BN),
@@ -312,7 +312,7 @@ def run_cuda(args):
     if rank == 0:
         peak, peak_src = peaks()
         es = np.dtype(DTYPE).itemsize
-        local_blocks = nblk // world + (1 if rank < nblk % world else 0)
+        local_blocks = nblk // world + (1 if rank < nblk % world else 0)     # rank 0's shard
         per_launch = local_blocks * (BM * BN + BM + BN) * es        # algorithmic bytes of one gemv launch
         kn, kt = kstats["gemv_n"], kstats["gemv_t"]
         dom = "gemv_t" if kt["ms"] >= kn["ms"] else "gemv_n"
@@ -334,8 +334,8 @@ def run_cuda(args):
                     kernels[name]["GBps"] = per_launch / (st["ms"] / st["launches"] * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, nblk),
             "applies_per_s": 2.0 / (ms_per_step * 1e-3),
             "frac_of_aggregate_hbm_peak": value / (peak * world),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -372,6 +372,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--blocks", type=int, default=NBLK, help="number of diagonal blocks (default: the BASELINE config)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the BASELINE operator's 64 blocks are sharded over the N ranks; "
+                         "weak: 64 blocks per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: skips the e2e pass, the clock-sampling loop and the CPU baseline")

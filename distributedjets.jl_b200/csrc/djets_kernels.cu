@@ -555,7 +555,7 @@ __device__ __forceinline__ ACC load_as(const void* p, int dtype, long long i) {
 
 // generic path: any mix of operand element types
 template <typename TD, typename ACC>
-__global__ void __launch_bounds__(kThreads) lincomb_generic(TD* __restrict__ dest, LincombDev a, long long n) {
+__global__ void __launch_bounds__(kThreads) lincomb_generic(TD* dest /* may alias an operand */, LincombDev a, long long n) {
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     ACC s;
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(kThreads) lincomb_generic(TD* __restrict__ des
 
 // fast path: all operands and dest share one element type; 128-bit loads / stores
 template <typename T, typename ACC, int NT>
-__global__ void __launch_bounds__(kThreads) lincomb_vec(T* __restrict__ dest, LincombDev a, long long n) {
+__global__ void __launch_bounds__(kThreads) lincomb_vec(T* dest /* may alias an operand */, LincombDev a, long long n) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   const long long nvec = n / VEC;
@@ -677,8 +677,7 @@ cudaError_t launch_fill(int dtype, void* dest, double a, long long n, cudaStream
 }
 
 template <typename T, int OP>
-__global__ void __launch_bounds__(kThreads) binary_kernel(T* __restrict__ dest, const T* __restrict__ a,
-                                                          const T* __restrict__ b, long long n) {
+__global__ void __launch_bounds__(kThreads) binary_kernel(T* dest /* may alias a or b */, const T* a, const T* b, long long n) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   const long long nvec = n / VEC;
