@@ -51,6 +51,8 @@ def main():
             rng = np.random.default_rng(17)
             kind = lambda i, j: "diag" if (i == 2 and j == 3) else ("zero" if (i, j) == (1, 1) else "dense")  # noqa
             rs, cs = [300, 200, 257, 64, 129], [200, 128, 200, 300, 31, 77]
+            rs = (rs * world)[:max(len(rs), world)]             # at least one block row / column per rank
+            cs = (cs * world)[:max(len(cs), world)]
             oop, gop, oblocks = build_pair(dj, O, rng, rs, cs, kind, dtype, list(range(world)), [n1, n2], ctx=ctx)
             xo = oop.dom.rand(rng)
             xg = gop.domain().zeros()
