@@ -246,10 +246,13 @@ class JetDSpace:
     def rand(self, rng: Optional[np.random.Generator] = None) -> "DBArray":
         rng = rng or np.random.default_rng()
         x = self.Array()
-        for ib, shape in enumerate(self.block_shapes(), start=1):
-            blk = rng.random(shape, dtype=self.dtype)    # drawn on every process: identical streams
-            x.setblock(ib, blk)
-        return x
+        flat = np.empty(len(self), dtype=self.dtype)
+        o = 0
+        for shape in self.block_shapes():                # block by block: drawn on every process, identical streams
+            n = _size(shape)
+            flat[o:o + n] = rng.random(shape, dtype=self.dtype).reshape(-1, order="F")
+            o += n
+        return x.scatter(flat)                           # one DMA per rank
 
 
 def _mypid(ctx: Context, pid: Optional[int]) -> int:

@@ -98,6 +98,11 @@ struct RankCtx {
   double ms[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
   std::vector<KernelEvent> pending;
   std::vector<cudaEvent_t> pool;
+  // Stream-ordered cache of vector-part allocations: a freed part is handed to the next DBArray of the
+  // same size on this rank without a device synchronisation (the reference's non-dotted arithmetic
+  // allocates a fresh DBArray per operation, src:353-356, so allocation has to be cheap).
+  std::multimap<size_t, char*> vec_cache;
+  size_t vec_cache_bytes = 0;
 };
 
 struct djets_ctx_s {
@@ -233,7 +238,46 @@ struct VecPart {
   int rank = 0;
   int64_t blk_first = 0, blk_count = 0, elem_first = 0, elem_count = 0;
   char* d = nullptr;  // device storage on the owner (nullptr when the owner is another process)
+  size_t cap = 0;     // allocated bytes
 };
+
+namespace {
+
+constexpr size_t kVecCacheLimit = size_t(32) << 30;  // bytes kept per rank before freed parts go back to the driver
+
+char* part_alloc(RankCtx& rc, size_t bytes) {
+  auto it = rc.vec_cache.find(bytes);
+  if (it != rc.vec_cache.end()) {
+    char* p = it->second;
+    rc.vec_cache.erase(it);
+    rc.vec_cache_bytes -= bytes;
+    return p;  // every earlier use was ordered before the free on this rank's stream
+  }
+  char* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaErrorMemoryAllocation && !rc.vec_cache.empty()) {  // give the cache back and retry
+    (void)cudaGetLastError();
+    CK(cudaStreamSynchronize(rc.stream));
+    for (auto& kv : rc.vec_cache) cudaFree(kv.second);
+    rc.vec_cache.clear();
+    rc.vec_cache_bytes = 0;
+    e = cudaMalloc(&p, bytes);
+  }
+  CK(e);
+  return p;
+}
+
+void part_free(RankCtx& rc, char* p, size_t bytes) {
+  if (rc.vec_cache_bytes + bytes > kVecCacheLimit) {
+    cudaStreamSynchronize(rc.stream);
+    cudaFree(p);
+    return;
+  }
+  rc.vec_cache.emplace(bytes, p);
+  rc.vec_cache_bytes += bytes;
+}
+
+}  // namespace
 
 struct djets_vec_s {
   djets_ctx ctx = nullptr;
@@ -283,8 +327,9 @@ djets_vec make_vec(djets_ctx ctx, int dtype, int nparts, const int32_t* part_ran
     b0 += part.blk_count;
     if (RankCtx* rc = ctx->local(part.rank)) {
       use(*rc);
-      const size_t bytes = (size_t)part.elem_count * es + 256;  // slack: 16-byte bulk copies may over-read
-      CK(cudaMalloc(&part.d, bytes));
+      const size_t bytes = (size_t)round_up(part.elem_count * es + 256, 512);  // slack for 16-byte over-reads
+      part.d = part_alloc(*rc, bytes);
+      part.cap = bytes;
       CK(cudaMemsetAsync(part.d, 0, bytes, rc->stream));
     }
   }
@@ -297,8 +342,7 @@ void free_vec(djets_vec v) {
     if (!p.d) continue;
     if (RankCtx* rc = v->ctx->local(p.rank)) {
       cudaSetDevice(rc->device);
-      cudaStreamSynchronize(rc->stream);
-      cudaFree(p.d);
+      part_free(*rc, p.d, p.cap);
     }
   }
   delete v;
@@ -1217,6 +1261,7 @@ int32_t djets_ctx_destroy(djets_ctx ctx) {
         cudaEventDestroy(k.b);
       }
       for (auto e : rc.pool) cudaEventDestroy(e);
+      for (auto& kv : rc.vec_cache) cudaFree(kv.second);
       cudaFree(rc.d_partials);
       cudaFree(rc.d_result);
       cudaFreeHost(rc.h_result);

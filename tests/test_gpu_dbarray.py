@@ -201,3 +201,24 @@ def test_large_vector_reductions_and_axpy(dj, ctx4):
     y.lincomb_([0.5, 1.0], [x, y])                                        # y .= 0.5.*x .+ y
     assert y.sum() == 0.5 * s * bl + 2.0 * nb * bl
     assert y[1] == 2.5 and y[nb * bl] == 0.5 * nb + 2.0
+
+
+def test_allocation_cache_reuses_parts_safely(dj, ctx4):
+    """Freed DBArray parts are recycled without synchronising; recycled storage starts zeroed and earlier
+    results are not disturbed (non-dotted arithmetic allocates per operation, src:353-356)."""
+    x = dj.DBArray(lambda i: np.arange(1000, dtype=np.float64) + i, (8,), [0, 1, 2, 3])
+    ref = x.to_array()
+    acc = x.copy()
+    for k in range(50):
+        tmp = 2.0 * acc                                    # new DBArray every iteration
+        acc = tmp - acc                                    # ... and another; the old ones are freed
+    assert np.array_equal(acc.to_array(), ref)
+    z = dj.zeros(x.space())
+    assert not z.to_array().any()                          # recycled storage is zero-initialised
+    import time
+    ctx4.sync()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        tmp = x.similar()
+    ctx4.sync()
+    assert (time.perf_counter() - t0) / 200 < 500e-6       # no cudaMalloc + device sync per allocation
