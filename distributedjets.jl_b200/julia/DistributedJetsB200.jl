@@ -95,8 +95,13 @@ function JetDSpace(::Type{T}, blkshapes::Vector{Vector{Dims}}, pids) where {T}
     JetDSpace{T}(blkshapes, collect(Int, pids), blkindices, indices)
 end
 Base.:(==)(R::JetDSpace, S::JetDSpace) = R.blkshapes == S.blkshapes && R.blkindices == S.blkindices && R.indices == S.indices
+Base.similar(::JetDSpace{T}, dims::NTuple{1,Int}) where {T} = JetSpace(T, dims)                       # src:71-72
+Base.similar(R::JetDSpace, dims::Int...) = similar(R, dims)
 Base.size(R::JetDSpace) = (R.indices[end][end],)
 Base.eltype(::JetDSpace{T}) where {T} = T
+Base.eltype(::Type{JetDSpace{T}}) where {T} = T                                                         # src:83-84
+Base.vec(R::JetDSpace) = R                                                                               # src:85
+Jets.space(R::JetDSpace{T}, ipart::Integer) where {T} = JetBSpace([JetSpace(T, s) for s in R.blkshapes[ipart]])  # src:88 (indexes by worker: reference quirk)
 Jets.indices(R::JetDSpace) = R.indices
 Jets.nblocks(R::JetDSpace) = R.blkindices[end][end]
 blockmap(R::JetDSpace) = R.blkindices

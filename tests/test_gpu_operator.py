@@ -309,3 +309,30 @@ def test_perfstatfile_schema(dj, O, ctx4, tmp_path):
     s = json.load(open(path))
     assert [st["pid"][1]["operation"] for st in s["step"]] == ["df", "df′", "df"]
     assert isinstance(s["step"][1]["pid"][0]["hostname"], str)
+
+
+def test_cgls_solver_loop_converges_to_lstsq(dj, O, ctx4):
+    """The solver loop of BASELINE config 5 (mul!, adjoint, dot, norm, axpy per iteration) on a mixed
+    dense/diagonal operator, against numpy's least-squares solution of the assembled matrix."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "cgls_example", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "cgls.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(12)
+    nbr, nbc, bs = 5, 4, 24                                # over-determined: 120 x 96
+    rs, cs = [bs] * nbr, [bs] * nbc
+    kind = lambda i, j: "diag" if (i % 2 == 0 and j % 2 == 1) else "dense"
+    oop, gop, oblocks = build_pair(dj, O, rng, rs, cs, kind, np.float64, [0, 1, 2, 3], [2, 2], ctx=ctx4)
+    dense = np.zeros((nbr * bs, nbc * bs))
+    for i in range(nbr):
+        for j in range(nbc):
+            b = oblocks[i][j]
+            dense[i * bs:(i + 1) * bs, j * bs:(j + 1) * bs] = b.A if b.kind == "dense" else np.diag(b.d)
+    rhs = rng.random(nbr * bs)
+    b = gop.range().zeros().scatter(rhs)
+    x, hist = mod.cgls(gop, b, iters=400, tol=1e-13)
+    want = np.linalg.lstsq(dense, rhs, rcond=None)[0]
+    assert np.linalg.norm(x.to_array() - want) <= 1e-6 * np.linalg.norm(want)
+    assert hist[-1] < hist[0]
