@@ -354,8 +354,10 @@ class DBArray:
     def eltype(self):
         return self.dtype
 
-    def __getitem__(self, i: int):
-        """``x[i]``, 1-based (src:174-179)."""
+    def __getitem__(self, i):
+        """``x[i]``, 1-based (src:174-179); ``x[range(a, b+1)]`` is Julia's ``x[a:b]`` (test:138, 167)."""
+        if isinstance(i, range):
+            return np.array([self[k] for k in i], dtype=self.dtype)
         if not 1 <= int(i) <= len(self):
             raise IndexError(f"BoundsError: attempt to access {len(self)}-element DBArray at index [{i}]")
         out = C.c_double()

@@ -336,3 +336,20 @@ def test_cgls_solver_loop_converges_to_lstsq(dj, O, ctx4):
     want = np.linalg.lstsq(dense, rhs, rcond=None)[0]
     assert np.linalg.norm(x.to_array() - want) <= 1e-6 * np.linalg.norm(want)
     assert hist[-1] < hist[0]
+
+
+def test_nan_follows_the_reference_through_zero_blocks(dj, O, ctx4):
+    """A NaN in one domain block reaches exactly the block rows that have a non-zero block in that
+    column: zero blocks are skipped (iszero, src:587,634), not multiplied."""
+    rng = np.random.default_rng(2)
+    kind = lambda i, j: "zero" if (i, j) in ((1, 2), (3, 2)) else ("diag" if (i, j) == (2, 2) else "dense")
+    oop, gop, oblocks = build_pair(dj, O, rng, [7, 5, 9], [6, 5, 4], kind, np.float64, [0, 1, 2, 3], [2, 2], ctx=ctx4)
+    x = gop.domain().rand(rng)
+    blk = x.getblock(2)
+    blk[3] = np.nan
+    x.setblock(2, blk)
+    y = gop @ x
+    assert np.isfinite(y.getblock(1)).all() and np.isfinite(y.getblock(3)).all()
+    yb = y.getblock(2)
+    assert np.isnan(yb[3]) and np.isfinite(np.delete(yb, 3)).all()        # the diagonal block touches one row only
+    assert np.array_equal(x[range(6 + 4, 6 + 5)], [np.nan], equal_nan=True)  # x[10:10]
