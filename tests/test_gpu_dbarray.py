@@ -222,3 +222,25 @@ def test_allocation_cache_reuses_parts_safely(dj, ctx4):
         tmp = x.similar()
     ctx4.sync()
     assert (time.perf_counter() - t0) / 200 < 500e-6       # no cudaMalloc + device sync per allocation
+
+
+def test_part_longer_than_2_pow_31_elements(dj, ctx1):
+    """Maximum sizes: one worker's part holds more than 2^31 Float32 elements (8.6 GB), so every kernel
+    and every offset on the path must index with 64 bits.  Only scalars and single elements cross PCIe."""
+    big = (1 << 31) + 5
+    R = dj.JetDSpace([[(3,), (big,), (2,)]], [0], np.float32, ctx=ctx1)
+    x = R.ones()
+    n = big + 5
+    assert len(x) == n and x.indices == [range(1, n + 1)] and x.nblocks() == 3
+    assert x.norm(0) == n                                   # count(!iszero): exact in Float32? no -> compare as float
+    assert float(x.norm(1)) == float(np.float32(n))
+    assert x.maximum() == 1.0 and x.minimum() == 1.0
+    x.setblock(3, np.array([7.0, -9.0], dtype=np.float32))  # the last two elements, beyond 2^31
+    assert x[n] == -9.0 and x[n - 1] == 7.0 and x[n - 2] == 1.0
+    assert x.minimum() == -9.0 and x.maximum() == 7.0 and x.maximum(abs) == 9.0
+    y = x.similar().fill(2.0)
+    got = float(x.dot(y))
+    assert got == float(np.float32(2.0 * (n - 2) + 2 * 7.0 - 2 * 9.0))
+    y.lincomb_([0.5, 1.0], [x, y])                          # y .= 0.5 .* x .+ y
+    assert y[n] == 0.5 * -9.0 + 2.0 and y[1] == 2.5 and y[n - 2] == 2.5
+    assert np.array_equal(y.getblock(3), [5.5, -2.5]) and np.array_equal(y.getblock(1), [2.5, 2.5, 2.5])
