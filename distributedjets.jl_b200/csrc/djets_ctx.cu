@@ -1,0 +1,332 @@
+// Contexts of libdjets_b200: one rank = one GPU = one former Distributed.jl worker; streams, events,
+// timers, per-kernel accounting, tuning parameters, and the host-only planning entry points.
+#include "djets_internal.h"
+
+using namespace djets;
+
+namespace djets {
+
+thread_local std::string g_last_error;
+std::recursive_mutex g_api_mutex;
+
+
+void use(RankCtx& rc) { CK(cudaSetDevice(rc.device)); }
+
+cudaEvent_t pool_event(RankCtx& rc) {
+  if (!rc.pool.empty()) {
+    cudaEvent_t e = rc.pool.back();
+    rc.pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  return e;
+}
+
+void drain_events(RankCtx& rc) {
+  if (rc.pending.empty()) return;
+  use(rc);
+  CK(cudaStreamSynchronize(rc.stream));
+  for (auto& k : rc.pending) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, k.a, k.b));
+    rc.ms[k.kind] += ms;
+    rc.pool.push_back(k.a);
+    rc.pool.push_back(k.b);
+  }
+  rc.pending.clear();
+}
+
+// dst stream waits for everything enqueued so far on src stream
+void stream_after(RankCtx& src, RankCtx& dst) {
+  if (&src == &dst) return;
+  use(src);
+  CK(cudaEventRecord(src.ev, src.stream));
+  use(dst);
+  CK(cudaStreamWaitEvent(dst.stream, src.ev, 0));
+}
+
+
+}  // namespace djets
+
+extern "C" {
+
+int32_t djets_version(void) { return 100; }
+const char* djets_last_error(void) { return g_last_error.c_str(); }
+
+int32_t djets_even_cuts(int64_t n, int32_t nparts, int64_t* cuts) {
+  return guard([&] {
+    REQUIRE(n >= 0 && nparts >= 1 && cuts, DJETS_ERR_INVALID, "even_cuts: bad arguments");
+    const int64_t q = n / nparts, rem = n % nparts;
+    cuts[0] = 0;
+    for (int k = 0; k < nparts; ++k) cuts[k + 1] = cuts[k] + q + (k < rem ? 1 : 0);
+  });
+}
+
+int32_t djets_grid_rank(int32_t n1, int32_t n2, int32_t r, int32_t c, const int32_t* grid_ranks, int32_t* rank) {
+  return guard([&] {
+    REQUIRE(n1 >= 1 && n2 >= 1 && r >= 0 && r < n1 && c >= 0 && c < n2 && rank, DJETS_ERR_INVALID,
+            "grid_rank: bad arguments");
+    const int idx = r + c * n1;
+    *rank = grid_ranks ? grid_ranks[idx] : idx;
+  });
+}
+
+int32_t djets_device_count(int32_t* n) {
+  return guard([&] {
+    int c = 0;
+    CK(cudaGetDeviceCount(&c));
+    *n = c;
+  });
+}
+
+int32_t djets_nccl_unique_id(uint8_t* out128) {
+  return guard([&] {
+    const char* why = nullptr;
+    const NcclApi* api = nccl_api(&why);
+    REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCK(api, api->GetUniqueId(&id));
+    memcpy(out128, &id, 128);
+  });
+}
+
+int32_t djets_host_alloc(int64_t bytes, void** out) {
+  return guard([&] {
+    REQUIRE(bytes >= 0 && out, DJETS_ERR_INVALID, "host_alloc: bad arguments");
+    CK(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable));
+  });
+}
+int32_t djets_host_free(void* p) {
+  return guard([&] {
+    if (p) CK(cudaFreeHost(p));
+  });
+}
+
+int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ranks, const int32_t* device_ids,
+                         const uint8_t* nccl_uid, djets_ctx* out) {
+  return guard([&] {
+    REQUIRE(out, DJETS_ERR_INVALID, "ctx_create: null out");
+    REQUIRE(world >= 1 && nlocal >= 1 && nlocal <= world, DJETS_ERR_INVALID, "ctx_create: bad world / nlocal");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    REQUIRE(ndev > 0, DJETS_ERR_CUDA, "no CUDA device: libdjets_b200 has no CPU path");
+    auto ctx = std::make_unique<djets_ctx_s>();
+    ctx->world = world;
+    ctx->local_of_rank.assign(world, -1);
+    ctx->ranks.resize(nlocal);
+    for (int l = 0; l < nlocal; ++l) {
+      RankCtx& rc = ctx->ranks[l];
+      rc.rank = local_ranks ? local_ranks[l] : l;
+      rc.device = device_ids ? device_ids[l] : (l % ndev);
+      REQUIRE(rc.rank >= 0 && rc.rank < world && ctx->local_of_rank[rc.rank] < 0, DJETS_ERR_INVALID,
+              "ctx_create: bad or repeated local rank");
+      REQUIRE(rc.device >= 0 && rc.device < ndev, DJETS_ERR_INVALID, "ctx_create: device id out of range");
+      ctx->local_of_rank[rc.rank] = l;
+      use(rc);
+      cudaDeviceProp prop;
+      CK(cudaGetDeviceProperties(&prop, rc.device));
+      REQUIRE(prop.major >= 10, DJETS_ERR_CUDA,
+              std::string("device ") + prop.name + " is not sm_100-class: libdjets_b200 carries sm_100a code only");
+      CK(cudaStreamCreateWithFlags(&rc.stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&rc.ev, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&rc.ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreate(&rc.t0));
+      CK(cudaEventCreate(&rc.t1));
+      CK(cudaMalloc(&rc.d_partials, sizeof(double) * reduce_max_ctas()));
+      CK(cudaMalloc(&rc.d_result, sizeof(double) * 2 * kMaxParts));
+      CK(cudaHostAlloc(&rc.h_result, sizeof(double) * 2 * kMaxParts, cudaHostAllocPortable));
+    }
+    // peer access between the GPUs this process drives: local->local exchange is in-place peer
+    // loads / stores from the kernels (or a peer copy when p2p is off)
+    ctx->ndev = ndev;
+    ctx->peer.assign((size_t)ndev * ndev, 0);
+    for (RankCtx& a : ctx->ranks)
+      for (RankCtx& b : ctx->ranks) {
+        if (a.device == b.device) continue;
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, a.device, b.device));
+        if (can) {
+          use(a);
+          cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+          (void)cudaGetLastError();
+          ctx->peer[(size_t)a.device * ndev + b.device] = 1;
+        }
+      }
+    if (nccl_uid) {
+      const char* why = nullptr;
+      const NcclApi* api = nccl_api(&why);
+      REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
+      ncclUniqueId id;
+      memcpy(&id, nccl_uid, 128);
+      NCK(api, api->GroupStart());
+      for (RankCtx& rc : ctx->ranks) {
+        use(rc);
+        NCK(api, api->CommInitRank(&rc.comm, world, id, rc.rank));
+      }
+      NCK(api, api->GroupEnd());
+      ctx->has_nccl = true;
+    }
+    *out = ctx.release();
+  });
+}
+
+int32_t djets_ctx_destroy(djets_ctx ctx) {
+  return guard([&] {
+    if (!ctx) return;
+    const NcclApi* api = ctx->has_nccl ? nccl_api(nullptr) : nullptr;
+    for (RankCtx& rc : ctx->ranks) {
+      cudaSetDevice(rc.device);
+      cudaStreamSynchronize(rc.stream);
+      if (rc.comm && api) api->CommDestroy(rc.comm);
+      for (auto& k : rc.pending) {
+        cudaEventDestroy(k.a);
+        cudaEventDestroy(k.b);
+      }
+      for (auto e : rc.pool) cudaEventDestroy(e);
+      for (auto& kv : rc.vec_cache) cudaFree(kv.second);
+      cudaFree(rc.d_partials);
+      cudaFree(rc.d_result);
+      cudaFreeHost(rc.h_result);
+      cudaEventDestroy(rc.ev);
+      cudaEventDestroy(rc.ev_fork);
+      cudaEventDestroy(rc.t0);
+      cudaEventDestroy(rc.t1);
+      cudaStreamDestroy(rc.stream);
+    }
+    delete ctx;
+  });
+}
+
+int32_t djets_ctx_sync(djets_ctx ctx) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      CK(cudaStreamSynchronize(rc.stream));
+    }
+  });
+}
+
+int32_t djets_ctx_info(djets_ctx ctx, int32_t* world, int32_t* nlocal, int32_t* has_nccl) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    if (world) *world = ctx->world;
+    if (nlocal) *nlocal = (int32_t)ctx->ranks.size();
+    if (has_nccl) *has_nccl = ctx->has_nccl ? 1 : 0;
+  });
+}
+
+int32_t djets_ctx_is_local(djets_ctx ctx, int32_t rank, int32_t* is_local) {
+  return guard([&] {
+    REQUIRE(ctx && is_local, DJETS_ERR_INVALID, "null argument");
+    *is_local = ctx->local(rank) ? 1 : 0;
+  });
+}
+
+int32_t djets_timer_start(djets_ctx ctx) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      CK(cudaEventRecord(rc.t0, rc.stream));
+    }
+  });
+}
+
+int32_t djets_timer_stop(djets_ctx ctx, float* ms) {
+  return guard([&] {
+    REQUIRE(ctx && ms, DJETS_ERR_INVALID, "null argument");
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      CK(cudaEventRecord(rc.t1, rc.stream));
+    }
+    float worst = 0.f;
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      CK(cudaEventSynchronize(rc.t1));
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, rc.t0, rc.t1));
+      worst = std::max(worst, t);
+    }
+    *ms = worst;
+  });
+}
+
+int32_t djets_ctx_kernel_timing(djets_ctx ctx, int32_t enable) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    if (!enable)
+      for (RankCtx& rc : ctx->ranks) drain_events(rc);
+    ctx->timing = enable != 0;
+  });
+}
+
+int32_t djets_ctx_kernel_stats(djets_ctx ctx, int32_t kind, int64_t* launches, double* total_ms) {
+  return guard([&] {
+    REQUIRE(ctx && kind >= 0 && kind < DJETS_K_COUNT, DJETS_ERR_INVALID, "kernel_stats: bad arguments");
+    int64_t n = 0;
+    double ms = 0.0;
+    for (RankCtx& rc : ctx->ranks) {
+      drain_events(rc);
+      n += rc.launches[kind];
+      ms = std::max(ms, rc.ms[kind]);
+    }
+    if (launches) *launches = n;
+    if (total_ms) *total_ms = ms;
+  });
+}
+
+int32_t djets_ctx_reset_stats(djets_ctx ctx) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    for (RankCtx& rc : ctx->ranks) {
+      drain_events(rc);
+      for (int k = 0; k < DJETS_K_COUNT; ++k) {
+        rc.launches[k] = 0;
+        rc.ms[k] = 0.0;
+      }
+    }
+  });
+}
+
+int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
+  return guard([&] {
+    REQUIRE(ctx && name, DJETS_ERR_INVALID, "null argument");
+    const std::string n(name);
+    if (n == "fwd_tx") {
+      REQUIRE(value == 32 || value == 64 || value == 128 || value == 256, DJETS_ERR_INVALID, "fwd_tx in {32,64,128,256}");
+      ctx->fwd_tx = value;
+    } else if (n == "fwd_tc") {
+      REQUIRE(value >= 1 && value <= kFwdMaxTC, DJETS_ERR_INVALID, "fwd_tc in 1..1024");
+      ctx->fwd_tc = value;
+    } else if (n == "adj_ru") {
+      REQUIRE(value == 1 || value == 2 || value == 4, DJETS_ERR_INVALID, "adj_ru in {1,2,4}");
+      ctx->adj_ru = value;
+    } else if (n == "adj_tc") {
+      REQUIRE(value >= kAdjCW && value <= 4096, DJETS_ERR_INVALID, "adj_tc in 4..4096");
+      ctx->adj_tc = value;
+    } else if (n == "ld_policy") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "ld_policy in {0,1}");
+      ctx->ld_policy = value;
+    } else if (n == "pdl") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "pdl in {0,1}");
+      set_pdl((int)value);
+    } else if (n == "auto_tile") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "auto_tile in {0,1}");
+      ctx->auto_tile = value;
+    } else if (n == "p2p") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "p2p in {0,1}");
+      ctx->p2p = value;
+    } else if (n == "graphs") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "graphs in {0,1}");
+      ctx->graphs = value;
+    } else {
+      fail(DJETS_ERR_INVALID, "unknown parameter " + n);
+    }
+  });
+}
+
+}  // extern "C"

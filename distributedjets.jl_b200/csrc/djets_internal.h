@@ -1,0 +1,176 @@
+// Internal declarations shared by the host-side translation units of libdjets_b200
+// (djets_ctx.cu: contexts, timers, tuning; djets_vec.cu: DBArray; djets_op.cu: the distributed block
+// operator).  Nothing here is part of the ABI: include/djets.h is.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <exception>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/djets.h"
+#include "djets_kernels.h"
+#include "djets_nccl.h"
+
+namespace djets {
+
+// ---- errors ---------------------------------------------------------------------------------------
+extern thread_local std::string g_last_error;
+// One lock for the whole ABI: the contract is one calling thread per context, but *_destroy may
+// arrive from a finalizer thread (Julia GC) while the master thread is inside another call.
+extern std::recursive_mutex g_api_mutex;
+
+struct Err {
+  int code;
+  std::string msg;
+};
+
+[[noreturn]] inline void fail(int code, const std::string& msg) { throw Err{code, msg}; }
+
+#define CK(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      ::djets::fail(DJETS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorName(e__) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+#define NCK(api, expr)                                                                    \
+  do {                                                                                    \
+    ncclResult_t r__ = (expr);                                                            \
+    if (r__ != ncclSuccess) ::djets::fail(DJETS_ERR_NCCL, std::string(#expr) + ": " + (api)->GetErrorString(r__)); \
+  } while (0)
+
+#define REQUIRE(cond, code, msg)          \
+  do {                                    \
+    if (!(cond)) ::djets::fail(code, msg); \
+  } while (0)
+
+// Every extern "C" entry point runs inside guard(): no C++ exception crosses the ABI.
+template <class F>
+int32_t guard(F&& f) {
+  std::lock_guard<std::recursive_mutex> api_lock(g_api_mutex);
+  try {
+    f();
+    return DJETS_OK;
+  } catch (const Err& e) {
+    g_last_error = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = std::string("internal: ") + e.what();
+    return DJETS_ERR_INVALID;
+  } catch (...) {
+    g_last_error = "internal: unknown exception";
+    return DJETS_ERR_INVALID;
+  }
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+constexpr int kMaxParts = 1024;
+
+}  // namespace djets
+
+// ---- context --------------------------------------------------------------------------------------
+struct KernelEvent {
+  int kind;
+  cudaEvent_t a, b;
+};
+
+struct RankCtx {
+  int rank = -1, device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev = nullptr;  // scratch event for cross-stream ordering
+  cudaEvent_t ev_fork = nullptr;  // fork / join of a captured apply
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  double* d_partials = nullptr;  // reduce stage-1 partials
+  double* d_result = nullptr;    // 2*kMaxParts doubles: per-part results, then the all-reduce buffer
+  double* h_result = nullptr;    // pinned mirror
+  ncclComm_t comm = nullptr;
+  int64_t launches[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
+  double ms[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
+  std::vector<KernelEvent> pending;
+  std::vector<cudaEvent_t> pool;
+  // Stream-ordered cache of vector-part allocations: a freed part is handed to the next DBArray of the
+  // same size on this rank without a device synchronisation (the reference's non-dotted arithmetic
+  // allocates a fresh DBArray per operation, src:353-356, so allocation has to be cheap).
+  std::multimap<size_t, char*> vec_cache;
+  size_t vec_cache_bytes = 0;
+};
+
+struct djets_ctx_s {
+  int world = 0;
+  std::vector<RankCtx> ranks;
+  std::vector<int> local_of_rank;
+  bool has_nccl = false;
+  bool timing = false;
+  int64_t fwd_tx = 64, fwd_tc = 512, adj_ru = 4, adj_tc = 64, ld_policy = 1;
+  int64_t auto_tile = 1;  // shrink tiles of small operators so a launch still fills the SMs
+  int64_t graphs = 1;  // replay multi-launch applies as CUDA graphs
+  int64_t p2p = 1;     // kernels of one rank read / write another local rank's buffers in place
+  std::vector<char> peer;  // peer[a * ndev + b]: device a can address device b's memory
+  int ndev = 0;
+  bool can_address(const RankCtx& a, const RankCtx& b) const {
+    return a.device == b.device || peer[(size_t)a.device * ndev + b.device];
+  }
+
+  RankCtx* local(int rank) {
+    if (rank < 0 || rank >= world) return nullptr;
+    const int l = local_of_rank[rank];
+    return l < 0 ? nullptr : &ranks[l];
+  }
+};
+
+namespace djets {
+
+void use(RankCtx& rc);
+cudaEvent_t pool_event(RankCtx& rc);
+void drain_events(RankCtx& rc);
+void stream_after(RankCtx& src, RankCtx& dst);  // dst stream waits for everything enqueued so far on src stream
+
+template <class F>
+void launch_counted(djets_ctx ctx, RankCtx& rc, int kind, F&& f) {
+  rc.launches[kind] += 1;
+  if (ctx->timing) {
+    if (rc.pending.size() > 200000) drain_events(rc);
+    KernelEvent k{kind, pool_event(rc), pool_event(rc)};
+    CK(cudaEventRecord(k.a, rc.stream));
+    CK(f());
+    CK(cudaEventRecord(k.b, rc.stream));
+    rc.pending.push_back(k);
+  } else {
+    CK(f());
+  }
+}
+
+}  // namespace djets
+
+// ---- DBArray --------------------------------------------------------------------------------------
+struct VecPart {
+  int rank = 0;
+  int64_t blk_first = 0, blk_count = 0, elem_first = 0, elem_count = 0;
+  char* d = nullptr;  // device storage on the owner (nullptr when the owner is another process)
+  size_t cap = 0;     // allocated bytes
+};
+
+struct djets_vec_s {
+  djets_ctx ctx = nullptr;
+  int dtype = 0;
+  std::vector<VecPart> parts;
+  std::vector<int64_t> block_len, block_off;  // block_off: global element offset, nblocks+1 entries
+  std::vector<int> block_part;
+  int64_t length = 0;
+};
+
+namespace djets {
+
+djets_vec make_vec(djets_ctx ctx, int dtype, int nparts, const int32_t* part_rank, const int64_t* part_nblocks,
+                   const int64_t* block_len);
+
+}  // namespace djets

@@ -1,5 +1,5 @@
 // Device-side work descriptors and launcher prototypes shared by the host scheduler
-// (djets_api.cu) and the sm_100a kernels (djets_kernels.cu).
+// (djets_ctx.cu, djets_vec.cu, djets_op.cu) and the sm_100a kernels (djets_kernels.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

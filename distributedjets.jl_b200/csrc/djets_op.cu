@@ -1,438 +1,8 @@
-// Host side of libdjets_b200: contexts (one rank = one GPU = one former Distributed.jl worker),
-// device-resident DBArrays, the distributed block operator with its tile schedules, the
-// cross-rank exchange and the C ABI of include/djets.h.  See DESIGN.md for the layout.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <string.h>
-
-#include <algorithm>
-#include <exception>
-#include <map>
-#include <memory>
-#include <mutex>
-#include <string>
-#include <vector>
-
-#include "../../include/djets.h"
-#include "djets_kernels.h"
-#include "djets_nccl.h"
+// The distributed block operator of libdjets_b200 (reference: src/DistributedJets.jl:414-721, 805-861):
+// block payloads, tile schedules, the cross-rank exchange, CUDA-graph replay, and its C ABI.
+#include "djets_internal.h"
 
 using namespace djets;
-
-// ---- errors ---------------------------------------------------------------------------------------
-namespace {
-
-thread_local std::string g_last_error;
-
-struct Err {
-  int code;
-  std::string msg;
-};
-
-[[noreturn]] void fail(int code, const std::string& msg) { throw Err{code, msg}; }
-
-#define CK(expr)                                                                                      \
-  do {                                                                                                \
-    cudaError_t e__ = (expr);                                                                         \
-    if (e__ != cudaSuccess)                                                                           \
-      fail(DJETS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorName(e__) + ": " + cudaGetErrorString(e__)); \
-  } while (0)
-
-#define NCK(api, expr)                                                                    \
-  do {                                                                                    \
-    ncclResult_t r__ = (expr);                                                            \
-    if (r__ != ncclSuccess) fail(DJETS_ERR_NCCL, std::string(#expr) + ": " + (api)->GetErrorString(r__)); \
-  } while (0)
-
-#define REQUIRE(cond, code, msg) \
-  do {                           \
-    if (!(cond)) fail(code, msg); \
-  } while (0)
-
-// One lock for the whole ABI: the contract is one calling thread per context, but *_destroy may
-// arrive from a finalizer thread (Julia GC) while the master thread is inside another call.
-std::recursive_mutex g_api_mutex;
-
-template <class F>
-int32_t guard(F&& f) {
-  std::lock_guard<std::recursive_mutex> api_lock(g_api_mutex);
-  try {
-    f();
-    return DJETS_OK;
-  } catch (const Err& e) {
-    g_last_error = e.msg;
-    return e.code;
-  } catch (const std::exception& e) {
-    g_last_error = std::string("internal: ") + e.what();
-    return DJETS_ERR_INVALID;
-  } catch (...) {
-    g_last_error = "internal: unknown exception";
-    return DJETS_ERR_INVALID;
-  }
-}
-
-inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
-inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
-
-constexpr int kMaxParts = 1024;
-
-}  // namespace
-
-// ---- context --------------------------------------------------------------------------------------
-struct KernelEvent {
-  int kind;
-  cudaEvent_t a, b;
-};
-
-struct RankCtx {
-  int rank = -1, device = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev = nullptr;  // scratch event for cross-stream ordering
-  cudaEvent_t ev_fork = nullptr;  // fork / join of a captured apply
-  cudaEvent_t t0 = nullptr, t1 = nullptr;
-  double* d_partials = nullptr;  // reduce stage-1 partials
-  double* d_result = nullptr;    // 2*kMaxParts doubles: per-part results, then the all-reduce buffer
-  double* h_result = nullptr;    // pinned mirror
-  ncclComm_t comm = nullptr;
-  int64_t launches[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
-  double ms[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
-  std::vector<KernelEvent> pending;
-  std::vector<cudaEvent_t> pool;
-  // Stream-ordered cache of vector-part allocations: a freed part is handed to the next DBArray of the
-  // same size on this rank without a device synchronisation (the reference's non-dotted arithmetic
-  // allocates a fresh DBArray per operation, src:353-356, so allocation has to be cheap).
-  std::multimap<size_t, char*> vec_cache;
-  size_t vec_cache_bytes = 0;
-};
-
-struct djets_ctx_s {
-  int world = 0;
-  std::vector<RankCtx> ranks;
-  std::vector<int> local_of_rank;
-  bool has_nccl = false;
-  bool timing = false;
-  int64_t fwd_tx = 64, fwd_tc = 512, adj_ru = 4, adj_tc = 64, ld_policy = 1;
-  int64_t auto_tile = 1;  // shrink tiles of small operators so a launch still fills the SMs
-  int64_t graphs = 1;  // replay multi-launch applies as CUDA graphs
-  int64_t p2p = 1;     // kernels of one rank read / write another local rank's buffers in place
-  std::vector<char> peer;  // peer[a * ndev + b]: device a can address device b's memory
-  int ndev = 0;
-  bool can_address(const RankCtx& a, const RankCtx& b) const {
-    return a.device == b.device || peer[(size_t)a.device * ndev + b.device];
-  }
-
-  RankCtx* local(int rank) {
-    if (rank < 0 || rank >= world) return nullptr;
-    const int l = local_of_rank[rank];
-    return l < 0 ? nullptr : &ranks[l];
-  }
-};
-
-namespace {
-
-void use(RankCtx& rc) { CK(cudaSetDevice(rc.device)); }
-
-cudaEvent_t pool_event(RankCtx& rc) {
-  if (!rc.pool.empty()) {
-    cudaEvent_t e = rc.pool.back();
-    rc.pool.pop_back();
-    return e;
-  }
-  cudaEvent_t e;
-  CK(cudaEventCreate(&e));
-  return e;
-}
-
-void drain_events(RankCtx& rc) {
-  if (rc.pending.empty()) return;
-  use(rc);
-  CK(cudaStreamSynchronize(rc.stream));
-  for (auto& k : rc.pending) {
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, k.a, k.b));
-    rc.ms[k.kind] += ms;
-    rc.pool.push_back(k.a);
-    rc.pool.push_back(k.b);
-  }
-  rc.pending.clear();
-}
-
-template <class F>
-void launch_counted(djets_ctx ctx, RankCtx& rc, int kind, F&& f) {
-  rc.launches[kind] += 1;
-  if (ctx->timing) {
-    if (rc.pending.size() > 200000) drain_events(rc);
-    KernelEvent k{kind, pool_event(rc), pool_event(rc)};
-    CK(cudaEventRecord(k.a, rc.stream));
-    CK(f());
-    CK(cudaEventRecord(k.b, rc.stream));
-    rc.pending.push_back(k);
-  } else {
-    CK(f());
-  }
-}
-
-// dst stream waits for everything enqueued so far on src stream
-void stream_after(RankCtx& src, RankCtx& dst) {
-  if (&src == &dst) return;
-  use(src);
-  CK(cudaEventRecord(src.ev, src.stream));
-  use(dst);
-  CK(cudaStreamWaitEvent(dst.stream, src.ev, 0));
-}
-
-struct Transfer {
-  int src_rank;
-  const char* src;
-  int dst_rank;
-  char* dst;
-  size_t bytes;
-};
-
-// One exchange phase: local->local pairs are device copies ordered with events; pairs with one end
-// in another process go through ncclSend/ncclRecv inside one group.
-void run_transfers(djets_ctx ctx, const std::vector<Transfer>& ts) {
-  if (ts.empty()) return;
-  const NcclApi* api = nullptr;
-  bool grouped = false;
-  for (const Transfer& t : ts) {
-    if (t.bytes == 0) continue;
-    RankCtx* s = ctx->local(t.src_rank);
-    RankCtx* d = ctx->local(t.dst_rank);
-    if (s && d) {
-      stream_after(*d, *s);  // destination buffer is free once d's earlier work is done
-      use(*s);
-      if (s->device == d->device)
-        CK(cudaMemcpyAsync(t.dst, t.src, t.bytes, cudaMemcpyDeviceToDevice, s->stream));
-      else
-        CK(cudaMemcpyPeerAsync(t.dst, d->device, t.src, s->device, t.bytes, s->stream));
-      stream_after(*s, *d);
-    } else if (s || d) {
-      REQUIRE(ctx->has_nccl, DJETS_ERR_NCCL,
-              "exchange with a rank of another process needs a context created with an NCCL unique id");
-      if (!api) {
-        const char* why = nullptr;
-        api = nccl_api(&why);
-        REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
-      }
-      if (!grouped) {
-        NCK(api, api->GroupStart());
-        grouped = true;
-      }
-      if (s) {
-        use(*s);
-        NCK(api, api->Send(t.src, t.bytes, ncclChar, t.dst_rank, s->comm, s->stream));
-      } else {
-        use(*d);
-        NCK(api, api->Recv(t.dst, t.bytes, ncclChar, t.src_rank, d->comm, d->stream));
-      }
-    }
-  }
-  if (grouped) NCK(api, api->GroupEnd());
-}
-
-}  // namespace
-
-// ---- DBArray --------------------------------------------------------------------------------------
-struct VecPart {
-  int rank = 0;
-  int64_t blk_first = 0, blk_count = 0, elem_first = 0, elem_count = 0;
-  char* d = nullptr;  // device storage on the owner (nullptr when the owner is another process)
-  size_t cap = 0;     // allocated bytes
-};
-
-namespace {
-
-constexpr size_t kVecCacheLimit = size_t(32) << 30;  // bytes kept per rank before freed parts go back to the driver
-
-char* part_alloc(RankCtx& rc, size_t bytes) {
-  auto it = rc.vec_cache.find(bytes);
-  if (it != rc.vec_cache.end()) {
-    char* p = it->second;
-    rc.vec_cache.erase(it);
-    rc.vec_cache_bytes -= bytes;
-    return p;  // every earlier use was ordered before the free on this rank's stream
-  }
-  char* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytes);
-  if (e == cudaErrorMemoryAllocation && !rc.vec_cache.empty()) {  // give the cache back and retry
-    (void)cudaGetLastError();
-    CK(cudaStreamSynchronize(rc.stream));
-    for (auto& kv : rc.vec_cache) cudaFree(kv.second);
-    rc.vec_cache.clear();
-    rc.vec_cache_bytes = 0;
-    e = cudaMalloc(&p, bytes);
-  }
-  CK(e);
-  return p;
-}
-
-void part_free(RankCtx& rc, char* p, size_t bytes) {
-  if (rc.vec_cache_bytes + bytes > kVecCacheLimit) {
-    cudaStreamSynchronize(rc.stream);
-    cudaFree(p);
-    return;
-  }
-  rc.vec_cache.emplace(bytes, p);
-  rc.vec_cache_bytes += bytes;
-}
-
-}  // namespace
-
-struct djets_vec_s {
-  djets_ctx ctx = nullptr;
-  int dtype = 0;
-  std::vector<VecPart> parts;
-  std::vector<int64_t> block_len, block_off;  // block_off: global element offset, nblocks+1 entries
-  std::vector<int> block_part;
-  int64_t length = 0;
-};
-
-namespace {
-
-djets_vec make_vec(djets_ctx ctx, int dtype, int nparts, const int32_t* part_rank, const int64_t* part_nblocks,
-                   const int64_t* block_len) {
-  REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
-  REQUIRE(dtype == DJETS_F32 || dtype == DJETS_F64, DJETS_ERR_INVALID, "dtype must be DJETS_F32 or DJETS_F64");
-  REQUIRE(nparts >= 1 && nparts <= kMaxParts, DJETS_ERR_INVALID, "nparts out of range");
-  auto v = std::make_unique<djets_vec_s>();
-  v->ctx = ctx;
-  v->dtype = dtype;
-  int64_t nblocks = 0;
-  for (int p = 0; p < nparts; ++p) {
-    REQUIRE(part_nblocks[p] >= 0, DJETS_ERR_INVALID, "negative block count");
-    REQUIRE(part_rank[p] >= 0 && part_rank[p] < ctx->world, DJETS_ERR_INVALID, "part rank outside the job");
-    nblocks += part_nblocks[p];
-  }
-  v->block_len.assign(block_len, block_len + nblocks);
-  v->block_off.resize(nblocks + 1);
-  v->block_part.resize(nblocks);
-  v->block_off[0] = 0;
-  for (int64_t b = 0; b < nblocks; ++b) {
-    REQUIRE(block_len[b] >= 0, DJETS_ERR_INVALID, "negative block length");
-    v->block_off[b + 1] = v->block_off[b] + block_len[b];
-  }
-  v->length = v->block_off[nblocks];
-  v->parts.resize(nparts);
-  int64_t b0 = 0;
-  const int es = elem_size(dtype);
-  for (int p = 0; p < nparts; ++p) {
-    VecPart& part = v->parts[p];
-    part.rank = part_rank[p];
-    part.blk_first = b0;
-    part.blk_count = part_nblocks[p];
-    part.elem_first = v->block_off[b0];
-    part.elem_count = v->block_off[b0 + part.blk_count] - part.elem_first;
-    for (int64_t b = b0; b < b0 + part.blk_count; ++b) v->block_part[b] = p;
-    b0 += part.blk_count;
-    if (RankCtx* rc = ctx->local(part.rank)) {
-      use(*rc);
-      const size_t bytes = (size_t)round_up(part.elem_count * es + 256, 512);  // slack for 16-byte over-reads
-      part.d = part_alloc(*rc, bytes);
-      part.cap = bytes;
-      CK(cudaMemsetAsync(part.d, 0, bytes, rc->stream));
-    }
-  }
-  return v.release();
-}
-
-void free_vec(djets_vec v) {
-  if (!v) return;
-  for (VecPart& p : v->parts) {
-    if (!p.d) continue;
-    if (RankCtx* rc = v->ctx->local(p.rank)) {
-      cudaSetDevice(rc->device);
-      part_free(*rc, p.d, p.cap);
-    }
-  }
-  delete v;
-}
-
-bool same_layout(djets_vec a, djets_vec b) {
-  if (a->ctx != b->ctx || a->parts.size() != b->parts.size() || a->block_len != b->block_len) return false;
-  for (size_t p = 0; p < a->parts.size(); ++p)
-    if (a->parts[p].rank != b->parts[p].rank || a->parts[p].blk_count != b->parts[p].blk_count) return false;
-  return true;
-}
-
-double round_to(int dtype, double v) { return dtype == DJETS_F32 ? (double)(float)v : v; }
-
-// Per-part partial reductions: one result per part in out_parts (all parts, after the cross-process
-// exchange when some parts live elsewhere).
-void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_parts) {
-  djets_ctx ctx = x->ctx;
-  const int np = (int)x->parts.size();
-  bool any_remote = false;
-  for (RankCtx& rc : ctx->ranks) {
-    use(rc);
-    CK(cudaMemsetAsync(rc.d_result, 0, sizeof(double) * np, rc.stream));
-  }
-  for (int p = 0; p < np; ++p) {
-    VecPart& part = x->parts[p];
-    RankCtx* rc = ctx->local(part.rank);
-    if (!rc) {
-      any_remote = true;
-      continue;
-    }
-    use(*rc);
-    const void* yp = y ? y->parts[p].d : nullptr;
-    launch_counted(ctx, *rc, DJETS_K_REDUCE, [&] {
-      return launch_reduce(x->dtype, kind, part.d, yp, part.elem_count, param, rc->d_partials, rc->d_result + p,
-                           rc->stream);
-    });
-  }
-  // Every process of a multi-process job makes the same calls, so the decision to exchange must not
-  // depend on which parts happen to be local: with NCCL up, always all-reduce.
-  const bool multi_process = (int)ctx->ranks.size() < ctx->world;
-  if (multi_process && ctx->has_nccl) {
-    const char* why = nullptr;
-    const NcclApi* api = nccl_api(&why);
-    REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
-    // every rank contributes its own parts and zeros elsewhere: the sum is exact
-    NCK(api, api->GroupStart());
-    for (RankCtx& rc : ctx->ranks) {
-      use(rc);
-      NCK(api, api->AllReduce(rc.d_result, rc.d_result, np, ncclDouble, ncclSum, rc.comm, rc.stream));
-    }
-    NCK(api, api->GroupEnd());
-  } else {
-    REQUIRE(!any_remote, DJETS_ERR_NCCL, "vector has parts in other processes but the context has no NCCL");
-  }
-  for (RankCtx& rc : ctx->ranks) {
-    use(rc);
-    CK(cudaMemcpyAsync(rc.h_result, rc.d_result, sizeof(double) * np, cudaMemcpyDeviceToHost, rc.stream));
-  }
-  for (RankCtx& rc : ctx->ranks) {
-    use(rc);
-    CK(cudaStreamSynchronize(rc.stream));
-  }
-  for (int p = 0; p < np; ++p) {
-    RankCtx* rc = ctx->local(x->parts[p].rank);
-    out_parts[p] = rc ? rc->h_result[p] : ctx->ranks[0].h_result[p];
-  }
-}
-
-bool kind_is_min(int kind) { return kind == DJETS_RED_MIN || kind == DJETS_RED_ABSMIN; }
-bool kind_is_max(int kind) { return kind == DJETS_RED_MAX || kind == DJETS_RED_ABSMAX; }
-
-// master-side fold over the per-worker partials in the element type (src:222, 236, 249, 262, 276)
-double fold_parts(int dtype, int kind, const double* z, int np) {
-  if (kind_is_min(kind)) {
-    double m = INFINITY;
-    for (int p = 0; p < np; ++p) m = fmin(m, round_to(dtype, z[p]));
-    return m;
-  }
-  if (kind_is_max(kind)) {
-    double m = -INFINITY;
-    for (int p = 0; p < np; ++p) m = fmax(m, round_to(dtype, z[p]));
-    return m;
-  }
-  double s = 0.0;
-  for (int p = 0; p < np; ++p) s = round_to(dtype, s + round_to(dtype, z[p]));
-  return s;
-}
-
-}  // namespace
 
 // ---- distributed block operator -------------------------------------------------------------------
 struct Block {
@@ -503,6 +73,57 @@ struct djets_op_s {
 };
 
 namespace {
+
+struct Transfer {
+  int src_rank;
+  const char* src;
+  int dst_rank;
+  char* dst;
+  size_t bytes;
+};
+
+// One exchange phase: local->local pairs are device copies ordered with events; pairs with one end
+// in another process go through ncclSend/ncclRecv inside one group.
+void run_transfers(djets_ctx ctx, const std::vector<Transfer>& ts) {
+  if (ts.empty()) return;
+  const NcclApi* api = nullptr;
+  bool grouped = false;
+  for (const Transfer& t : ts) {
+    if (t.bytes == 0) continue;
+    RankCtx* s = ctx->local(t.src_rank);
+    RankCtx* d = ctx->local(t.dst_rank);
+    if (s && d) {
+      stream_after(*d, *s);  // destination buffer is free once d's earlier work is done
+      use(*s);
+      if (s->device == d->device)
+        CK(cudaMemcpyAsync(t.dst, t.src, t.bytes, cudaMemcpyDeviceToDevice, s->stream));
+      else
+        CK(cudaMemcpyPeerAsync(t.dst, d->device, t.src, s->device, t.bytes, s->stream));
+      stream_after(*s, *d);
+    } else if (s || d) {
+      REQUIRE(ctx->has_nccl, DJETS_ERR_NCCL,
+              "exchange with a rank of another process needs a context created with an NCCL unique id");
+      if (!api) {
+        const char* why = nullptr;
+        api = nccl_api(&why);
+        REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
+      }
+      if (!grouped) {
+        NCK(api, api->GroupStart());
+        grouped = true;
+      }
+      if (s) {
+        use(*s);
+        NCK(api, api->Send(t.src, t.bytes, ncclChar, t.dst_rank, s->comm, s->stream));
+      } else {
+        use(*d);
+        NCK(api, api->Recv(t.dst, t.bytes, ncclChar, t.src_rank, d->comm, d->stream));
+      }
+    }
+  }
+  if (grouped) NCK(api, api->GroupEnd());
+}
+
 
 void free_plan(DirPlan& p) {
   cudaFree(p.d_tiles);
@@ -1092,31 +713,7 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
 
 }  // namespace
 
-// ===================================================================================================
-// C ABI
-// ===================================================================================================
 extern "C" {
-
-int32_t djets_version(void) { return 100; }
-const char* djets_last_error(void) { return g_last_error.c_str(); }
-
-int32_t djets_even_cuts(int64_t n, int32_t nparts, int64_t* cuts) {
-  return guard([&] {
-    REQUIRE(n >= 0 && nparts >= 1 && cuts, DJETS_ERR_INVALID, "even_cuts: bad arguments");
-    const int64_t q = n / nparts, rem = n % nparts;
-    cuts[0] = 0;
-    for (int k = 0; k < nparts; ++k) cuts[k + 1] = cuts[k] + q + (k < rem ? 1 : 0);
-  });
-}
-
-int32_t djets_grid_rank(int32_t n1, int32_t n2, int32_t r, int32_t c, const int32_t* grid_ranks, int32_t* rank) {
-  return guard([&] {
-    REQUIRE(n1 >= 1 && n2 >= 1 && r >= 0 && r < n1 && c >= 0 && c < n2 && rank, DJETS_ERR_INVALID,
-            "grid_rank: bad arguments");
-    const int idx = r + c * n1;
-    *rank = grid_ranks ? grid_ranks[idx] : idx;
-  });
-}
 
 int32_t djets_plan_tiles(int32_t dtype, int64_t m, int64_t n, int32_t adjoint, int64_t* tile_rows, int64_t* tile_cols,
                          int64_t* ntiles) {
@@ -1147,524 +744,6 @@ int32_t djets_plan_exchange(int32_t n1, int32_t n2, int32_t isdiag, int32_t adjo
   });
 }
 
-int32_t djets_device_count(int32_t* n) {
-  return guard([&] {
-    int c = 0;
-    CK(cudaGetDeviceCount(&c));
-    *n = c;
-  });
-}
-
-int32_t djets_nccl_unique_id(uint8_t* out128) {
-  return guard([&] {
-    const char* why = nullptr;
-    const NcclApi* api = nccl_api(&why);
-    REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
-    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
-    ncclUniqueId id;
-    NCK(api, api->GetUniqueId(&id));
-    memcpy(out128, &id, 128);
-  });
-}
-
-int32_t djets_host_alloc(int64_t bytes, void** out) {
-  return guard([&] {
-    REQUIRE(bytes >= 0 && out, DJETS_ERR_INVALID, "host_alloc: bad arguments");
-    CK(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable));
-  });
-}
-int32_t djets_host_free(void* p) {
-  return guard([&] {
-    if (p) CK(cudaFreeHost(p));
-  });
-}
-
-int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ranks, const int32_t* device_ids,
-                         const uint8_t* nccl_uid, djets_ctx* out) {
-  return guard([&] {
-    REQUIRE(out, DJETS_ERR_INVALID, "ctx_create: null out");
-    REQUIRE(world >= 1 && nlocal >= 1 && nlocal <= world, DJETS_ERR_INVALID, "ctx_create: bad world / nlocal");
-    int ndev = 0;
-    CK(cudaGetDeviceCount(&ndev));
-    REQUIRE(ndev > 0, DJETS_ERR_CUDA, "no CUDA device: libdjets_b200 has no CPU path");
-    auto ctx = std::make_unique<djets_ctx_s>();
-    ctx->world = world;
-    ctx->local_of_rank.assign(world, -1);
-    ctx->ranks.resize(nlocal);
-    for (int l = 0; l < nlocal; ++l) {
-      RankCtx& rc = ctx->ranks[l];
-      rc.rank = local_ranks ? local_ranks[l] : l;
-      rc.device = device_ids ? device_ids[l] : (l % ndev);
-      REQUIRE(rc.rank >= 0 && rc.rank < world && ctx->local_of_rank[rc.rank] < 0, DJETS_ERR_INVALID,
-              "ctx_create: bad or repeated local rank");
-      REQUIRE(rc.device >= 0 && rc.device < ndev, DJETS_ERR_INVALID, "ctx_create: device id out of range");
-      ctx->local_of_rank[rc.rank] = l;
-      use(rc);
-      cudaDeviceProp prop;
-      CK(cudaGetDeviceProperties(&prop, rc.device));
-      REQUIRE(prop.major >= 10, DJETS_ERR_CUDA,
-              std::string("device ") + prop.name + " is not sm_100-class: libdjets_b200 carries sm_100a code only");
-      CK(cudaStreamCreateWithFlags(&rc.stream, cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&rc.ev, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&rc.ev_fork, cudaEventDisableTiming));
-      CK(cudaEventCreate(&rc.t0));
-      CK(cudaEventCreate(&rc.t1));
-      CK(cudaMalloc(&rc.d_partials, sizeof(double) * reduce_max_ctas()));
-      CK(cudaMalloc(&rc.d_result, sizeof(double) * 2 * kMaxParts));
-      CK(cudaHostAlloc(&rc.h_result, sizeof(double) * 2 * kMaxParts, cudaHostAllocPortable));
-    }
-    // peer access between the GPUs this process drives: local->local exchange is in-place peer
-    // loads / stores from the kernels (or a peer copy when p2p is off)
-    ctx->ndev = ndev;
-    ctx->peer.assign((size_t)ndev * ndev, 0);
-    for (RankCtx& a : ctx->ranks)
-      for (RankCtx& b : ctx->ranks) {
-        if (a.device == b.device) continue;
-        int can = 0;
-        CK(cudaDeviceCanAccessPeer(&can, a.device, b.device));
-        if (can) {
-          use(a);
-          cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
-          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
-          (void)cudaGetLastError();
-          ctx->peer[(size_t)a.device * ndev + b.device] = 1;
-        }
-      }
-    if (nccl_uid) {
-      const char* why = nullptr;
-      const NcclApi* api = nccl_api(&why);
-      REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
-      ncclUniqueId id;
-      memcpy(&id, nccl_uid, 128);
-      NCK(api, api->GroupStart());
-      for (RankCtx& rc : ctx->ranks) {
-        use(rc);
-        NCK(api, api->CommInitRank(&rc.comm, world, id, rc.rank));
-      }
-      NCK(api, api->GroupEnd());
-      ctx->has_nccl = true;
-    }
-    *out = ctx.release();
-  });
-}
-
-int32_t djets_ctx_destroy(djets_ctx ctx) {
-  return guard([&] {
-    if (!ctx) return;
-    const NcclApi* api = ctx->has_nccl ? nccl_api(nullptr) : nullptr;
-    for (RankCtx& rc : ctx->ranks) {
-      cudaSetDevice(rc.device);
-      cudaStreamSynchronize(rc.stream);
-      if (rc.comm && api) api->CommDestroy(rc.comm);
-      for (auto& k : rc.pending) {
-        cudaEventDestroy(k.a);
-        cudaEventDestroy(k.b);
-      }
-      for (auto e : rc.pool) cudaEventDestroy(e);
-      for (auto& kv : rc.vec_cache) cudaFree(kv.second);
-      cudaFree(rc.d_partials);
-      cudaFree(rc.d_result);
-      cudaFreeHost(rc.h_result);
-      cudaEventDestroy(rc.ev);
-      cudaEventDestroy(rc.ev_fork);
-      cudaEventDestroy(rc.t0);
-      cudaEventDestroy(rc.t1);
-      cudaStreamDestroy(rc.stream);
-    }
-    delete ctx;
-  });
-}
-
-int32_t djets_ctx_sync(djets_ctx ctx) {
-  return guard([&] {
-    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
-    for (RankCtx& rc : ctx->ranks) {
-      use(rc);
-      CK(cudaStreamSynchronize(rc.stream));
-    }
-  });
-}
-
-int32_t djets_ctx_info(djets_ctx ctx, int32_t* world, int32_t* nlocal, int32_t* has_nccl) {
-  return guard([&] {
-    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
-    if (world) *world = ctx->world;
-    if (nlocal) *nlocal = (int32_t)ctx->ranks.size();
-    if (has_nccl) *has_nccl = ctx->has_nccl ? 1 : 0;
-  });
-}
-
-int32_t djets_ctx_is_local(djets_ctx ctx, int32_t rank, int32_t* is_local) {
-  return guard([&] {
-    REQUIRE(ctx && is_local, DJETS_ERR_INVALID, "null argument");
-    *is_local = ctx->local(rank) ? 1 : 0;
-  });
-}
-
-int32_t djets_timer_start(djets_ctx ctx) {
-  return guard([&] {
-    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
-    for (RankCtx& rc : ctx->ranks) {
-      use(rc);
-      CK(cudaEventRecord(rc.t0, rc.stream));
-    }
-  });
-}
-
-int32_t djets_timer_stop(djets_ctx ctx, float* ms) {
-  return guard([&] {
-    REQUIRE(ctx && ms, DJETS_ERR_INVALID, "null argument");
-    for (RankCtx& rc : ctx->ranks) {
-      use(rc);
-      CK(cudaEventRecord(rc.t1, rc.stream));
-    }
-    float worst = 0.f;
-    for (RankCtx& rc : ctx->ranks) {
-      use(rc);
-      CK(cudaEventSynchronize(rc.t1));
-      float t = 0.f;
-      CK(cudaEventElapsedTime(&t, rc.t0, rc.t1));
-      worst = std::max(worst, t);
-    }
-    *ms = worst;
-  });
-}
-
-int32_t djets_ctx_kernel_timing(djets_ctx ctx, int32_t enable) {
-  return guard([&] {
-    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
-    if (!enable)
-      for (RankCtx& rc : ctx->ranks) drain_events(rc);
-    ctx->timing = enable != 0;
-  });
-}
-
-int32_t djets_ctx_kernel_stats(djets_ctx ctx, int32_t kind, int64_t* launches, double* total_ms) {
-  return guard([&] {
-    REQUIRE(ctx && kind >= 0 && kind < DJETS_K_COUNT, DJETS_ERR_INVALID, "kernel_stats: bad arguments");
-    int64_t n = 0;
-    double ms = 0.0;
-    for (RankCtx& rc : ctx->ranks) {
-      drain_events(rc);
-      n += rc.launches[kind];
-      ms = std::max(ms, rc.ms[kind]);
-    }
-    if (launches) *launches = n;
-    if (total_ms) *total_ms = ms;
-  });
-}
-
-int32_t djets_ctx_reset_stats(djets_ctx ctx) {
-  return guard([&] {
-    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
-    for (RankCtx& rc : ctx->ranks) {
-      drain_events(rc);
-      for (int k = 0; k < DJETS_K_COUNT; ++k) {
-        rc.launches[k] = 0;
-        rc.ms[k] = 0.0;
-      }
-    }
-  });
-}
-
-int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
-  return guard([&] {
-    REQUIRE(ctx && name, DJETS_ERR_INVALID, "null argument");
-    const std::string n(name);
-    if (n == "fwd_tx") {
-      REQUIRE(value == 32 || value == 64 || value == 128 || value == 256, DJETS_ERR_INVALID, "fwd_tx in {32,64,128,256}");
-      ctx->fwd_tx = value;
-    } else if (n == "fwd_tc") {
-      REQUIRE(value >= 1 && value <= kFwdMaxTC, DJETS_ERR_INVALID, "fwd_tc in 1..1024");
-      ctx->fwd_tc = value;
-    } else if (n == "adj_ru") {
-      REQUIRE(value == 1 || value == 2 || value == 4, DJETS_ERR_INVALID, "adj_ru in {1,2,4}");
-      ctx->adj_ru = value;
-    } else if (n == "adj_tc") {
-      REQUIRE(value >= kAdjCW && value <= 4096, DJETS_ERR_INVALID, "adj_tc in 4..4096");
-      ctx->adj_tc = value;
-    } else if (n == "ld_policy") {
-      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "ld_policy in {0,1}");
-      ctx->ld_policy = value;
-    } else if (n == "pdl") {
-      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "pdl in {0,1}");
-      set_pdl((int)value);
-    } else if (n == "auto_tile") {
-      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "auto_tile in {0,1}");
-      ctx->auto_tile = value;
-    } else if (n == "p2p") {
-      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "p2p in {0,1}");
-      ctx->p2p = value;
-    } else if (n == "graphs") {
-      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "graphs in {0,1}");
-      ctx->graphs = value;
-    } else {
-      fail(DJETS_ERR_INVALID, "unknown parameter " + n);
-    }
-  });
-}
-
-// ---- DBArray ------------------------------------------------------------------------------------------
-int32_t djets_vec_create(djets_ctx ctx, int32_t dtype, int32_t nparts, const int32_t* part_rank,
-                         const int64_t* part_nblocks, const int64_t* block_len, djets_vec* out) {
-  return guard([&] {
-    REQUIRE(out && part_rank && part_nblocks && block_len, DJETS_ERR_INVALID, "vec_create: null argument");
-    *out = make_vec(ctx, dtype, nparts, part_rank, part_nblocks, block_len);
-  });
-}
-
-int32_t djets_vec_similar(djets_vec x, int32_t dtype, djets_vec* out) {
-  return guard([&] {
-    REQUIRE(x && out, DJETS_ERR_INVALID, "vec_similar: null argument");
-    std::vector<int32_t> ranks;
-    std::vector<int64_t> nb;
-    for (VecPart& p : x->parts) {
-      ranks.push_back(p.rank);
-      nb.push_back(p.blk_count);
-    }
-    *out = make_vec(x->ctx, dtype, (int)x->parts.size(), ranks.data(), nb.data(), x->block_len.data());
-  });
-}
-
-int32_t djets_vec_destroy(djets_vec x) {
-  return guard([&] {
-    if (!x) return;
-    free_vec(x);
-  });
-}
-
-int32_t djets_vec_info(djets_vec x, int32_t* dtype, int64_t* length, int64_t* nblocks, int32_t* nparts) {
-  return guard([&] {
-    REQUIRE(x, DJETS_ERR_INVALID, "null vector");
-    if (dtype) *dtype = x->dtype;
-    if (length) *length = x->length;
-    if (nblocks) *nblocks = (int64_t)x->block_len.size();
-    if (nparts) *nparts = (int32_t)x->parts.size();
-  });
-}
-
-int32_t djets_vec_part_info(djets_vec x, int32_t part, int32_t* rank, int64_t* blk_first, int64_t* blk_count,
-                            int64_t* elem_first, int64_t* elem_count) {
-  return guard([&] {
-    REQUIRE(x && part >= 0 && part < (int)x->parts.size(), DJETS_ERR_INVALID, "part_info: bad part");
-    const VecPart& p = x->parts[part];
-    if (rank) *rank = p.rank;
-    if (blk_first) *blk_first = p.blk_first;
-    if (blk_count) *blk_count = p.blk_count;
-    if (elem_first) *elem_first = p.elem_first;
-    if (elem_count) *elem_count = p.elem_count;
-  });
-}
-
-int32_t djets_vec_block_info(djets_vec x, int64_t iblock, int32_t* part, int64_t* elem_first, int64_t* len) {
-  return guard([&] {
-    REQUIRE(x && iblock >= 0 && iblock < (int64_t)x->block_len.size(), DJETS_ERR_INVALID, "block index out of range");
-    if (part) *part = x->block_part[iblock];
-    if (elem_first) *elem_first = x->block_off[iblock];
-    if (len) *len = x->block_len[iblock];
-  });
-}
-
-static void block_copy(djets_vec x, int64_t iblock, void* host, bool to_device) {
-  REQUIRE(x && iblock >= 0 && iblock < (int64_t)x->block_len.size(), DJETS_ERR_INVALID, "block index out of range");
-  VecPart& p = x->parts[x->block_part[iblock]];
-  RankCtx* rc = x->ctx->local(p.rank);
-  if (!rc) {
-    if (to_device) return;  // setblock! on a process that does not drive the owner is a no-op
-    fail(DJETS_ERR_NOT_LOCAL, "getblock: block is owned by a rank of another process");
-  }
-  const int es = elem_size(x->dtype);
-  const size_t bytes = (size_t)x->block_len[iblock] * es;
-  if (bytes == 0) return;
-  REQUIRE(host, DJETS_ERR_INVALID, "null host pointer");
-  use(*rc);
-  char* d = p.d + (size_t)(x->block_off[iblock] - p.elem_first) * es;
-  if (to_device)
-    CK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, rc->stream));
-  else
-    CK(cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, rc->stream));
-  CK(cudaStreamSynchronize(rc->stream));
-}
-
-int32_t djets_vec_setblock(djets_vec x, int64_t iblock, const void* host_src) {
-  return guard([&] { block_copy(x, iblock, const_cast<void*>(host_src), true); });
-}
-int32_t djets_vec_getblock(djets_vec x, int64_t iblock, void* host_dst) {
-  return guard([&] { block_copy(x, iblock, host_dst, false); });
-}
-
-int32_t djets_vec_getindex(djets_vec x, int64_t i, double* out) {
-  return guard([&] {
-    REQUIRE(x && out, DJETS_ERR_INVALID, "null argument");
-    REQUIRE(i >= 0 && i < x->length, DJETS_ERR_INVALID, "BoundsError: index outside the DBArray");
-    for (VecPart& p : x->parts) {
-      if (i < p.elem_first || i >= p.elem_first + p.elem_count) continue;  // findfirst(rng->i in rng) src:175
-      RankCtx* rc = x->ctx->local(p.rank);
-      REQUIRE(rc, DJETS_ERR_NOT_LOCAL, "getindex: element is owned by a rank of another process");
-      use(*rc);
-      const int es = elem_size(x->dtype);
-      double buf = 0.0;
-      CK(cudaMemcpyAsync(&buf, p.d + (size_t)(i - p.elem_first) * es, es, cudaMemcpyDeviceToHost, rc->stream));
-      CK(cudaStreamSynchronize(rc->stream));
-      if (x->dtype == DJETS_F32) {
-        float f;
-        memcpy(&f, &buf, 4);
-        *out = (double)f;
-      } else {
-        *out = buf;
-      }
-      return;
-    }
-    fail(DJETS_ERR_INVALID, "getindex: no part holds the index");
-  });
-}
-
-static void bulk_copy(djets_vec x, void* host, bool to_device) {
-  REQUIRE(x, DJETS_ERR_INVALID, "null vector");
-  REQUIRE(host || x->length == 0, DJETS_ERR_INVALID, "null host pointer");
-  const int es = elem_size(x->dtype);
-  for (VecPart& p : x->parts) {
-    RankCtx* rc = x->ctx->local(p.rank);
-    if (!rc || p.elem_count == 0) continue;
-    use(*rc);
-    char* h = reinterpret_cast<char*>(host) + (size_t)p.elem_first * es;
-    if (to_device)
-      CK(cudaMemcpyAsync(p.d, h, (size_t)p.elem_count * es, cudaMemcpyHostToDevice, rc->stream));
-    else
-      CK(cudaMemcpyAsync(h, p.d, (size_t)p.elem_count * es, cudaMemcpyDeviceToHost, rc->stream));
-  }
-  for (VecPart& p : x->parts)
-    if (RankCtx* rc = x->ctx->local(p.rank)) {
-      use(*rc);
-      CK(cudaStreamSynchronize(rc->stream));
-    }
-}
-
-int32_t djets_vec_collect(djets_vec x, void* host_dst) {
-  return guard([&] { bulk_copy(x, host_dst, false); });
-}
-int32_t djets_vec_scatter(djets_vec x, const void* host_src) {
-  return guard([&] { bulk_copy(x, const_cast<void*>(host_src), true); });
-}
-
-int32_t djets_vec_fill(djets_vec x, double a) {
-  return guard([&] {
-    REQUIRE(x, DJETS_ERR_INVALID, "null vector");
-    for (VecPart& p : x->parts) {
-      RankCtx* rc = x->ctx->local(p.rank);
-      if (!rc) continue;
-      use(*rc);
-      launch_counted(x->ctx, *rc, DJETS_K_ELTWISE,
-                     [&] { return launch_fill(x->dtype, p.d, a, p.elem_count, rc->stream); });
-    }
-  });
-}
-
-int32_t djets_vec_lincomb(djets_vec dest, int32_t nterms, const double* coef, const djets_vec* xs, int32_t flags) {
-  return guard([&] {
-    REQUIRE(dest && coef && xs, DJETS_ERR_INVALID, "lincomb: null argument");
-    REQUIRE(nterms >= 1 && nterms <= 4, DJETS_ERR_UNSUPPORTED, "lincomb: 1 to 4 terms");
-    for (int k = 0; k < nterms; ++k) {
-      REQUIRE(xs[k], DJETS_ERR_INVALID, "lincomb: null operand");
-      REQUIRE(same_layout(dest, xs[k]), DJETS_ERR_MISMATCH,
-              "DimensionMismatch: broadcast operands have different block layouts");
-    }
-    for (size_t p = 0; p < dest->parts.size(); ++p) {
-      VecPart& dp = dest->parts[p];
-      RankCtx* rc = dest->ctx->local(dp.rank);
-      if (!rc) continue;
-      use(*rc);
-      LincombArgs a;
-      a.nterms = nterms;
-      for (int k = 0; k < nterms; ++k) {
-        a.x[k] = xs[k]->parts[p].d;
-        a.coef[k] = coef[k];
-        a.xdtype[k] = xs[k]->dtype;
-      }
-      launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE,
-                     [&] { return launch_lincomb(dest->dtype, dp.d, a, dp.elem_count, flags & 1, rc->stream); });
-    }
-  });
-}
-
-int32_t djets_vec_binary(djets_vec dest, int32_t op, djets_vec a, djets_vec b) {
-  return guard([&] {
-    REQUIRE(dest && a && b, DJETS_ERR_INVALID, "binary: null argument");
-    REQUIRE(op == 0 || op == 1, DJETS_ERR_UNSUPPORTED, "binary: op 0 (.*) or 1 (./)");
-    REQUIRE(same_layout(dest, a) && same_layout(dest, b), DJETS_ERR_MISMATCH,
-            "DimensionMismatch: broadcast operands have different block layouts");
-    REQUIRE(dest->dtype == a->dtype && dest->dtype == b->dtype, DJETS_ERR_UNSUPPORTED,
-            "binary: operands must share the element type");
-    for (size_t p = 0; p < dest->parts.size(); ++p) {
-      VecPart& dp = dest->parts[p];
-      RankCtx* rc = dest->ctx->local(dp.rank);
-      if (!rc) continue;
-      use(*rc);
-      launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE, [&] {
-        return launch_binary(dest->dtype, op, dp.d, a->parts[p].d, b->parts[p].d, dp.elem_count, rc->stream);
-      });
-    }
-  });
-}
-
-int32_t djets_vec_reduce_parts(djets_vec x, int32_t kind, double param, double* out_parts) {
-  return guard([&] {
-    REQUIRE(x && out_parts, DJETS_ERR_INVALID, "reduce: null argument");
-    REQUIRE(kind >= 0 && kind <= DJETS_RED_SUMSQ_SHIFT, DJETS_ERR_INVALID, "reduce: unknown kind");
-    reduce_parts(x, nullptr, kind, param, out_parts);
-  });
-}
-
-int32_t djets_vec_reduce(djets_vec x, int32_t kind, double param, double* out) {
-  return guard([&] {
-    REQUIRE(x && out, DJETS_ERR_INVALID, "reduce: null argument");
-    REQUIRE(kind >= 0 && kind <= DJETS_RED_SUMSQ_SHIFT, DJETS_ERR_INVALID, "reduce: unknown kind");
-    std::vector<double> z(x->parts.size());
-    reduce_parts(x, nullptr, kind, param, z.data());
-    *out = fold_parts(x->dtype, kind, z.data(), (int)z.size());
-  });
-}
-
-int32_t djets_vec_dot(djets_vec x, djets_vec y, double* out) {
-  return guard([&] {
-    REQUIRE(x && y && out, DJETS_ERR_INVALID, "dot: null argument");
-    REQUIRE(same_layout(x, y), DJETS_ERR_MISMATCH, "DimensionMismatch: dot of DBArrays with different block layouts");
-    REQUIRE(x->dtype == y->dtype, DJETS_ERR_MISMATCH, "dot: element types differ (reference: MethodError, src:214)");
-    std::vector<double> z(x->parts.size());
-    reduce_parts(x, y, RED_DOT, 0.0, z.data());
-    *out = fold_parts(x->dtype, DJETS_RED_SUM, z.data(), (int)z.size());
-  });
-}
-
-int32_t djets_vec_norm(djets_vec x, double p, double* out) {
-  return guard([&] {
-    REQUIRE(x && out, DJETS_ERR_INVALID, "norm: null argument");
-    const int np = (int)x->parts.size();
-    const int dt = x->dtype;
-    std::vector<double> z(np);
-    if (p == INFINITY) {  // src:200-201
-      reduce_parts(x, nullptr, DJETS_RED_ABSMAX, 0.0, z.data());
-      *out = fold_parts(dt, DJETS_RED_MAX, z.data(), np);
-    } else if (p == -INFINITY) {  // src:202-203
-      reduce_parts(x, nullptr, DJETS_RED_ABSMIN, 0.0, z.data());
-      *out = fold_parts(dt, DJETS_RED_MIN, z.data(), np);
-    } else if (p == 0.0 || p == 1.0) {  // src:204-205
-      reduce_parts(x, nullptr, p == 0.0 ? DJETS_RED_NNZ : DJETS_RED_ABSSUM, 0.0, z.data());
-      *out = fold_parts(dt, DJETS_RED_SUM, z.data(), np);
-    } else {  // src:206-209: per-worker norms z, then (sum z^p)^(1/p) in float(real(T))
-      const double pp = round_to(dt, p);
-      reduce_parts(x, nullptr, p == 2.0 ? DJETS_RED_SUMSQ : DJETS_RED_SUMPOW, pp, z.data());
-      double s = 0.0;
-      for (int k = 0; k < np; ++k) {
-        const double zk = round_to(dt, p == 2.0 ? sqrt(z[k]) : pow(z[k], 1.0 / pp));
-        s = round_to(dt, s + round_to(dt, p == 2.0 ? zk * zk : pow(zk, pp)));
-      }
-      *out = round_to(dt, p == 2.0 ? sqrt(s) : pow(s, round_to(dt, 1.0 / pp)));
-    }
-  });
-}
-
-// ---- operator ---------------------------------------------------------------------------------------
 int32_t djets_op_create(djets_ctx ctx, int32_t dtype, int64_t nbrow, int64_t nbcol, const int64_t* row_len,
                         const int64_t* col_len, int32_t n1, int32_t n2, const int32_t* grid_ranks,
                         const int64_t* row_cuts, const int64_t* col_cuts, int32_t isdiag, djets_op* out) {

@@ -1,0 +1,458 @@
+// DBArray side of libdjets_b200 (reference: src/DistributedJets.jl:109-412): device-resident block
+// vectors, block access, reductions with the reference's master-side folds, closed-set broadcasting.
+#include "djets_internal.h"
+
+using namespace djets;
+
+namespace {
+
+
+constexpr size_t kVecCacheLimit = size_t(32) << 30;  // bytes kept per rank before freed parts go back to the driver
+
+char* part_alloc(RankCtx& rc, size_t bytes) {
+  auto it = rc.vec_cache.find(bytes);
+  if (it != rc.vec_cache.end()) {
+    char* p = it->second;
+    rc.vec_cache.erase(it);
+    rc.vec_cache_bytes -= bytes;
+    return p;  // every earlier use was ordered before the free on this rank's stream
+  }
+  char* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaErrorMemoryAllocation && !rc.vec_cache.empty()) {  // give the cache back and retry
+    (void)cudaGetLastError();
+    CK(cudaStreamSynchronize(rc.stream));
+    for (auto& kv : rc.vec_cache) cudaFree(kv.second);
+    rc.vec_cache.clear();
+    rc.vec_cache_bytes = 0;
+    e = cudaMalloc(&p, bytes);
+  }
+  CK(e);
+  return p;
+}
+
+void part_free(RankCtx& rc, char* p, size_t bytes) {
+  if (rc.vec_cache_bytes + bytes > kVecCacheLimit) {
+    cudaStreamSynchronize(rc.stream);
+    cudaFree(p);
+    return;
+  }
+  rc.vec_cache.emplace(bytes, p);
+  rc.vec_cache_bytes += bytes;
+}
+
+}  // namespace
+
+namespace djets {
+
+
+djets_vec make_vec(djets_ctx ctx, int dtype, int nparts, const int32_t* part_rank, const int64_t* part_nblocks,
+                   const int64_t* block_len) {
+  REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+  REQUIRE(dtype == DJETS_F32 || dtype == DJETS_F64, DJETS_ERR_INVALID, "dtype must be DJETS_F32 or DJETS_F64");
+  REQUIRE(nparts >= 1 && nparts <= kMaxParts, DJETS_ERR_INVALID, "nparts out of range");
+  auto v = std::make_unique<djets_vec_s>();
+  v->ctx = ctx;
+  v->dtype = dtype;
+  int64_t nblocks = 0;
+  for (int p = 0; p < nparts; ++p) {
+    REQUIRE(part_nblocks[p] >= 0, DJETS_ERR_INVALID, "negative block count");
+    REQUIRE(part_rank[p] >= 0 && part_rank[p] < ctx->world, DJETS_ERR_INVALID, "part rank outside the job");
+    nblocks += part_nblocks[p];
+  }
+  v->block_len.assign(block_len, block_len + nblocks);
+  v->block_off.resize(nblocks + 1);
+  v->block_part.resize(nblocks);
+  v->block_off[0] = 0;
+  for (int64_t b = 0; b < nblocks; ++b) {
+    REQUIRE(block_len[b] >= 0, DJETS_ERR_INVALID, "negative block length");
+    v->block_off[b + 1] = v->block_off[b] + block_len[b];
+  }
+  v->length = v->block_off[nblocks];
+  v->parts.resize(nparts);
+  int64_t b0 = 0;
+  const int es = elem_size(dtype);
+  for (int p = 0; p < nparts; ++p) {
+    VecPart& part = v->parts[p];
+    part.rank = part_rank[p];
+    part.blk_first = b0;
+    part.blk_count = part_nblocks[p];
+    part.elem_first = v->block_off[b0];
+    part.elem_count = v->block_off[b0 + part.blk_count] - part.elem_first;
+    for (int64_t b = b0; b < b0 + part.blk_count; ++b) v->block_part[b] = p;
+    b0 += part.blk_count;
+    if (RankCtx* rc = ctx->local(part.rank)) {
+      use(*rc);
+      const size_t bytes = (size_t)round_up(part.elem_count * es + 256, 512);  // slack for 16-byte over-reads
+      part.d = part_alloc(*rc, bytes);
+      part.cap = bytes;
+      CK(cudaMemsetAsync(part.d, 0, bytes, rc->stream));
+    }
+  }
+  return v.release();
+}
+
+}  // namespace djets
+
+namespace {
+
+void free_vec(djets_vec v) {
+  if (!v) return;
+  for (VecPart& p : v->parts) {
+    if (!p.d) continue;
+    if (RankCtx* rc = v->ctx->local(p.rank)) {
+      cudaSetDevice(rc->device);
+      part_free(*rc, p.d, p.cap);
+    }
+  }
+  delete v;
+}
+
+bool same_layout(djets_vec a, djets_vec b) {
+  if (a->ctx != b->ctx || a->parts.size() != b->parts.size() || a->block_len != b->block_len) return false;
+  for (size_t p = 0; p < a->parts.size(); ++p)
+    if (a->parts[p].rank != b->parts[p].rank || a->parts[p].blk_count != b->parts[p].blk_count) return false;
+  return true;
+}
+
+double round_to(int dtype, double v) { return dtype == DJETS_F32 ? (double)(float)v : v; }
+
+// Per-part partial reductions: one result per part in out_parts (all parts, after the cross-process
+// exchange when some parts live elsewhere).
+void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_parts) {
+  djets_ctx ctx = x->ctx;
+  const int np = (int)x->parts.size();
+  bool any_remote = false;
+  for (RankCtx& rc : ctx->ranks) {
+    use(rc);
+    CK(cudaMemsetAsync(rc.d_result, 0, sizeof(double) * np, rc.stream));
+  }
+  for (int p = 0; p < np; ++p) {
+    VecPart& part = x->parts[p];
+    RankCtx* rc = ctx->local(part.rank);
+    if (!rc) {
+      any_remote = true;
+      continue;
+    }
+    use(*rc);
+    const void* yp = y ? y->parts[p].d : nullptr;
+    launch_counted(ctx, *rc, DJETS_K_REDUCE, [&] {
+      return launch_reduce(x->dtype, kind, part.d, yp, part.elem_count, param, rc->d_partials, rc->d_result + p,
+                           rc->stream);
+    });
+  }
+  // Every process of a multi-process job makes the same calls, so the decision to exchange must not
+  // depend on which parts happen to be local: with NCCL up, always all-reduce.
+  const bool multi_process = (int)ctx->ranks.size() < ctx->world;
+  if (multi_process && ctx->has_nccl) {
+    const char* why = nullptr;
+    const NcclApi* api = nccl_api(&why);
+    REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
+    // every rank contributes its own parts and zeros elsewhere: the sum is exact
+    NCK(api, api->GroupStart());
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      NCK(api, api->AllReduce(rc.d_result, rc.d_result, np, ncclDouble, ncclSum, rc.comm, rc.stream));
+    }
+    NCK(api, api->GroupEnd());
+  } else {
+    REQUIRE(!any_remote, DJETS_ERR_NCCL, "vector has parts in other processes but the context has no NCCL");
+  }
+  for (RankCtx& rc : ctx->ranks) {
+    use(rc);
+    CK(cudaMemcpyAsync(rc.h_result, rc.d_result, sizeof(double) * np, cudaMemcpyDeviceToHost, rc.stream));
+  }
+  for (RankCtx& rc : ctx->ranks) {
+    use(rc);
+    CK(cudaStreamSynchronize(rc.stream));
+  }
+  for (int p = 0; p < np; ++p) {
+    RankCtx* rc = ctx->local(x->parts[p].rank);
+    out_parts[p] = rc ? rc->h_result[p] : ctx->ranks[0].h_result[p];
+  }
+}
+
+bool kind_is_min(int kind) { return kind == DJETS_RED_MIN || kind == DJETS_RED_ABSMIN; }
+bool kind_is_max(int kind) { return kind == DJETS_RED_MAX || kind == DJETS_RED_ABSMAX; }
+
+// master-side fold over the per-worker partials in the element type (src:222, 236, 249, 262, 276)
+double fold_parts(int dtype, int kind, const double* z, int np) {
+  if (kind_is_min(kind)) {
+    double m = INFINITY;
+    for (int p = 0; p < np; ++p) m = fmin(m, round_to(dtype, z[p]));
+    return m;
+  }
+  if (kind_is_max(kind)) {
+    double m = -INFINITY;
+    for (int p = 0; p < np; ++p) m = fmax(m, round_to(dtype, z[p]));
+    return m;
+  }
+  double s = 0.0;
+  for (int p = 0; p < np; ++p) s = round_to(dtype, s + round_to(dtype, z[p]));
+  return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t djets_vec_create(djets_ctx ctx, int32_t dtype, int32_t nparts, const int32_t* part_rank,
+                         const int64_t* part_nblocks, const int64_t* block_len, djets_vec* out) {
+  return guard([&] {
+    REQUIRE(out && part_rank && part_nblocks && block_len, DJETS_ERR_INVALID, "vec_create: null argument");
+    *out = make_vec(ctx, dtype, nparts, part_rank, part_nblocks, block_len);
+  });
+}
+
+int32_t djets_vec_similar(djets_vec x, int32_t dtype, djets_vec* out) {
+  return guard([&] {
+    REQUIRE(x && out, DJETS_ERR_INVALID, "vec_similar: null argument");
+    std::vector<int32_t> ranks;
+    std::vector<int64_t> nb;
+    for (VecPart& p : x->parts) {
+      ranks.push_back(p.rank);
+      nb.push_back(p.blk_count);
+    }
+    *out = make_vec(x->ctx, dtype, (int)x->parts.size(), ranks.data(), nb.data(), x->block_len.data());
+  });
+}
+
+int32_t djets_vec_destroy(djets_vec x) {
+  return guard([&] {
+    if (!x) return;
+    free_vec(x);
+  });
+}
+
+int32_t djets_vec_info(djets_vec x, int32_t* dtype, int64_t* length, int64_t* nblocks, int32_t* nparts) {
+  return guard([&] {
+    REQUIRE(x, DJETS_ERR_INVALID, "null vector");
+    if (dtype) *dtype = x->dtype;
+    if (length) *length = x->length;
+    if (nblocks) *nblocks = (int64_t)x->block_len.size();
+    if (nparts) *nparts = (int32_t)x->parts.size();
+  });
+}
+
+int32_t djets_vec_part_info(djets_vec x, int32_t part, int32_t* rank, int64_t* blk_first, int64_t* blk_count,
+                            int64_t* elem_first, int64_t* elem_count) {
+  return guard([&] {
+    REQUIRE(x && part >= 0 && part < (int)x->parts.size(), DJETS_ERR_INVALID, "part_info: bad part");
+    const VecPart& p = x->parts[part];
+    if (rank) *rank = p.rank;
+    if (blk_first) *blk_first = p.blk_first;
+    if (blk_count) *blk_count = p.blk_count;
+    if (elem_first) *elem_first = p.elem_first;
+    if (elem_count) *elem_count = p.elem_count;
+  });
+}
+
+int32_t djets_vec_block_info(djets_vec x, int64_t iblock, int32_t* part, int64_t* elem_first, int64_t* len) {
+  return guard([&] {
+    REQUIRE(x && iblock >= 0 && iblock < (int64_t)x->block_len.size(), DJETS_ERR_INVALID, "block index out of range");
+    if (part) *part = x->block_part[iblock];
+    if (elem_first) *elem_first = x->block_off[iblock];
+    if (len) *len = x->block_len[iblock];
+  });
+}
+
+static void block_copy(djets_vec x, int64_t iblock, void* host, bool to_device) {
+  REQUIRE(x && iblock >= 0 && iblock < (int64_t)x->block_len.size(), DJETS_ERR_INVALID, "block index out of range");
+  VecPart& p = x->parts[x->block_part[iblock]];
+  RankCtx* rc = x->ctx->local(p.rank);
+  if (!rc) {
+    if (to_device) return;  // setblock! on a process that does not drive the owner is a no-op
+    fail(DJETS_ERR_NOT_LOCAL, "getblock: block is owned by a rank of another process");
+  }
+  const int es = elem_size(x->dtype);
+  const size_t bytes = (size_t)x->block_len[iblock] * es;
+  if (bytes == 0) return;
+  REQUIRE(host, DJETS_ERR_INVALID, "null host pointer");
+  use(*rc);
+  char* d = p.d + (size_t)(x->block_off[iblock] - p.elem_first) * es;
+  if (to_device)
+    CK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, rc->stream));
+  else
+    CK(cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, rc->stream));
+  CK(cudaStreamSynchronize(rc->stream));
+}
+
+int32_t djets_vec_setblock(djets_vec x, int64_t iblock, const void* host_src) {
+  return guard([&] { block_copy(x, iblock, const_cast<void*>(host_src), true); });
+}
+int32_t djets_vec_getblock(djets_vec x, int64_t iblock, void* host_dst) {
+  return guard([&] { block_copy(x, iblock, host_dst, false); });
+}
+
+int32_t djets_vec_getindex(djets_vec x, int64_t i, double* out) {
+  return guard([&] {
+    REQUIRE(x && out, DJETS_ERR_INVALID, "null argument");
+    REQUIRE(i >= 0 && i < x->length, DJETS_ERR_INVALID, "BoundsError: index outside the DBArray");
+    for (VecPart& p : x->parts) {
+      if (i < p.elem_first || i >= p.elem_first + p.elem_count) continue;  // findfirst(rng->i in rng) src:175
+      RankCtx* rc = x->ctx->local(p.rank);
+      REQUIRE(rc, DJETS_ERR_NOT_LOCAL, "getindex: element is owned by a rank of another process");
+      use(*rc);
+      const int es = elem_size(x->dtype);
+      double buf = 0.0;
+      CK(cudaMemcpyAsync(&buf, p.d + (size_t)(i - p.elem_first) * es, es, cudaMemcpyDeviceToHost, rc->stream));
+      CK(cudaStreamSynchronize(rc->stream));
+      if (x->dtype == DJETS_F32) {
+        float f;
+        memcpy(&f, &buf, 4);
+        *out = (double)f;
+      } else {
+        *out = buf;
+      }
+      return;
+    }
+    fail(DJETS_ERR_INVALID, "getindex: no part holds the index");
+  });
+}
+
+static void bulk_copy(djets_vec x, void* host, bool to_device) {
+  REQUIRE(x, DJETS_ERR_INVALID, "null vector");
+  REQUIRE(host || x->length == 0, DJETS_ERR_INVALID, "null host pointer");
+  const int es = elem_size(x->dtype);
+  for (VecPart& p : x->parts) {
+    RankCtx* rc = x->ctx->local(p.rank);
+    if (!rc || p.elem_count == 0) continue;
+    use(*rc);
+    char* h = reinterpret_cast<char*>(host) + (size_t)p.elem_first * es;
+    if (to_device)
+      CK(cudaMemcpyAsync(p.d, h, (size_t)p.elem_count * es, cudaMemcpyHostToDevice, rc->stream));
+    else
+      CK(cudaMemcpyAsync(h, p.d, (size_t)p.elem_count * es, cudaMemcpyDeviceToHost, rc->stream));
+  }
+  for (VecPart& p : x->parts)
+    if (RankCtx* rc = x->ctx->local(p.rank)) {
+      use(*rc);
+      CK(cudaStreamSynchronize(rc->stream));
+    }
+}
+
+int32_t djets_vec_collect(djets_vec x, void* host_dst) {
+  return guard([&] { bulk_copy(x, host_dst, false); });
+}
+int32_t djets_vec_scatter(djets_vec x, const void* host_src) {
+  return guard([&] { bulk_copy(x, const_cast<void*>(host_src), true); });
+}
+
+int32_t djets_vec_fill(djets_vec x, double a) {
+  return guard([&] {
+    REQUIRE(x, DJETS_ERR_INVALID, "null vector");
+    for (VecPart& p : x->parts) {
+      RankCtx* rc = x->ctx->local(p.rank);
+      if (!rc) continue;
+      use(*rc);
+      launch_counted(x->ctx, *rc, DJETS_K_ELTWISE,
+                     [&] { return launch_fill(x->dtype, p.d, a, p.elem_count, rc->stream); });
+    }
+  });
+}
+
+int32_t djets_vec_lincomb(djets_vec dest, int32_t nterms, const double* coef, const djets_vec* xs, int32_t flags) {
+  return guard([&] {
+    REQUIRE(dest && coef && xs, DJETS_ERR_INVALID, "lincomb: null argument");
+    REQUIRE(nterms >= 1 && nterms <= 4, DJETS_ERR_UNSUPPORTED, "lincomb: 1 to 4 terms");
+    for (int k = 0; k < nterms; ++k) {
+      REQUIRE(xs[k], DJETS_ERR_INVALID, "lincomb: null operand");
+      REQUIRE(same_layout(dest, xs[k]), DJETS_ERR_MISMATCH,
+              "DimensionMismatch: broadcast operands have different block layouts");
+    }
+    for (size_t p = 0; p < dest->parts.size(); ++p) {
+      VecPart& dp = dest->parts[p];
+      RankCtx* rc = dest->ctx->local(dp.rank);
+      if (!rc) continue;
+      use(*rc);
+      LincombArgs a;
+      a.nterms = nterms;
+      for (int k = 0; k < nterms; ++k) {
+        a.x[k] = xs[k]->parts[p].d;
+        a.coef[k] = coef[k];
+        a.xdtype[k] = xs[k]->dtype;
+      }
+      launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE,
+                     [&] { return launch_lincomb(dest->dtype, dp.d, a, dp.elem_count, flags & 1, rc->stream); });
+    }
+  });
+}
+
+int32_t djets_vec_binary(djets_vec dest, int32_t op, djets_vec a, djets_vec b) {
+  return guard([&] {
+    REQUIRE(dest && a && b, DJETS_ERR_INVALID, "binary: null argument");
+    REQUIRE(op == 0 || op == 1, DJETS_ERR_UNSUPPORTED, "binary: op 0 (.*) or 1 (./)");
+    REQUIRE(same_layout(dest, a) && same_layout(dest, b), DJETS_ERR_MISMATCH,
+            "DimensionMismatch: broadcast operands have different block layouts");
+    REQUIRE(dest->dtype == a->dtype && dest->dtype == b->dtype, DJETS_ERR_UNSUPPORTED,
+            "binary: operands must share the element type");
+    for (size_t p = 0; p < dest->parts.size(); ++p) {
+      VecPart& dp = dest->parts[p];
+      RankCtx* rc = dest->ctx->local(dp.rank);
+      if (!rc) continue;
+      use(*rc);
+      launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE, [&] {
+        return launch_binary(dest->dtype, op, dp.d, a->parts[p].d, b->parts[p].d, dp.elem_count, rc->stream);
+      });
+    }
+  });
+}
+
+int32_t djets_vec_reduce_parts(djets_vec x, int32_t kind, double param, double* out_parts) {
+  return guard([&] {
+    REQUIRE(x && out_parts, DJETS_ERR_INVALID, "reduce: null argument");
+    REQUIRE(kind >= 0 && kind <= DJETS_RED_SUMSQ_SHIFT, DJETS_ERR_INVALID, "reduce: unknown kind");
+    reduce_parts(x, nullptr, kind, param, out_parts);
+  });
+}
+
+int32_t djets_vec_reduce(djets_vec x, int32_t kind, double param, double* out) {
+  return guard([&] {
+    REQUIRE(x && out, DJETS_ERR_INVALID, "reduce: null argument");
+    REQUIRE(kind >= 0 && kind <= DJETS_RED_SUMSQ_SHIFT, DJETS_ERR_INVALID, "reduce: unknown kind");
+    std::vector<double> z(x->parts.size());
+    reduce_parts(x, nullptr, kind, param, z.data());
+    *out = fold_parts(x->dtype, kind, z.data(), (int)z.size());
+  });
+}
+
+int32_t djets_vec_dot(djets_vec x, djets_vec y, double* out) {
+  return guard([&] {
+    REQUIRE(x && y && out, DJETS_ERR_INVALID, "dot: null argument");
+    REQUIRE(same_layout(x, y), DJETS_ERR_MISMATCH, "DimensionMismatch: dot of DBArrays with different block layouts");
+    REQUIRE(x->dtype == y->dtype, DJETS_ERR_MISMATCH, "dot: element types differ (reference: MethodError, src:214)");
+    std::vector<double> z(x->parts.size());
+    reduce_parts(x, y, RED_DOT, 0.0, z.data());
+    *out = fold_parts(x->dtype, DJETS_RED_SUM, z.data(), (int)z.size());
+  });
+}
+
+int32_t djets_vec_norm(djets_vec x, double p, double* out) {
+  return guard([&] {
+    REQUIRE(x && out, DJETS_ERR_INVALID, "norm: null argument");
+    const int np = (int)x->parts.size();
+    const int dt = x->dtype;
+    std::vector<double> z(np);
+    if (p == INFINITY) {  // src:200-201
+      reduce_parts(x, nullptr, DJETS_RED_ABSMAX, 0.0, z.data());
+      *out = fold_parts(dt, DJETS_RED_MAX, z.data(), np);
+    } else if (p == -INFINITY) {  // src:202-203
+      reduce_parts(x, nullptr, DJETS_RED_ABSMIN, 0.0, z.data());
+      *out = fold_parts(dt, DJETS_RED_MIN, z.data(), np);
+    } else if (p == 0.0 || p == 1.0) {  // src:204-205
+      reduce_parts(x, nullptr, p == 0.0 ? DJETS_RED_NNZ : DJETS_RED_ABSSUM, 0.0, z.data());
+      *out = fold_parts(dt, DJETS_RED_SUM, z.data(), np);
+    } else {  // src:206-209: per-worker norms z, then (sum z^p)^(1/p) in float(real(T))
+      const double pp = round_to(dt, p);
+      reduce_parts(x, nullptr, p == 2.0 ? DJETS_RED_SUMSQ : DJETS_RED_SUMPOW, pp, z.data());
+      double s = 0.0;
+      for (int k = 0; k < np; ++k) {
+        const double zk = round_to(dt, p == 2.0 ? sqrt(z[k]) : pow(z[k], 1.0 / pp));
+        s = round_to(dt, s + round_to(dt, p == 2.0 ? zk * zk : pow(zk, pp)));
+      }
+      *out = round_to(dt, p == 2.0 ? sqrt(s) : pow(s, round_to(dt, 1.0 / pp)));
+    }
+  });
+}
+
+}  // extern "C"
