@@ -203,7 +203,7 @@ class JetDSpace:
                 and self.blkindices == other.blkindices and self.indices == other.indices)
 
     def __len__(self):
-        return self.indices[-1][-1] if self.indices else 0
+        return self.indices[-1].stop - 1 if self.indices else 0      # Julia's indices[end][end], empty ranges included
 
     def size(self):                                      # src:78
         return (len(self),)
@@ -213,7 +213,7 @@ class JetDSpace:
         return self.dtype
 
     def nblocks(self) -> int:                            # src:89
-        return self.blkindices[-1][-1]
+        return self.blkindices[-1].stop - 1
 
     def blockmap(self) -> List[range]:                   # src:104
         return self.blkindices
@@ -345,7 +345,7 @@ class DBArray:
 
     # array interface (src:166-187) --------------------------------------------------------------------
     def __len__(self):
-        return self.indices[-1][-1] if self.indices else 0
+        return self.indices[-1].stop - 1 if self.indices else 0      # Julia's indices[end][end], empty ranges included
 
     def size(self):
         return (len(self),)
@@ -391,7 +391,7 @@ class DBArray:
         return len(self.pids)
 
     def nblocks(self) -> int:
-        return self.blkindices[-1][-1]
+        return self.blkindices[-1].stop - 1
 
     def blockmap(self) -> List[range]:
         return self.blkindices

@@ -168,7 +168,7 @@ class BlockArray:
             ibeg = iend + 1
 
     def __len__(self):
-        return self.indices[-1][-1] if self.indices and len(self.indices[-1]) else 0
+        return self.indices[-1].stop - 1 if self.indices else 0      # indices[end][end]; an empty last block is k+1:k
 
     @property
     def dtype(self):
@@ -284,25 +284,25 @@ class OJetDSpace:
         for s in blkspaces:
             self.blkindices.append(ur(blk0, blk0 + s.nblocks() - 1))
             self.indices.append(ur(i0, i0 + len(s) - 1))
-            blk0 = self.blkindices[-1][-1] + 1
-            i0 = self.indices[-1][-1] + 1
+            blk0 = self.blkindices[-1].stop
+            i0 = self.indices[-1].stop
 
     def __eq__(self, other):                                     # src:69
         return (self.blkspaces == other.blkspaces and self.blkindices == other.blkindices
                 and self.indices == other.indices)
 
     def size(self):                                              # src:78
-        return (self.indices[-1][-1],)
+        return (self.indices[-1].stop - 1,)
 
     def __len__(self):
-        return self.indices[-1][-1]
+        return self.indices[-1].stop - 1
 
     @property
     def dtype(self):
         return self.blkspaces[0].dtype
 
     def nblocks(self):                                           # src:89
-        return self.blkindices[-1][-1]
+        return self.blkindices[-1].stop - 1
 
     def blockmap(self):                                          # src:104
         return self.blkindices
@@ -372,13 +372,13 @@ class ODBArray:
         return self.parts[0].dtype
 
     def size(self):                                              # src:168
-        return (self.indices[-1][-1],)
+        return (self.indices[-1].stop - 1,)
 
     def __len__(self):
-        return self.indices[-1][-1]
+        return self.indices[-1].stop - 1
 
     def nblocks(self):                                           # src:297
-        return self.blkindices[-1][-1]
+        return self.blkindices[-1].stop - 1
 
     def blockmap(self):                                          # src:304
         return self.blkindices
