@@ -182,6 +182,9 @@ def run_cuda(args):
         box = [dj.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         ctx = dj.Context.spmd(rank, world, local_rank, box[0])
+    elif args.single_process and args.gpus > 1:
+        world = args.gpus
+        ctx = dj.Context(world=world, devices=list(range(world)))
     else:
         ctx = dj.Context(world=1, devices=[0])
     dj.set_default_context(ctx)
@@ -312,6 +315,9 @@ def run_cuda(args):
         peak, peak_src = peaks()
         es = np.dtype(DTYPE).itemsize
         local_blocks = nblk // world + (1 if rank < nblk % world else 0)     # rank 0's shard
+        if args.single_process:
+            for name in ("gemv_n", "gemv_t"):                               # stats hold the max over local ranks' totals
+                kstats[name]["launches"] //= world
         per_launch = local_blocks * (BM * BN + BM + BN) * es        # algorithmic bytes of one gemv launch
         kn, kt = kstats["gemv_n"], kstats["gemv_t"]
         dom = "gemv_t" if kt["ms"] >= kn["ms"] else "gemv_n"
@@ -344,7 +350,8 @@ def run_cuda(args):
             "cpu_baseline": cpu,
             "e2e": {"value": bytes_total / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
-            "gpu_launches": launches if world == 1 else int(launches * world),
+            "gpu_launches": launches if (world == 1 or args.single_process) else int(launches * world),
+            "mode": "one host process" if (args.single_process or world == 1) else "one process per GPU (NCCL)",
             "clocks": clocks, "host_cores": os.cpu_count(), "parity_relerr_block1": parity, "build_s": t_build,
             "schedule": {"fwd_tiles_items": A.schedule_info(False), "adj_tiles_items": A.schedule_info(True)},
         }
@@ -374,6 +381,9 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong (default): the BASELINE operator's 64 blocks are sharded over the N ranks; "
                          "weak: 64 blocks per rank")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive all --gpus N ranks from this one process (the Julia-master model) instead of one "
+                         "process per GPU under torchrun")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: skips the e2e pass, the clock-sampling loop and the CPU baseline")
