@@ -122,11 +122,25 @@ double round_to(int dtype, double v) { return dtype == DJETS_F32 ? (double)(floa
 void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_parts) {
   djets_ctx ctx = x->ctx;
   const int np = (int)x->parts.size();
-  bool any_remote = false;
-  for (RankCtx& rc : ctx->ranks) {
-    use(rc);
-    CK(cudaMemsetAsync(rc.d_result, 0, sizeof(double) * np, rc.stream));
+  // Every process of a multi-process job makes the same calls, so the decision to exchange must not
+  // depend on which parts happen to be local: with NCCL up, always all-reduce.
+  const bool multi_process = (int)ctx->ranks.size() < ctx->world;
+  const bool exchange = multi_process && ctx->has_nccl;
+  // ranks that take part: the owners of x's parts; with an exchange every rank this process drives
+  std::vector<RankCtx*> involved;
+  if (exchange) {
+    for (RankCtx& rc : ctx->ranks) involved.push_back(&rc);
+  } else {
+    for (const VecPart& part : x->parts)
+      if (RankCtx* rc = ctx->local(part.rank))
+        if (std::find(involved.begin(), involved.end(), rc) == involved.end()) involved.push_back(rc);
   }
+  if (exchange)
+    for (RankCtx* rc : involved) {  // zeros in the slots of parts owned elsewhere: the sum is then exact
+      use(*rc);
+      CK(cudaMemsetAsync(rc->d_result, 0, sizeof(double) * np, rc->stream));
+    }
+  bool any_remote = false;
   for (int p = 0; p < np; ++p) {
     VecPart& part = x->parts[p];
     RankCtx* rc = ctx->local(part.rank);
@@ -141,34 +155,30 @@ void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_
                            rc->stream);
     });
   }
-  // Every process of a multi-process job makes the same calls, so the decision to exchange must not
-  // depend on which parts happen to be local: with NCCL up, always all-reduce.
-  const bool multi_process = (int)ctx->ranks.size() < ctx->world;
-  if (multi_process && ctx->has_nccl) {
+  if (exchange) {
     const char* why = nullptr;
     const NcclApi* api = nccl_api(&why);
     REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
-    // every rank contributes its own parts and zeros elsewhere: the sum is exact
     NCK(api, api->GroupStart());
-    for (RankCtx& rc : ctx->ranks) {
-      use(rc);
-      NCK(api, api->AllReduce(rc.d_result, rc.d_result, np, ncclDouble, ncclSum, rc.comm, rc.stream));
+    for (RankCtx* rc : involved) {
+      use(*rc);
+      NCK(api, api->AllReduce(rc->d_result, rc->d_result, np, ncclDouble, ncclSum, rc->comm, rc->stream));
     }
     NCK(api, api->GroupEnd());
   } else {
     REQUIRE(!any_remote, DJETS_ERR_NCCL, "vector has parts in other processes but the context has no NCCL");
   }
-  for (RankCtx& rc : ctx->ranks) {
-    use(rc);
-    CK(cudaMemcpyAsync(rc.h_result, rc.d_result, sizeof(double) * np, cudaMemcpyDeviceToHost, rc.stream));
+  for (RankCtx* rc : involved) {
+    use(*rc);
+    CK(cudaMemcpyAsync(rc->h_result, rc->d_result, sizeof(double) * np, cudaMemcpyDeviceToHost, rc->stream));
   }
-  for (RankCtx& rc : ctx->ranks) {
-    use(rc);
-    CK(cudaStreamSynchronize(rc.stream));
+  for (RankCtx* rc : involved) {
+    use(*rc);
+    CK(cudaStreamSynchronize(rc->stream));
   }
   for (int p = 0; p < np; ++p) {
     RankCtx* rc = ctx->local(x->parts[p].rank);
-    out_parts[p] = rc ? rc->h_result[p] : ctx->ranks[0].h_result[p];
+    out_parts[p] = rc ? rc->h_result[p] : involved.front()->h_result[p];
   }
 }
 
