@@ -40,9 +40,8 @@ void drain_events(RankCtx& rc) {
 // dst stream waits for everything enqueued so far on src stream
 void stream_after(RankCtx& src, RankCtx& dst) {
   if (&src == &dst) return;
-  use(src);
+  // no cudaSetDevice: event record / stream wait only need event and stream to agree, not the current device
   CK(cudaEventRecord(src.ev, src.stream));
-  use(dst);
   CK(cudaStreamWaitEvent(dst.stream, src.ev, 0));
 }
 

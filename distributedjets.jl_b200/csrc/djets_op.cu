@@ -422,8 +422,7 @@ void finalize_op(djets_op op) {
   op->finalized = true;
 }
 
-// Enqueues one apply on the ranks' streams: exchange phase 0, tile kernels (+ fused sums), exchange
-// phase 1, owners' segmented sums.  Returns the number of enqueued operations.
+// perfstatfile: bracket every cell's share of an apply with events on its stream
 void perfstat_mark(djets_op op, bool begin) {
   if (!op->perfstat) return;
   for (Cell& cell : op->cells) {
@@ -448,6 +447,8 @@ int apply_enqueue_timed(djets_op op, djets_vec out, djets_vec in, bool adjoint) 
   return n;
 }
 
+// Enqueues one apply on the ranks' streams: exchange phase 0, tile kernels (+ fused sums), exchange
+// phase 1, owners' segmented sums.  Returns the number of enqueued operations.
 int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   djets_ctx ctx = op->ctx;
   int nops = 0;
