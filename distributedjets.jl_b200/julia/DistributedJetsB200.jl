@@ -22,7 +22,8 @@ import Libdl
 
 export DBArray, JetDSpace, blockmap, localblockindices
 
-const libdjets = Ref{String}(joinpath(@__DIR__, "..", "libdjets_b200.so"))
+# a constant: `ccall((:symbol, lib), ...)` needs the library as a compile-time constant
+const libdjets = get(ENV, "DJETS_B200_LIB", joinpath(@__DIR__, "..", "libdjets_b200.so"))
 
 const DJETS_F32, DJETS_F64 = Int32(0), Int32(1)
 const BLOCK_ZERO, BLOCK_DENSE, BLOCK_DIAG = Int32(0), Int32(1), Int32(2)
@@ -32,7 +33,7 @@ dtypecode(::Type{Float32}) = DJETS_F32
 dtypecode(::Type{Float64}) = DJETS_F64
 dtypecode(::Type{T}) where {T} = error("DistributedJetsB200: element type $T is not supported (Float32, Float64)")
 
-lasterror() = unsafe_string(ccall((:djets_last_error, libdjets[]), Cstring, ()))
+lasterror() = unsafe_string(ccall((:djets_last_error, libdjets), Cstring, ()))
 function check(status::Int32)
     status == 0 && return nothing
     msg = lasterror()
@@ -41,7 +42,7 @@ function check(status::Int32)
 end
 macro dj(f, argtypes, args...)
     quote
-        check(ccall(($(QuoteNode(f)), libdjets[]), Int32, $(esc(argtypes)), $(map(esc, args)...)))
+        check(ccall(($(QuoteNode(f)), libdjets), Int32, $(esc(argtypes)), $(map(esc, args)...)))
     end
 end
 
@@ -117,7 +118,7 @@ mutable struct DBArray{T} <: AbstractArray{T,1}
     space::JetDSpace{T}
     function DBArray{T}(h, space) where {T}
         x = new{T}(h, space)
-        finalizer(x -> (x.h == C_NULL || ccall((:djets_vec_destroy, libdjets[]), Int32, (Ptr{Cvoid},), x.h); x.h = C_NULL), x)
+        finalizer(x -> (x.h == C_NULL || ccall((:djets_vec_destroy, libdjets), Int32, (Ptr{Cvoid},), x.h); x.h = C_NULL), x)
     end
 end
 function Base.Array(R::JetDSpace{T}) where {T}                                             # src:379-381
@@ -323,7 +324,7 @@ mutable struct DBlockOp{T}
     mrep::Any                              # DBArray home of a replicated (plain-array) model, made on demand
     function DBlockOp{T}(h, pids, bm, isdiag) where {T}
         op = new{T}(h, pids, bm, isdiag, nothing)
-        finalizer(o -> (o.h == C_NULL || ccall((:djets_op_destroy, libdjets[]), Int32, (Ptr{Cvoid},), o.h); o.h = C_NULL), op)
+        finalizer(o -> (o.h == C_NULL || ccall((:djets_op_destroy, libdjets), Int32, (Ptr{Cvoid},), o.h); o.h = C_NULL), op)
     end
 end
 
