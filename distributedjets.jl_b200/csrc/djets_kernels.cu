@@ -292,19 +292,19 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(const DenseTile* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// Adjoint dense tiles: partial[c] = sum_r A[r,c] y[r].  A warp owns kAdjCW columns at a time and
+// Adjoint dense tiles: partial[c] = sum_r A[r,c] y[r].  A warp owns CW columns at a time and
 // streams down them with 128-bit loads (each lane VEC rows, 32 lanes = 512 contiguous bytes per
-// column), RU row chunks unrolled -> kAdjCW*RU independent loads in flight per lane; the y slice is
-// staged once per CTA in shared memory and each 128-bit LDS of y is reused for the kAdjCW columns;
-// the per-lane sums are combined with a shuffle butterfly.
+// column), RU row chunks unrolled -> CW*RU = 16 independent loads in flight per lane whatever the
+// column height: (RU,CW) = (4,4) for tall columns, (2,8) and (1,16) for short ones; the y slice is
+// staged once per CTA in shared memory and each 128-bit LDS of y is reused for the CW columns; the
+// per-lane sums are combined with a column-halving shuffle butterfly.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int RU, int POLICY>
+template <typename T, int RU, int CW, int POLICY>
 __global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __restrict__ tiles,
                                                              const T* __restrict__ in, T* W, T* __restrict__ out,
                                                              FusedFinish ff) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
-  constexpr int CW = kAdjCW;
   constexpr int S = 32 * VEC;  // rows one warp covers with one load per lane
   __shared__ __align__(128) T ys[kAdjMaxTRBytes / sizeof(T)];
   __shared__ __align__(8) uint64_t bar;
@@ -327,9 +327,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __
 
   for (int g = warp; g < ngroups; g += kThreads / 32) {
     const int c0 = g * CW;
-    const T* col[CW];
-#pragma unroll
-    for (int k = 0; k < CW; ++k) col[k] = A + (long long)min(c0 + k, cols - 1) * ld + lane * VEC;
+    const int last = cols - 1 - c0;  // columns past the tile edge re-read the last one and are not stored
+    const T* base = A + (long long)c0 * ld + lane * VEC;
     T acc[CW];
 #pragma unroll
     for (int k = 0; k < CW; ++k) acc[k] = T(0);
@@ -341,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __
       for (int u = 0; u < RU; ++u)
 #pragma unroll
         for (int k = 0; k < CW; ++k)
-          a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(col[k] + rb + u * S), pol);
+          a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
 #pragma unroll
       for (int u = 0; u < RU; ++u) {
         const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
@@ -349,26 +348,84 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __
         for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[u][k], y);
       }
     }
-    for (; rb < rowsv; rb += S) {
-      if (rb + lane * VEC < rowsv) {
-        V a[CW];
+    if (CW == 4) {
+      // tall columns: the remainder is at most RU-1 chunks: pairs of chunks first, then a guarded last one
+      if (RU > 2) {
+        for (; rb + 2 * S <= rowsv; rb += 2 * S) {
+          V a[2][CW];
 #pragma unroll
-        for (int k = 0; k < CW; ++k) a[k] = ld_stream<POLICY>(reinterpret_cast<const V*>(col[k] + rb), pol);
-        const V y = *reinterpret_cast<const V*>(ys + rb + lane * VEC);
+          for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[k], y);
+            for (int k = 0; k < CW; ++k)
+              a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
+#pragma unroll
+            for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[u][k], y);
+          }
+        }
+      }
+      for (; rb < rowsv; rb += S) {
+        if (rb + lane * VEC < rowsv) {
+          V a[CW];
+#pragma unroll
+          for (int k = 0; k < CW; ++k)
+            a[k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb), pol);
+          const V y = *reinterpret_cast<const V*>(ys + rb + lane * VEC);
+#pragma unroll
+          for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[k], y);
+        }
+      }
+    } else if (rb < rowsv) {
+      // short columns: the remainder IS most of the column -- one guarded batch, CW*RU loads in flight
+      V a[RU][CW];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const bool ok = rb + u * S + lane * VEC < rowsv;
+#pragma unroll
+        for (int k = 0; k < CW; ++k) {
+          if (ok)
+            a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        if (rb + u * S + lane * VEC < rowsv) {
+          const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
+#pragma unroll
+          for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[u][k], y);
+        }
       }
     }
+    // Warp reduction of CW columns at once: while more than one column is live, each butterfly step
+    // also halves the columns a lane keeps (the lanes with the offset bit set keep the upper half), so
+    // CW columns cost CW-1 + (5 - log2 CW) shuffles instead of 5*CW.  The pattern is fixed: deterministic.
+    int width = CW;
 #pragma unroll
-    for (int k = 0; k < CW; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      if (width > 1) {
+        width >>= 1;
+        const bool upper = (lane & o) != 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        for (int k = 0; k < CW / 2; ++k) {
+          if (k < width) {
+            const T send = upper ? acc[k] : acc[k + width];
+            const T keep = upper ? acc[k + width] : acc[k];
+            acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+      } else {
+        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+      }
     }
-    T mine = acc[0];
+    // lane bits 16, 8, ... (one per halving step) spell the column a lane ended up with
+    constexpr int kHalvings = (CW == 16) ? 4 : (CW == 8) ? 3 : (CW == 4) ? 2 : (CW == 2) ? 1 : 0;
+    int mycol = 0;
 #pragma unroll
-    for (int k = 1; k < CW; ++k)
-      if (lane == k) mine = acc[k];
-    if (lane < CW && c0 + lane < cols) dst[c0 + lane] = mine;
+    for (int h = 0; h < kHalvings; ++h) mycol |= ((lane >> (4 - h)) & 1) << (kHalvings - 1 - h);
+    const bool writer = (lane & ((32 >> kHalvings) - 1)) == 0;
+    if (writer && c0 + mycol < cols) dst[c0 + mycol] = acc[0];
   }
   if (t.fin >= 0) fused_finish<T>(t, ff, in, W, out);
 }
@@ -756,28 +813,28 @@ cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile*
 }
 
 template <typename T, int POLICY>
-static cudaError_t launch_gemv_t_t(int adj_ru, const DenseTile* tiles, int ntiles, const void* in, void* W, void* out,
-                                   FusedFinish ff, cudaStream_t stream) {
+static cudaError_t launch_gemv_t_t(int adj_ru, int adj_cw, const DenseTile* tiles, int ntiles, const void* in, void* W,
+                                   void* out, FusedFinish ff, cudaStream_t stream) {
   const T* i = reinterpret_cast<const T*>(in);
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
-  switch (adj_ru) {
-    case 1: return launch_tiles(gemv_t_kernel<T, 1, POLICY>, ntiles, stream, tiles, i, w, o, ff);
-    case 2: return launch_tiles(gemv_t_kernel<T, 2, POLICY>, ntiles, stream, tiles, i, w, o, ff);
-    case 4: return launch_tiles(gemv_t_kernel<T, 4, POLICY>, ntiles, stream, tiles, i, w, o, ff);
-    default: return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
+  // (rows unrolled, columns per warp): tall columns stream down 4 columns, short ones fan out over 16
+  if (adj_cw == 16 && adj_ru == 1) return launch_tiles(gemv_t_kernel<T, 1, 16, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+  if (adj_cw == 8 && adj_ru == 2) return launch_tiles(gemv_t_kernel<T, 2, 8, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+  if (adj_cw == 4 && adj_ru == 4) return launch_tiles(gemv_t_kernel<T, 4, 4, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+  if (adj_cw == 4 && adj_ru == 2) return launch_tiles(gemv_t_kernel<T, 2, 4, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+  if (adj_cw == 4 && adj_ru == 1) return launch_tiles(gemv_t_kernel<T, 1, 4, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+  return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_gemv_t(int dtype, int adj_ru, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
-                          void* W, void* out, FusedFinish ff, cudaStream_t stream) {
+cudaError_t launch_gemv_t(int dtype, int adj_ru, int adj_cw, int ld_policy, const DenseTile* tiles, int ntiles,
+                          const void* in, void* W, void* out, FusedFinish ff, cudaStream_t stream) {
   if (ntiles <= 0) return cudaSuccess;
   if (dtype == 0)
-    return ld_policy ? launch_gemv_t_t<float, 1>(adj_ru, tiles, ntiles, in, W, out, ff, stream)
-                     : launch_gemv_t_t<float, 0>(adj_ru, tiles, ntiles, in, W, out, ff, stream);
-  return ld_policy ? launch_gemv_t_t<double, 1>(adj_ru, tiles, ntiles, in, W, out, ff, stream)
-                   : launch_gemv_t_t<double, 0>(adj_ru, tiles, ntiles, in, W, out, ff, stream);
+    return ld_policy ? launch_gemv_t_t<float, 1>(adj_ru, adj_cw, tiles, ntiles, in, W, out, ff, stream)
+                     : launch_gemv_t_t<float, 0>(adj_ru, adj_cw, tiles, ntiles, in, W, out, ff, stream);
+  return ld_policy ? launch_gemv_t_t<double, 1>(adj_ru, adj_cw, tiles, ntiles, in, W, out, ff, stream)
+                   : launch_gemv_t_t<double, 0>(adj_ru, adj_cw, tiles, ntiles, in, W, out, ff, stream);
 }
 
 cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,

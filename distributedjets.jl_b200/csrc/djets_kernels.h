@@ -52,8 +52,8 @@ struct FusedFinish {
 };
 cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
                           void* W, void* out, FusedFinish ff, cudaStream_t stream);
-cudaError_t launch_gemv_t(int dtype, int adj_ru, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
-                          void* W, void* out, FusedFinish ff, cudaStream_t stream);
+cudaError_t launch_gemv_t(int dtype, int adj_ru, int adj_cw, int ld_policy, const DenseTile* tiles, int ntiles,
+                          const void* in, void* W, void* out, FusedFinish ff, cudaStream_t stream);
 cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,
                           const void* W, const void* R, void* out, cudaStream_t stream);
 
@@ -85,7 +85,7 @@ inline int elem_size(int dtype) { return dtype == 0 ? 4 : 8; }
 constexpr int kThreads = 256;
 constexpr int kFwdMaxTC = 1024;   // columns of x staged in shared memory by a forward tile
 constexpr int kAdjMaxTRBytes = 32768;  // bytes of y staged in shared memory by an adjoint tile
-constexpr int kAdjCW = 4;         // columns a warp handles at once in the adjoint kernel
+constexpr int kAdjCW = 4;         // fewest columns a warp handles at once in the adjoint kernel (tall columns)
 constexpr int kFinishChunk = 1024;
 inline int adj_max_rows(int dtype) { return kAdjMaxTRBytes / elem_size(dtype); }
 

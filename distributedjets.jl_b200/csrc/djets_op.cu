@@ -22,6 +22,7 @@ struct DirPlan {
   char* stage_in = nullptr;   // input slice received from its owner
   char* stage_out = nullptr;  // reduced partial pushed to the owner
   char* R = nullptr;          // planes received from the other cells of the grid row / column
+  int adj_ru = 4, adj_cw = 4;  // adjoint kernel shape chosen for this cell (rows unrolled, columns per warp)
 };
 
 struct Cell {
@@ -209,20 +210,48 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   // operators; small ones get smaller tiles so that one launch still fills 148 SMs several times over
   // (auto_tile).  One value per cell: every block of a block row / column must cut the same strips.
   int64_t eff_fwd_tc = ctx->fwd_tc, eff_adj_tc = ctx->adj_tc;
+  int adj_ru = (int)op->p_adj_ru, adj_cw = kAdjCW;
   if (ctx->auto_tile) {
     int64_t dense_bytes = 0, max_rows = 1;
+    double weighted_rows = 0.0;
     for (int64_t i = r0; i < r1; ++i)
       for (int64_t j = c0; j < c1; ++j) {
         if (op->isdiag && i != j) continue;
         if (op->block(i, j).kind != DJETS_BLOCK_DENSE) continue;
-        dense_bytes += op->row_len[i] * op->col_len[j] * es;
+        const int64_t b = op->row_len[i] * op->col_len[j] * es;
+        dense_bytes += b;
+        weighted_rows += (double)b * (double)op->row_len[i];
         max_rows = std::max(max_rows, op->row_len[i]);
       }
     const int64_t tile_bytes = std::max<int64_t>(64 * 1024, dense_bytes / (148 * 6));
     const int64_t tr = op->p_fwd_tx * vec_elems(op->dtype);
     eff_fwd_tc = std::max<int64_t>(64, std::min<int64_t>(ctx->fwd_tc, round_up(std::max<int64_t>(tile_bytes / (tr * es), 1), 64)));
+    // adjoint: short columns (bytes-weighted mean height) fan a warp out over more columns, and get wider
+    // tiles so that a tile is still >= 256 KB
+    const int64_t typical_rows = dense_bytes > 0 ? (int64_t)(weighted_rows / (double)dense_bytes) : 1;
+    const int64_t chunks = ceil_div(std::min<int64_t>(typical_rows, adj_max_rows(op->dtype)), 32 * vec_elems(op->dtype));
+    if (chunks <= 2) {
+      adj_ru = 1;
+      adj_cw = 16;
+    } else if (chunks == 3) {
+      adj_ru = 2;
+      adj_cw = 8;
+    }
     const int64_t rows = std::min<int64_t>(max_rows, adj_max_rows(op->dtype));
-    eff_adj_tc = std::max<int64_t>(32, std::min<int64_t>(ctx->adj_tc, round_up(std::max<int64_t>(tile_bytes / (rows * es), 1), 32)));
+    if (adj_cw == kAdjCW) {
+      // tall columns: adj_tc columns (tuned at 16 KB columns = 1 MiB tiles), more of them when the
+      // columns are shorter so that a tile stays about 1 MiB; smaller only for small operators
+      const int64_t cap = std::min<int64_t>(1024, std::max<int64_t>(ctx->adj_tc, round_up(ctx->adj_tc * 16384 / (rows * es), 32)));
+      eff_adj_tc = std::max<int64_t>(32, std::min<int64_t>(cap, round_up(std::max<int64_t>(tile_bytes / (rows * es), 1), 32)));
+    } else {
+      const int64_t pass = 8 * adj_cw;  // columns one CTA covers per pass over its warps
+      const int64_t want = std::min<int64_t>(std::max<int64_t>(tile_bytes, 256 * 1024), 1 << 20) / (rows * es);
+      eff_adj_tc = std::min<int64_t>(4096, std::max<int64_t>(pass, round_up(std::max<int64_t>(want, 1), pass)));
+    }
+  }
+  if (adjoint) {
+    plan.adj_ru = adj_ru;
+    plan.adj_cw = adj_cw;
   }
   std::vector<DenseTile> tiles;
   std::vector<FinishItem> loose, fused;
@@ -525,8 +554,8 @@ int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
           });
         else
           launch_counted(ctx, *rc, DJETS_K_GEMV_T, [&] {
-            return launch_gemv_t(op->dtype, (int)op->p_adj_ru, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles, inp,
-                                 plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets}, rc->stream);
+            return launch_gemv_t(op->dtype, plan.adj_ru, plan.adj_cw, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles,
+                                 inp, plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets}, rc->stream);
           });
       }
       if (!owner && plan.nloose > 0) {
