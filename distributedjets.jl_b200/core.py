@@ -835,8 +835,12 @@ class JopDBlock:
     def size(self):
         return self.shape
 
-    def nblocks(self):
-        return (self.N, self.M)
+    def nblocks(self, dim: Optional[int] = None):
+        """``nblocks(A)`` / ``nblocks(A, dim)`` (test/runtests.jl:381-383)."""
+        return (self.N, self.M) if dim is None else (self.N, self.M)[dim - 1]
+
+    def isblockop(self) -> bool:                           # src:827
+        return True
 
     def procs(self) -> List[List[int]]:
         return self.pids

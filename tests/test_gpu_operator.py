@@ -105,7 +105,7 @@ def test_operator_metadata_and_getblock(dj, O, ctx4):
     rng = np.random.default_rng(3)
     kind = lambda i, j: "diag" if (i % 2 == 0 and j % 2 == 1) else ("zero" if (i, j) == (1, 5) else "dense")
     oop, gop, oblocks = build_pair(dj, O, rng, [10] * 3, [10] * 5, kind, np.float64, [0, 1, 2, 3], [2, 2], ctx=ctx4)
-    assert gop.nblocks() == (3, 5) == oop.nblocks()
+    assert gop.nblocks() == (3, 5) == oop.nblocks() and gop.nblocks(1) == 3 and gop.nblocks(2) == 5 and gop.isblockop()
     assert gop.procs() == oop.procs() == [[0, 2], [1, 3]]                  # column-major grid, test:543
     assert gop.blockmap() == oop.blockmap
     assert gop.blockmap()[0][0] == (range(1, 3), range(1, 4))               # test:536-539
