@@ -23,6 +23,7 @@ struct DirPlan {
   char* stage_out = nullptr;  // reduced partial pushed to the owner
   char* R = nullptr;          // planes received from the other cells of the grid row / column
   int adj_ru = 4, adj_cw = 4;  // adjoint kernel shape chosen for this cell (rows unrolled, columns per warp)
+  int fwd_tx = 64;             // forward kernel shape chosen for this cell (threads along the rows)
 };
 
 struct Cell {
@@ -211,9 +212,10 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   // (auto_tile).  One value per cell: every block of a block row / column must cut the same strips.
   int64_t eff_fwd_tc = ctx->fwd_tc, eff_adj_tc = ctx->adj_tc;
   int adj_ru = (int)op->p_adj_ru, adj_cw = kAdjCW;
+  int64_t fwd_tx = op->p_fwd_tx;
   if (ctx->auto_tile) {
     int64_t dense_bytes = 0, max_rows = 1;
-    double weighted_rows = 0.0;
+    double weighted_rows = 0.0, weighted_cols = 0.0;
     for (int64_t i = r0; i < r1; ++i)
       for (int64_t j = c0; j < c1; ++j) {
         if (op->isdiag && i != j) continue;
@@ -221,10 +223,18 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
         const int64_t b = op->row_len[i] * op->col_len[j] * es;
         dense_bytes += b;
         weighted_rows += (double)b * (double)op->row_len[i];
+        weighted_cols += (double)b * (double)op->col_len[j];
         max_rows = std::max(max_rows, op->row_len[i]);
       }
     const int64_t tile_bytes = std::max<int64_t>(64 * 1024, dense_bytes / (148 * 6));
-    const int64_t tr = op->p_fwd_tx * vec_elems(op->dtype);
+    // forward: narrow blocks (few columns) give a tile its bytes through more rows -- the CTA goes wider
+    // along the rows and needs fewer (or no) column groups to sum
+    const int64_t typical_cols = dense_bytes > 0 ? (int64_t)(weighted_cols / (double)dense_bytes) : 1;
+    const int64_t typical_rows_f = dense_bytes > 0 ? (int64_t)(weighted_rows / (double)dense_bytes) : 1;
+    int64_t wide = typical_cols <= 128 ? 256 : (typical_cols <= 256 ? 128 : fwd_tx);
+    while (wide > fwd_tx && wide * vec_elems(op->dtype) > typical_rows_f) wide /= 2;  // never wider than the blocks are tall
+    fwd_tx = std::max(fwd_tx, wide);
+    const int64_t tr = fwd_tx * vec_elems(op->dtype);
     eff_fwd_tc = std::max<int64_t>(64, std::min<int64_t>(ctx->fwd_tc, round_up(std::max<int64_t>(tile_bytes / (tr * es), 1), 64)));
     // adjoint: short columns (bytes-weighted mean height) fan a warp out over more columns, and get wider
     // tiles so that a tile is still >= 256 KB
@@ -252,6 +262,8 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   if (adjoint) {
     plan.adj_ru = adj_ru;
     plan.adj_cw = adj_cw;
+  } else {
+    plan.fwd_tx = (int)fwd_tx;
   }
   std::vector<DenseTile> tiles;
   std::vector<FinishItem> loose, fused;
@@ -276,7 +288,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
       Block& b = op->block(i, j);
       if (b.kind == DJETS_BLOCK_DENSE && op->row_len[i] > 0 && op->col_len[j] > 0) {
         dense.push_back({in, &b});
-        nplanes += plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, op->p_fwd_tx, eff_fwd_tc,
+        nplanes += plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, fwd_tx, eff_fwd_tc,
                               eff_adj_tc)
                        .nplanes;
       } else if (b.kind == DJETS_BLOCK_DIAG) {
@@ -320,7 +332,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     if (fuse) {
       const Contribution& cb = dense.front();
       const int64_t i = adjoint ? cb.in : o, j = adjoint ? o : cb.in;
-      const TileShape sh = plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, op->p_fwd_tx, eff_fwd_tc,
+      const TileShape sh = plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, fwd_tx, eff_fwd_tc,
                                       eff_adj_tc);
       strip = adjoint ? sh.tile_cols : sh.tile_rows;
       fused_first = emit_items(fused, strip);
@@ -332,7 +344,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     for (const Contribution& cb : dense) {
       const int64_t i = adjoint ? cb.in : o, j = adjoint ? o : cb.in;
       const int64_t m = op->row_len[i], n = op->col_len[j];
-      const TileShape sh = plan_shape(op->dtype, m, n, adjoint, op->p_fwd_tx, eff_fwd_tc, eff_adj_tc);
+      const TileShape sh = plan_shape(op->dtype, m, n, adjoint, fwd_tx, eff_fwd_tc, eff_adj_tc);
       if (!adjoint) {
         for (int64_t col0 = 0, p = 0; col0 < n; col0 += sh.tile_cols, ++p) {
           for (int64_t row0 = 0; row0 < m; row0 += sh.tile_rows) {
@@ -549,7 +561,7 @@ int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
         ++nops;
         if (!adjoint)
           launch_counted(ctx, *rc, DJETS_K_GEMV_N, [&] {
-            return launch_gemv_n(op->dtype, (int)op->p_fwd_tx, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles, inp,
+            return launch_gemv_n(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles, inp,
                                  plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets}, rc->stream);
           });
         else
