@@ -11,6 +11,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with `-m gpu` under gpurun)")
+    # a fresh checkout has no libdjets_b200.so (built artefacts are git-ignored): build it once, with the
+    # same recipe as __graft_entry__.build(); a failed build surfaces as the package's loud ImportError
+    lib = os.path.join(ROOT, "distributedjets.jl_b200", "libdjets_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "distributedjets.jl_b200", "csrc")], check=False)
 
 
 @pytest.fixture(scope="session")
