@@ -907,9 +907,13 @@ int32_t djets_op_set_dense(djets_op op, int64_t i, int64_t j, const void* host, 
     const size_t bytes = (size_t)b.ld * std::max<int64_t>(n, 1) * es;
     CK(cudaMalloc(&b.d, bytes + 256));
     if (b.ld != m) CK(cudaMemsetAsync(b.d, 0, bytes + 256, rc->stream));
-    if (m * n > 0)
-      CK(cudaMemcpy2DAsync(b.d, (size_t)b.ld * es, host, (size_t)ld * es, (size_t)m * es, (size_t)n,
-                           cudaMemcpyHostToDevice, rc->stream));
+    if (m * n > 0) {
+      if (ld == b.ld)  // contiguous on both sides: one linear DMA (much faster than a pitched copy from pageable memory)
+        CK(cudaMemcpyAsync(b.d, host, (size_t)m * n * es, cudaMemcpyHostToDevice, rc->stream));
+      else
+        CK(cudaMemcpy2DAsync(b.d, (size_t)b.ld * es, host, (size_t)ld * es, (size_t)m * es, (size_t)n,
+                             cudaMemcpyHostToDevice, rc->stream));
+    }
     CK(cudaStreamSynchronize(rc->stream));
   });
 }
