@@ -353,3 +353,27 @@ def test_nan_follows_the_reference_through_zero_blocks(dj, O, ctx4):
     yb = y.getblock(2)
     assert np.isnan(yb[3]) and np.isfinite(np.delete(yb, 3)).all()        # the diagonal block touches one row only
     assert np.array_equal(x[range(6 + 4, 6 + 5)], [np.nan], equal_nan=True)  # x[10:10]
+
+
+def test_dense_block_with_more_than_2_pow_31_elements(dj, ctx1):
+    """Maximum sizes: one dense Float32 block of 46400 x 46400 (2.15e9 elements, 8.6 GB) -- every tile
+    offset must be 64-bit.  A = ones except one marked row and one marked column, so the answers are known."""
+    n = 46400
+    A = np.ones((n, n), dtype=np.float32, order="F")
+    A[n - 1, :] = 2.0                                       # last row
+    A[:, n - 1] = 3.0                                       # last column (corner = 3)
+    op = dj.JopDBlock([[dj.JopDense(A)]], pids=[0], dist=[1, 1], ctx=ctx1)
+    del A
+    x = op.domain().zeros()
+    xs = np.zeros(n, dtype=np.float32)
+    xs[0], xs[n - 1] = 1.0, 0.5
+    x.scatter(xs)
+    y = (op @ x).to_array()
+    assert y[0] == 1.0 + 1.5 and y[n - 2] == 2.5 and y[n - 1] == 2.0 + 1.5
+    assert np.all(y[:n - 1] == 2.5)
+    d = op.range().zeros()
+    ds = np.zeros(n, dtype=np.float32)
+    ds[n - 1], ds[5] = 1.0, 0.25
+    d.scatter(ds)
+    m = (op.T @ d).to_array()
+    assert m[0] == 2.0 + 0.25 and m[n - 1] == 3.0 + 0.75 and np.all(m[:n - 1] == 2.25)
