@@ -1,7 +1,13 @@
-import os, sys, time
+"""How long it takes to build operators (upload of dense block payloads from pageable host memory)."""
+import os
+import sys
+import time
+
 import numpy as np
-sys.path.insert(0, "/root/repo")
-import djets_loader
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import djets_loader  # noqa: E402
+
 dj = djets_loader.load()
 ctx = dj.init(world=1, devices=[0])
 rng = np.random.default_rng(0)
