@@ -13,19 +13,16 @@ Everything that touches data calls libdjets_b200.so; nothing here computes on th
 from __future__ import annotations
 
 import ctypes as C
-import math
 import os
-from typing import Callable, List, Optional, Sequence, Tuple, Union
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import _lib
-from ._lib import DimensionMismatch, DJetsError, NotLocal
-from .partition import (cuts_from_ranges, default_grid, even_cuts, even_ranges, grid_of, ranges_from_cuts,
-                        urange)
+from ._lib import DimensionMismatch, DJetsError
+from .partition import cuts_from_ranges, default_grid, even_cuts, even_ranges, grid_of, urange
 
 _DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64}
-_NP = {_lib.F32: np.dtype(np.float32), _lib.F64: np.dtype(np.float64)}
 
 
 def _dt(dtype) -> int:

@@ -739,6 +739,10 @@ cudaError_t launch_lincomb(int ddtype, void* dest, const LincombArgs& a, long lo
   }
   d.nterms = a.nterms;
   d.unit0 = (a.nterms == 1 && a.coef[0] == 1.0) ? 1 : 0;
+  if (same && d.unit0) {  // `dest .= x` in one element type: a device copy
+    if (dest == a.x[0]) return cudaSuccess;
+    return cudaMemcpyAsync(dest, a.x[0], (size_t)n * elem_size(ddtype), cudaMemcpyDeviceToDevice, stream);
+  }
   if (same && !d.unit0) {
     if (ddtype == 1)
       launch_lincomb_vec<double, double>(reinterpret_cast<double*>(dest), d, n, stream);

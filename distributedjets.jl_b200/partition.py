@@ -7,7 +7,7 @@ inclusive like Julia's; a Julia ``a:b`` is the Python ``range(a, b + 1)``.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 from . import _lib
 
