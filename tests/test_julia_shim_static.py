@@ -1,0 +1,90 @@
+"""Static checks of the Julia ccall shim (it cannot be executed in this image: no Julia).  Every
+symbol it binds must be declared in include/djets.h with the same number of arguments, and every
+argument type must be the Julia spelling of the C type at that position."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "distributedjets.jl_b200", "julia", "DistributedJetsB200.jl")
+HEADER = os.path.join(ROOT, "include", "djets.h")
+
+C2JL = {
+    "int32_t": {"Int32"}, "int64_t": {"Int64"}, "double": {"Float64"}, "float": {"Float32"},
+    "int32_t*": {"Ptr{Int32}"}, "int64_t*": {"Ptr{Int64}"}, "double*": {"Ptr{Float64}"}, "float*": {"Ptr{Float32}"},
+    "uint8_t*": {"Ptr{UInt8}"}, "void*": {"Ptr{Cvoid}"}, "void**": {"Ptr{Ptr{Cvoid}}"}, "char*": {"Cstring", "Ptr{UInt8}"},
+    "djets_ctx": {"Ptr{Cvoid}"}, "djets_vec": {"Ptr{Cvoid}"}, "djets_op": {"Ptr{Cvoid}"},
+    "djets_ctx*": {"Ptr{Ptr{Cvoid}}"}, "djets_vec*": {"Ptr{Ptr{Cvoid}}"}, "djets_op*": {"Ptr{Ptr{Cvoid}}"},
+}
+
+
+def header_signatures():
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    sigs = {}
+    for m in re.finditer(r"\b(?:int32_t|const char\*)\s+(djets_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        name, args = m.group(1), m.group(2).strip()
+        types = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.replace("const", "").strip()
+                stars = a.count("*")
+                base = re.sub(r"[\*\s]+[A-Za-z_0-9]*$", "", a).strip() if stars == 0 else a.split("*")[0].strip()
+                if stars == 0:
+                    base = " ".join(a.split()[:-1]) if len(a.split()) > 1 else a
+                types.append(base + "*" * stars)
+        sigs[name] = types
+    return sigs
+
+
+def split_top_level(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "{(":
+            depth += 1
+        elif ch in "})":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def shim_bindings():
+    src = open(SHIM).read()
+    found = []
+    for m in re.finditer(r"@dj\s+(djets_[a-z0-9_]+)\s+\(((?:[^()]|\([^()]*\))*)\)", src):
+        found.append((m.group(1), split_top_level(m.group(2))))
+    for m in re.finditer(r"ccall\(\(:(djets_[a-z0-9_]+),\s*libdjets\),\s*(\w+),\s*\(((?:[^()]|\([^()]*\))*)\)", src):
+        found.append((m.group(1), split_top_level(m.group(3))))
+    return found
+
+
+def test_shim_symbols_and_arities_match_the_header():
+    sigs = header_signatures()
+    assert len(sigs) >= 50
+    bindings = shim_bindings()
+    assert len(bindings) >= 30
+    for name, jl_types in bindings:
+        assert name in sigs, f"{name} is bound in the Julia shim but not declared in include/djets.h"
+        c_types = sigs[name]
+        assert len(jl_types) == len(c_types), f"{name}: {len(jl_types)} Julia argument types vs {len(c_types)} in the header"
+        for k, (jt, ct) in enumerate(zip(jl_types, c_types)):
+            assert jt in C2JL[ct], f"{name} argument {k + 1}: Julia {jt} vs C {ct}"
+
+
+def test_shim_covers_the_hot_path_entry_points():
+    bound = {name for name, _ in shim_bindings()}
+    for needed in ("djets_ctx_create", "djets_vec_create", "djets_vec_similar", "djets_vec_destroy", "djets_vec_getblock",
+                   "djets_vec_setblock", "djets_vec_getindex", "djets_vec_collect", "djets_vec_scatter", "djets_vec_fill",
+                   "djets_vec_lincomb", "djets_vec_binary", "djets_vec_dot", "djets_vec_norm", "djets_vec_reduce",
+                   "djets_op_create", "djets_op_set_dense", "djets_op_set_diag", "djets_op_finalize", "djets_op_destroy",
+                   "djets_op_mul", "djets_op_mul_adjoint", "djets_op_getblock", "djets_op_perfstat"):
+        assert needed in bound, needed
+
+
+def test_shim_keeps_the_reference_exports():
+    src = open(SHIM).read()
+    assert re.search(r"^export DBArray, JetDSpace, blockmap, localblockindices$", src, flags=re.M)   # src:863
