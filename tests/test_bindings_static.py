@@ -88,3 +88,25 @@ def test_shim_covers_the_hot_path_entry_points():
 def test_shim_keeps_the_reference_exports():
     src = open(SHIM).read()
     assert re.search(r"^export DBArray, JetDSpace, blockmap, localblockindices$", src, flags=re.M)   # src:863
+
+
+def test_python_ctypes_signatures_match_the_header():
+    """The ctypes mirror binds every function with the header's arity and argument types."""
+    import ctypes as C
+    import djets_loader
+    djets_loader.load()
+    import djets_b200._lib as L
+    c2ct = {
+        "int32_t": C.c_int32, "int64_t": C.c_int64, "double": C.c_double, "float": C.c_float,
+        "int32_t*": C.POINTER(C.c_int32), "int64_t*": C.POINTER(C.c_int64), "double*": C.POINTER(C.c_double),
+        "float*": C.POINTER(C.c_float), "uint8_t*": C.POINTER(C.c_uint8), "void*": C.c_void_p,
+        "void**": C.POINTER(C.c_void_p), "char*": C.c_char_p, "djets_ctx": C.c_void_p, "djets_vec": C.c_void_p,
+        "djets_op": C.c_void_p, "djets_ctx*": C.POINTER(C.c_void_p), "djets_vec*": C.POINTER(C.c_void_p),
+        "djets_op*": C.POINTER(C.c_void_p),
+    }
+    sigs = header_signatures()
+    for name, argtypes in L.SIGNATURES.items():
+        want = [c2ct[t] for t in sigs[name]]
+        assert len(argtypes) == len(want), name
+        for k, (a, w) in enumerate(zip(argtypes, want)):
+            assert a is w or a == w, f"{name} argument {k + 1}: {a} vs {w}"
