@@ -37,6 +37,37 @@ void drain_events(RankCtx& rc) {
   rc.pending.clear();
 }
 
+unsigned long long* trace_slot(RankCtx& rc, int kind, int ctas) {
+  static const char* prefix = getenv("DJETS_TRACE");
+  if (!prefix || rc.trace_launches >= kTraceLaunches || ctas > kTraceCtas) return nullptr;
+  if (!rc.d_trace) {
+    CK(cudaMalloc(&rc.d_trace, sizeof(unsigned long long) * 4 * kTraceCtas * kTraceLaunches));
+    CK(cudaMemset(rc.d_trace, 0, sizeof(unsigned long long) * 4 * kTraceCtas * kTraceLaunches));
+  }
+  rc.trace_meta.push_back(kind);
+  rc.trace_meta.push_back(ctas);
+  return rc.d_trace + (size_t)4 * kTraceCtas * rc.trace_launches++;
+}
+
+static void trace_dump(RankCtx& rc) {
+  const char* prefix = getenv("DJETS_TRACE");
+  if (!prefix || !rc.d_trace || rc.trace_launches == 0) return;
+  const std::string path = std::string(prefix) + ".rank" + std::to_string(rc.rank) + ".bin";
+  if (FILE* f = fopen(path.c_str(), "wb")) {
+    std::vector<unsigned long long> h((size_t)4 * kTraceCtas);
+    int n = rc.trace_launches;
+    fwrite(&n, sizeof(int), 1, f);
+    fwrite(rc.trace_meta.data(), sizeof(int), rc.trace_meta.size(), f);
+    for (int l = 0; l < n; ++l) {
+      const int ctas = rc.trace_meta[2 * l + 1];
+      cudaMemcpy(h.data(), rc.d_trace + (size_t)4 * kTraceCtas * l, sizeof(unsigned long long) * 4 * ctas,
+                 cudaMemcpyDeviceToHost);
+      fwrite(h.data(), sizeof(unsigned long long), (size_t)4 * ctas, f);
+    }
+    fclose(f);
+  }
+}
+
 // dst stream waits for everything enqueued so far on src stream
 void stream_after(RankCtx& src, RankCtx& dst) {
   if (&src == &dst) return;
@@ -179,6 +210,8 @@ int32_t djets_ctx_destroy(djets_ctx ctx) {
     for (RankCtx& rc : ctx->ranks) {
       cudaSetDevice(rc.device);
       cudaStreamSynchronize(rc.stream);
+      trace_dump(rc);
+      cudaFree(rc.d_trace);
       if (rc.comm && api) api->CommDestroy(rc.comm);
       for (auto& k : rc.pending) {
         cudaEventDestroy(k.a);
@@ -283,6 +316,8 @@ int32_t djets_ctx_reset_stats(djets_ctx ctx) {
     REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
     for (RankCtx& rc : ctx->ranks) {
       drain_events(rc);
+      rc.trace_launches = 0;
+      rc.trace_meta.clear();
       for (int k = 0; k < DJETS_K_COUNT; ++k) {
         rc.launches[k] = 0;
         rc.ms[k] = 0.0;
@@ -312,7 +347,13 @@ int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
       ctx->ld_policy = value;
     } else if (n == "pdl") {
       REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "pdl in {0,1}");
-      set_pdl((int)value);
+      ctx->pdl = value;
+    } else if (n == "persistent") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "persistent in {0,1}");
+      ctx->persistent = value;
+    } else if (n == "prefetch") {
+      REQUIRE(value >= 0 && value <= (1 << 20), DJETS_ERR_INVALID, "prefetch in 0..1048576 bytes");
+      ctx->prefetch = value;
     } else if (n == "auto_tile") {
       REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "auto_tile in {0,1}");
       ctx->auto_tile = value;
@@ -325,6 +366,7 @@ int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
     } else {
       fail(DJETS_ERR_INVALID, "unknown parameter " + n);
     }
+    ctx->epoch += 1;  // applies captured under the old parameters are re-captured (djets_op.cu: apply)
   });
 }
 

@@ -1,0 +1,345 @@
+// The closed elementwise program of libdjets_b200 (djets_vec_eval): the reference evaluates any
+// `Broadcasted` tree per worker over the local blocks (src/DistributedJets.jl:363-375); a CUDA library
+// cannot run a Julia closure, so the host shims lower the tree to a postfix byte-code over a closed set
+// of operators and ONE streaming kernel interprets it per 128-bit vector: every input is read once,
+// the destination written once, whatever the expression.
+//
+// The interpreter keeps the expression stack in registers: `top` plus D-1 spill levels that are shifted
+// by push / binary-pop with compile-time indices (no local memory); unary operators and the
+// scalar-operand forms (x .+ a, a .* x, max.(x, a), x .^ p ...) touch `top` only.  All inputs of an
+// iteration are loaded before the program runs (several 128-bit loads in flight per thread); products
+// and sums use the non-contracting intrinsics so results round exactly like the unfused broadcast of
+// the reference (bit-identical to NumPy / Julia for + - * / abs sqrt min max neg x^2 x^3).
+#include "djets_kernels.h"
+
+#include <math.h>
+
+namespace djets {
+
+namespace {
+
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  using type = float4;
+  static constexpr int N = 4;
+};
+template <>
+struct Vec16<double> {
+  using type = double2;
+  static constexpr int N = 2;
+};
+
+__device__ __forceinline__ float ev_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double ev_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float ev_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double ev_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float ev_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double ev_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float ev_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double ev_div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float ev_sqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double ev_sqrt(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ float ev_abs(float a) { return fabsf(a); }
+__device__ __forceinline__ double ev_abs(double a) { return fabs(a); }
+__device__ __forceinline__ float ev_pow(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ double ev_pow(double a, double b) { return pow(a, b); }
+__device__ __forceinline__ float ev_exp(float a) { return expf(a); }
+__device__ __forceinline__ double ev_exp(double a) { return exp(a); }
+__device__ __forceinline__ float ev_log(float a) { return logf(a); }
+__device__ __forceinline__ double ev_log(double a) { return log(a); }
+// Julia's min / max propagate NaN (fmin / fmax drop it)
+template <typename A>
+__device__ __forceinline__ A ev_min(A a, A b) {
+  return (a != a) ? a : ((b != b) ? b : (a < b ? a : (b < a ? b : (signbit(a) ? a : b))));
+}
+template <typename A>
+__device__ __forceinline__ A ev_max(A a, A b) {
+  return (a != a) ? a : ((b != b) ? b : (a > b ? a : (b > a ? b : (signbit(a) ? b : a))));
+}
+
+struct EvalDev {
+  unsigned char op[kEvalMaxOps];
+  unsigned char arg[kEvalMaxOps];
+  const void* in[kEvalMaxIn];
+  double sc[kEvalMaxScalars];
+  const double* dsc[kEvalMaxScalars];
+  int in_dtype[kEvalMaxIn];
+  int nops, nin, nsc;
+};
+
+// The interpreter proper over E elements held in registers.  XIN(k, e) yields input k's element e.
+template <typename ACC, int E, int D, int NIN, typename XIN>
+__device__ __forceinline__ void run_program(const EvalDev& a, const ACC* __restrict__ sc, XIN xin, ACC (&top)[E]) {
+  ACC st[D - 1][E];
+#pragma unroll
+  for (int k = 0; k < D - 1; ++k)
+#pragma unroll
+    for (int e = 0; e < E; ++e) st[k][e] = ACC(0);
+#pragma unroll
+  for (int e = 0; e < E; ++e) top[e] = ACC(0);
+
+#define EV_PUSH()                                         \
+  do {                                                    \
+    _Pragma("unroll") for (int k = D - 2; k > 0; --k)    \
+        _Pragma("unroll") for (int e = 0; e < E; ++e) st[k][e] = st[k - 1][e]; \
+    _Pragma("unroll") for (int e = 0; e < E; ++e) st[0][e] = top[e];           \
+  } while (0)
+#define EV_BIN(expr)                                      \
+  do {                                                    \
+    _Pragma("unroll") for (int e = 0; e < E; ++e) {       \
+      const ACC x = st[0][e], y = top[e];                 \
+      top[e] = (expr);                                    \
+    }                                                     \
+    _Pragma("unroll") for (int k = 0; k < D - 2; ++k)     \
+        _Pragma("unroll") for (int e = 0; e < E; ++e) st[k][e] = st[k + 1][e]; \
+  } while (0)
+#define EV_UN(expr)                                       \
+  do {                                                    \
+    _Pragma("unroll") for (int e = 0; e < E; ++e) {       \
+      const ACC x = top[e];                               \
+      top[e] = (expr);                                    \
+    }                                                     \
+  } while (0)
+#define EV_SCL(expr)                                      \
+  do {                                                    \
+    const ACC s = sc[arg];                                \
+    _Pragma("unroll") for (int e = 0; e < E; ++e) {       \
+      const ACC x = top[e];                               \
+      top[e] = (expr);                                    \
+    }                                                     \
+  } while (0)
+
+  for (int pc = 0; pc < a.nops; ++pc) {
+    const int op = a.op[pc], arg = a.arg[pc];
+    switch (op) {
+      case EV_IN:
+        EV_PUSH();
+#pragma unroll
+        for (int k = 0; k < NIN; ++k)
+          if (k == arg) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) top[e] = xin(k, e);
+          }
+        break;
+      case EV_SC: {
+        EV_PUSH();
+        const ACC s = sc[arg];
+#pragma unroll
+        for (int e = 0; e < E; ++e) top[e] = s;
+      } break;
+      case EV_ADD: EV_BIN(ev_add(x, y)); break;
+      case EV_SUB: EV_BIN(ev_sub(x, y)); break;
+      case EV_MUL: EV_BIN(ev_mul(x, y)); break;
+      case EV_DIV: EV_BIN(ev_div(x, y)); break;
+      case EV_POW: EV_BIN(ev_pow(x, y)); break;
+      case EV_MIN: EV_BIN(ev_min(x, y)); break;
+      case EV_MAX: EV_BIN(ev_max(x, y)); break;
+      case EV_NEG: EV_UN(-x); break;
+      case EV_ABS: EV_UN(ev_abs(x)); break;
+      case EV_SQRT: EV_UN(ev_sqrt(x)); break;
+      case EV_SQUARE: EV_UN(ev_mul(x, x)); break;
+      case EV_CUBE: EV_UN(ev_mul(ev_mul(x, x), x)); break;
+      case EV_EXP: EV_UN(ev_exp(x)); break;
+      case EV_LOG: EV_UN(ev_log(x)); break;
+      case EV_ADDS: EV_SCL(ev_add(x, s)); break;
+      case EV_SUBS: EV_SCL(ev_sub(x, s)); break;
+      case EV_RSUBS: EV_SCL(ev_sub(s, x)); break;
+      case EV_MULS: EV_SCL(ev_mul(x, s)); break;
+      case EV_RMULS: EV_SCL(ev_mul(s, x)); break;
+      case EV_DIVS: EV_SCL(ev_div(x, s)); break;
+      case EV_RDIVS: EV_SCL(ev_div(s, x)); break;
+      case EV_POWS: EV_SCL(ev_pow(x, s)); break;
+      case EV_MINS: EV_SCL(ev_min(x, s)); break;
+      case EV_MAXS: EV_SCL(ev_max(x, s)); break;
+      default: break;
+    }
+  }
+#undef EV_PUSH
+#undef EV_BIN
+#undef EV_UN
+#undef EV_SCL
+}
+
+template <typename ACC>
+__device__ __forceinline__ void load_scalars(const EvalDev& a, ACC* sc) {
+  if (threadIdx.x < kEvalMaxScalars) {
+    const int k = threadIdx.x;
+    double v = 0.0;
+    if (k < a.nsc) v = a.dsc[k] ? *a.dsc[k] : a.sc[k];
+    sc[k] = (ACC)v;
+  }
+  __syncthreads();
+}
+
+// Vector path: destination and every input share the element type T.  Each thread iteration covers NV
+// 128-bit vectors per input (grid-strided, so a warp's loads stay fully coalesced), all loaded up front.
+template <typename T, typename ACC, int NV, int D, int NIN>
+__global__ void __launch_bounds__(kThreads) eval_vec_kernel(T* dest /* may alias an input */, EvalDev a, long long n) {
+  using V = typename Vec16<T>::type;
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int E = NV * VEC;
+  __shared__ ACC sc[kEvalMaxScalars];
+  load_scalars<ACC>(a, sc);
+  const long long nvec = (n + VEC - 1) / VEC;  // the last vector may be partial: parts carry >= 256 B of slack for the over-read
+  const long long gstride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += NV * gstride) {
+    V x[NIN][NV];
+#pragma unroll
+    for (int k = 0; k < NIN; ++k)
+      if (k < a.nin) {
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+          const long long idx = i + u * gstride;
+          if (idx < nvec) x[k][u] = reinterpret_cast<const V*>(a.in[k])[idx];
+        }
+      }
+    ACC top[E];
+    run_program<ACC, E, D, NIN>(
+        a, sc, [&](int k, int e) { return (ACC) reinterpret_cast<const T*>(&x[k][e / VEC])[e % VEC]; }, top);
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const long long idx = i + u * gstride;
+      if (idx >= nvec) continue;
+      V o;
+      T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) oe[e] = (T)top[u * VEC + e];
+      if ((idx + 1) * VEC <= n) {
+        reinterpret_cast<V*>(dest)[idx] = o;
+      } else {
+        for (int e = 0; e < VEC; ++e)
+          if (idx * VEC + e < n) dest[idx * VEC + e] = oe[e];
+      }
+    }
+  }
+}
+
+// Generic path: any mix of element types (conversions); one element per thread iteration, in double.
+template <typename TD>
+__global__ void __launch_bounds__(kThreads) eval_generic_kernel(TD* dest, EvalDev a, long long n) {
+  __shared__ double sc[kEvalMaxScalars];
+  load_scalars<double>(a, sc);
+  const long long gstride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += gstride) {
+    double x[kEvalMaxIn];
+#pragma unroll
+    for (int k = 0; k < kEvalMaxIn; ++k)
+      if (k < a.nin)
+        x[k] = a.in_dtype[k] == 0 ? (double) reinterpret_cast<const float*>(a.in[k])[i]
+                                  : reinterpret_cast<const double*>(a.in[k])[i];
+    double top[1];
+    run_program<double, 1, kEvalMaxDepth, kEvalMaxIn>(a, sc, [&](int k, int) { return x[k]; }, top);
+    dest[i] = (TD)top[0];
+  }
+}
+
+int eval_grid(long long work_items) {
+  long long want = (work_items + kThreads - 1) / kThreads;
+  const long long cap = 148LL * 8;
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+template <typename T, typename ACC, int NV, int NIN>
+void launch_vec_d(T* dest, const EvalDev& d, long long n, int depth, cudaStream_t stream) {
+  const long long nvec = (n + Vec16<T>::N - 1) / Vec16<T>::N;
+  const int grid = eval_grid((nvec + NV - 1) / NV);
+  if (depth <= 3)
+    eval_vec_kernel<T, ACC, NV, 3, NIN><<<grid, kThreads, 0, stream>>>(dest, d, n);
+  else
+    eval_vec_kernel<T, ACC, NV, kEvalMaxDepth, NIN><<<grid, kThreads, 0, stream>>>(dest, d, n);
+}
+
+// in-flight bytes per thread are kept near 64: fewer inputs -> more vectors per input per iteration
+template <typename T, typename ACC>
+void launch_vec(T* dest, const EvalDev& d, long long n, int depth, cudaStream_t stream) {
+  if (d.nin <= 1)
+    launch_vec_d<T, ACC, 4, 1>(dest, d, n, depth, stream);
+  else if (d.nin == 2)
+    launch_vec_d<T, ACC, 2, 2>(dest, d, n, depth, stream);
+  else if (d.nin <= 4)
+    launch_vec_d<T, ACC, 1, 4>(dest, d, n, depth, stream);
+  else
+    launch_vec_d<T, ACC, 1, kEvalMaxIn>(dest, d, n, depth, stream);
+}
+
+}  // namespace
+
+int eval_check(const EvalArgs& a, const char** why) {
+  static const char* msg = "";
+  auto bad = [&](const char* m) {
+    msg = m;
+    if (why) *why = msg;
+    return -1;
+  };
+  if (a.nops < 1 || a.nops > kEvalMaxOps) return bad("eval: 1 to 48 operations per program");
+  if (a.nin < 0 || a.nin > kEvalMaxIn) return bad("eval: at most 8 input vectors");
+  if (a.nsc < 0 || a.nsc > kEvalMaxScalars) return bad("eval: at most 16 scalars");
+  int sp = 0, depth = 0;
+  for (int pc = 0; pc < a.nops; ++pc) {
+    const int op = a.op[pc], arg = a.arg[pc];
+    if (op == EV_IN) {
+      if (arg >= a.nin) return bad("eval: input index outside the input list");
+      ++sp;
+    } else if (op == EV_SC) {
+      if (arg >= a.nsc) return bad("eval: scalar index outside the scalar list");
+      ++sp;
+    } else if (op >= EV_ADD && op <= EV_MAX) {
+      if (sp < 2) return bad("eval: binary operator on fewer than two operands");
+      --sp;
+    } else if (op >= EV_NEG && op <= EV_LOG) {
+      if (sp < 1) return bad("eval: unary operator on an empty stack");
+    } else if (op >= EV_ADDS && op <= EV_MAXS) {
+      if (sp < 1) return bad("eval: scalar-operand operator on an empty stack");
+      if (arg >= a.nsc) return bad("eval: scalar index outside the scalar list");
+    } else {
+      return bad("eval: unknown operation code");
+    }
+    depth = sp > depth ? sp : depth;
+    if (sp > kEvalMaxDepth) return bad("eval: expression deeper than 8 operands");
+  }
+  if (sp != 1) return bad("eval: the program must leave exactly one value");
+  return depth;
+}
+
+cudaError_t launch_eval(int ddtype, void* dest, const EvalArgs& a, long long n, int wide, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int depth = eval_check(a, nullptr);
+  if (depth < 0) return cudaErrorInvalidValue;
+  EvalDev d;
+  bool same = true;
+  for (int k = 0; k < kEvalMaxOps; ++k) {
+    d.op[k] = k < a.nops ? a.op[k] : 0;
+    d.arg[k] = k < a.nops ? a.arg[k] : 0;
+  }
+  for (int k = 0; k < kEvalMaxIn; ++k) {
+    d.in[k] = k < a.nin ? a.in[k] : nullptr;
+    d.in_dtype[k] = k < a.nin ? a.in_dtype[k] : ddtype;
+    if (k < a.nin && a.in_dtype[k] != ddtype) same = false;
+  }
+  for (int k = 0; k < kEvalMaxScalars; ++k) {
+    d.sc[k] = k < a.nsc ? a.sc[k] : 0.0;
+    d.dsc[k] = k < a.nsc ? a.dsc[k] : nullptr;
+  }
+  d.nops = a.nops;
+  d.nin = a.nin;
+  d.nsc = a.nsc;
+  if (same) {
+    if (ddtype == 1)
+      launch_vec<double, double>(reinterpret_cast<double*>(dest), d, n, depth, stream);
+    else if (wide)
+      launch_vec<float, double>(reinterpret_cast<float*>(dest), d, n, depth, stream);
+    else
+      launch_vec<float, float>(reinterpret_cast<float*>(dest), d, n, depth, stream);
+  } else {
+    const int grid = eval_grid(n);
+    if (ddtype == 1)
+      eval_generic_kernel<double><<<grid, kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), d, n);
+    else
+      eval_generic_kernel<float><<<grid, kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), d, n);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace djets

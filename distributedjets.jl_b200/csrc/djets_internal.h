@@ -74,6 +74,7 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 constexpr int kMaxParts = 1024;
+constexpr int kTraceLaunches = 16, kTraceCtas = 16384;
 
 }  // namespace djets
 
@@ -100,6 +101,11 @@ struct RankCtx {
   // Stream-ordered cache of vector-part allocations: a freed part is handed to the next DBArray of the
   // same size on this rank without a device synchronisation (the reference's non-dotted arithmetic
   // allocates a fresh DBArray per operation, src:353-356, so allocation has to be cheap).
+  // DJETS_TRACE=<file prefix>: per-CTA time stamps of the first kTraceLaunches tile-kernel launches after
+  // the last djets_ctx_reset_stats, written to <prefix>.rank<r>.bin when the context is destroyed
+  unsigned long long* d_trace = nullptr;
+  int trace_launches = 0;
+  std::vector<int> trace_meta;  // per traced launch: kind, CTAs
   std::multimap<size_t, char*> vec_cache;
   size_t vec_cache_bytes = 0;
 };
@@ -114,6 +120,13 @@ struct djets_ctx_s {
   int64_t auto_tile = 1;  // shrink tiles of small operators so a launch still fills the SMs
   int64_t graphs = 1;  // replay multi-launch applies as CUDA graphs
   int64_t p2p = 1;     // kernels of one rank read / write another local rank's buffers in place
+  int64_t pdl = 1;     // programmatic dependent launch of the tile kernels
+  // 1: the tile kernels run one resident wave of CTAs that draw tiles from a device-side queue; 0: one CTA
+  // per tile, handed out by the hardware scheduler.  Measured on B200 (profiles/r02_persistent_ab.txt): the
+  // queue is 2-3 % slower on 0.5 GiB shards and 0.5 % slower on 4 GiB, so it is off by default.
+  int64_t persistent = 0;
+  int64_t prefetch = 32768;  // bytes each first-wave CTA prefetches to L2 ahead of the dependency wait
+  uint64_t epoch = 0;  // bumped by every set_param: captured graphs of an older epoch are dropped
   std::vector<char> peer;  // peer[a * ndev + b]: device a can address device b's memory
   int ndev = 0;
   bool can_address(const RankCtx& a, const RankCtx& b) const {
@@ -133,6 +146,7 @@ void use(RankCtx& rc);
 cudaEvent_t pool_event(RankCtx& rc);
 void drain_events(RankCtx& rc);
 void stream_after(RankCtx& src, RankCtx& dst);  // dst stream waits for everything enqueued so far on src stream
+unsigned long long* trace_slot(RankCtx& rc, int kind, int ctas);  // nullptr unless DJETS_TRACE is set
 
 template <class F>
 void launch_counted(djets_ctx ctx, RankCtx& rc, int kind, F&& f) {

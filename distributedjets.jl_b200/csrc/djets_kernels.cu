@@ -13,6 +13,9 @@
 
 #include <math.h>
 
+#include <set>
+#include <utility>
+
 namespace djets {
 
 // ------------------------------------------------------------------------------------------------
@@ -102,20 +105,46 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// DJETS_TRACE: per-CTA time stamps (start, dependency released, input staged, done) of one launch
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int tile, int slot) {
+  if (trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[(size_t)tile * 4 + slot] = t;
+  }
+}
+
+// L2 prefetch of a contiguous run of an immutable block payload (TMA bulk prefetch, one instruction per
+// run; address and size 16-byte aligned).  Issued by the CTAs of a launch's first wave ahead of
+// griddepcontrol.wait: while the predecessor kernel drains, the idle HBM bandwidth already pulls this
+// kernel's first tiles towards L2.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Asynchronous two-step form used by the persistent tile loops: stage_issue starts the copy of a tile's
+// input slice (one elected thread arms the mbarrier and issues the bulk copy; pad elements are zeroed by
+// all threads) and returns whether the bulk path applies (CTA-uniform); stage_wait completes it: the bulk
+// path polls the mbarrier phase, the fallback copies with plain loads.  Both end in a CTA barrier.
+__device__ __forceinline__ void mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
 template <typename T>
-__device__ __forceinline__ void stage_vector(T* __restrict__ dst, const T* __restrict__ src, int n, int pad_to,
-                                             uint64_t* bar) {
-  const int tid = threadIdx.x;
+__device__ __forceinline__ bool stage_bulk_ok(const T* src, int n) {
   const uint32_t bytes = (uint32_t)n * (uint32_t)sizeof(T);
-  const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0) && bytes >= 512;
+  return ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0) && bytes >= 512;
+}
+
+template <typename T>
+__device__ __forceinline__ bool stage_issue(T* __restrict__ dst, const T* __restrict__ src, int n, int pad_to,
+                                            uint64_t* bar) {
+  const bool bulk = stage_bulk_ok(src, n);
   if (bulk) {
-    const uint32_t b = smem_u32(bar);
-    if (tid == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
+      const uint32_t b = smem_u32(bar);
+      const uint32_t bytes = (uint32_t)n * (uint32_t)sizeof(T);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
       asm volatile(
           "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -123,23 +152,30 @@ __device__ __forceinline__ void stage_vector(T* __restrict__ dst, const T* __res
           "l"(src), "r"(bytes), "r"(b)
           : "memory");
     }
-    for (int i = n + tid; i < pad_to; i += blockDim.x) dst[i] = T(0);
-    // all threads wait for the bytes to land (phase 0)
+    for (int i = n + threadIdx.x; i < pad_to; i += blockDim.x) dst[i] = T(0);
+  }
+  return bulk;
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_wait(bool bulk, T* __restrict__ dst, const T* __restrict__ src, int n,
+                                           int pad_to, uint64_t* bar, uint32_t parity) {
+  if (bulk) {
+    const uint32_t b = smem_u32(bar);
     uint32_t done = 0;
     while (!done) {
       asm volatile(
           "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
           "selp.u32 %0, 1, 0, p;\n\t}"
           : "=r"(done)
-          : "r"(b)
+          : "r"(b), "r"(parity)
           : "memory");
     }
-    __syncthreads();
   } else {
-    for (int i = tid; i < pad_to; i += blockDim.x) dst[i] = (i < n) ? src[i] : T(0);
-    __syncthreads();
+    for (int i = threadIdx.x; i < pad_to; i += blockDim.x) dst[i] = (i < n) ? src[i] : T(0);
   }
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -235,109 +271,169 @@ __device__ __forceinline__ void finish_item(const FinishItem& it, const DiagTerm
 // Ticket protocol of a fused strip: every contributing CTA publishes its plane (fence), takes a
 // ticket, and the CTA holding the last ticket sums all planes and rearms the ticket for the next apply.
 template <typename T>
-__device__ __forceinline__ void fused_finish(const DenseTile& t, const FusedFinish& ff, const T* __restrict__ in,
+__device__ __forceinline__ void fused_finish(int fin, const FusedFinish& ff, const T* __restrict__ in,
                                              const T* W, T* __restrict__ out) {
   __shared__ int s_last;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned old = atomicAdd(ff.tickets + t.fin, 1u);
-    s_last = (old + 1u == (unsigned)ff.items[t.fin].nplanes) ? 1 : 0;
+    const unsigned old = atomicAdd(ff.tickets + fin, 1u);
+    s_last = (old + 1u == (unsigned)ff.items[fin].nplanes) ? 1 : 0;
   }
   __syncthreads();
   if (s_last) {
     __threadfence();
-    finish_item<T, true>(ff.items[t.fin], ff.diags, in, W, nullptr, out);
-    if (threadIdx.x == 0) ff.tickets[t.fin] = 0u;
+    finish_item<T, true>(ff.items[fin], ff.diags, in, W, nullptr, out);
+    if (threadIdx.x == 0) ff.tickets[fin] = 0u;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent tile loop shared by both GEMV kernels.  The grid is one resident wave of CTAs (or fewer);
+// CTA b starts on tile b and then draws further tiles from an atomic counter, so tiles are handed out
+// in table order -- largest first, the last wave's worth cut finer by the scheduler -- to whichever CTA
+// frees up.  While a tile is being processed the next one is already known: its input slice is staged
+// into the other shared-memory buffer by a bulk copy, and (forward) its first batch of matrix loads is
+// issued before the current tile's epilogue.  Draws run two tiles ahead, so the atomic's round trip is never
+// waited for; every CTA makes exactly two draws past the table, and the CTA that makes the last draw of
+// the launch (ntiles + gridDim.x in total) rearms the counter for the next launch.
+// ------------------------------------------------------------------------------------------------
+struct TileQueue {
+  int ntiles;
+  unsigned* counter;  // zero between launches
+};
+
 // Forward dense tiles: partial[r] = sum_c A[r,c] x[c].  A is column-major, so a thread owns VEC
 // consecutive rows (one 128-bit load per column) and walks the columns; the CTA is TX threads wide
 // along the rows and TY = 256/TX column groups deep; the TY partial strips are summed in shared
 // memory in a fixed order.  U independent 128-bit loads are in flight per thread.
-// ------------------------------------------------------------------------------------------------
 template <typename T, int TX, int POLICY>
-__global__ void __launch_bounds__(kThreads) gemv_n_kernel(const DenseTile* __restrict__ tiles,
-                                                          const T* __restrict__ in, T* W, T* __restrict__ out,
-                                                          FusedFinish ff) {
+__global__ void __launch_bounds__(kThreads, 4) gemv_n_kernel(const DenseTile* __restrict__ tiles, TileQueue q,
+                                                             const T* __restrict__ in, T* W, T* __restrict__ out,
+                                                             FusedFinish ff, Prefetch pf) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   constexpr int TY = kThreads / TX;
   constexpr int TR = TX * VEC;
   constexpr int U = 8;
-  __shared__ __align__(128) T xs[kFwdMaxTC];
+  __shared__ __align__(128) T xs[2][kFwdMaxTC];
   __shared__ __align__(16) T red[(TY > 1) ? TY * TR : 1];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ int s_next[2];
 
   griddep_launch_dependents();
-  const DenseTile t = tiles[blockIdx.x];
+  int cur = blockIdx.x;  // descriptors stay in memory (L1-resident table); only what the hot loop needs is in registers
+  trace_stamp(pf.trace, cur, 0);
   const int tid = threadIdx.x;
-  const int rows = t.rows, cols = t.cols;
 
   uint64_t pol = 0;
   if (POLICY == 1) pol = make_evict_first_policy();
 
   const int tx = tid % TX, ty = tid / TX;
   const int r0 = tx * VEC;
-  T acc[VEC];
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) acc[k] = T(0);
 
-  const long long ld = t.ld;
-  const T* a = reinterpret_cast<const T*>(t.A) + r0 + (long long)ty * ld;
-  const long long cstep = (long long)TY * ld;
-  int c = ty;
-  // first batch of matrix loads goes out before the input vector is even looked at
-  const bool pre = (r0 < rows) && (c + (U - 1) * TY < cols);
-  V v0[U];
-  if (pre) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) v0[u] = ld_stream<POLICY>(reinterpret_cast<const V*>(a + u * cstep), pol);
+  // Ahead of the dependency wait the first-wave CTAs pull the head of their first tile towards L2 (the block
+  // payloads are immutable, so this is legal before the predecessor kernel has finished): one run of
+  // `rows` elements per column.
+  if ((int)blockIdx.x < pf.ctas) {
+    const DenseTile& t = tiles[cur];
+    const uint32_t run = ((uint32_t)t.rows * (uint32_t)sizeof(T)) & ~15u;
+    const int ncol = run ? min(t.cols, (int)(pf.bytes / run)) : 0;
+    const T* base = reinterpret_cast<const T*>(t.A);
+    for (int cc = tid; cc < ncol; cc += kThreads) prefetch_l2_bulk(base + (long long)cc * t.ld, run);
+  }
+  if (tid == 0) {
+    mbar_init(&bar[0]);
+    mbar_init(&bar[1]);
+    mbar_fence_init();
   }
   griddep_wait();
-  stage_vector<T>(xs, in + t.vin, cols, cols, &bar);
+  trace_stamp(pf.trace, cur, 1);
+  __syncthreads();  // barriers initialised
+  // bit 0: staging buffer in use; bits 1,2: phase parity of bar[0], bar[1]; bit 3: current tile staged by bulk copy
+  unsigned state = stage_issue<T>(xs[0], in + tiles[cur].vin, tiles[cur].cols, tiles[cur].cols, &bar[0]) ? 8u : 0u;
+  // Two draws ahead: the tile after `cur` is known at the top of an iteration (its x slice is staged while
+  // `cur` is processed); the draw issued at the top returns during the tile and is published at its end.
+  if (tid == 0) s_next[0] = (int)gridDim.x + (int)atomicAdd(q.counter, 1u);
+  int draw = 0;
 
-  if (r0 < rows) {
-    if (pre) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) fma_vec(acc, v0[u], xs[c + u * TY]);
-      a += U * cstep;
-      c += U * TY;
+  for (int it = 0;; ++it) {
+    const int buf = state & 1u;
+    if (tid == 0) draw = (int)gridDim.x + (int)atomicAdd(q.counter, 1u);
+    {
+      const DenseTile& t = tiles[cur];
+      stage_wait<T>((state & 8u) != 0u, xs[buf], in + t.vin, t.cols, t.cols, &bar[buf], (state >> (1 + buf)) & 1u);
     }
-    for (; c + (U - 1) * TY < cols; c += U * TY) {
-      V v[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = ld_stream<POLICY>(reinterpret_cast<const V*>(a + u * cstep), pol);
-#pragma unroll
-      for (int u = 0; u < U; ++u) fma_vec(acc, v[u], xs[c + u * TY]);
-      a += U * cstep;
+    if (state & 8u) state ^= 2u << buf;
+    trace_stamp(pf.trace, cur, 2);
+    const int nxt = s_next[it & 1];
+    const bool more = nxt < q.ntiles;
+    state &= ~8u;
+    if (more) {
+      const DenseTile& g = tiles[nxt];
+      if (stage_issue<T>(xs[buf ^ 1], in + g.vin, g.cols, g.cols, &bar[buf ^ 1])) state |= 8u;
     }
-    for (; c < cols; c += TY) {
-      V v = ld_stream<POLICY>(reinterpret_cast<const V*>(a), pol);
-      fma_vec(acc, v, xs[c]);
-      a += cstep;
-    }
-  }
 
-  T* dst = (t.direct ? out : W) + t.wout;
-  if (TY > 1) {
+    T acc[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) red[ty * TR + r0 + k] = acc[k];
-    __syncthreads();
-    for (int r = tid; r < rows; r += kThreads) {  // rows <= TR
-      T s = red[r];
+    for (int k = 0; k < VEC; ++k) acc[k] = T(0);
+    {
+      const int rows = tiles[cur].rows, cols = tiles[cur].cols;
+      const long long cstep = (long long)TY * tiles[cur].ld;
+      const T* x = xs[buf];
+      if (r0 < rows) {
+        const T* a = reinterpret_cast<const T*>(tiles[cur].A) + r0 + (long long)ty * tiles[cur].ld;
+        int c = ty;
+        for (; c + (U - 1) * TY < cols; c += U * TY) {
+          V v[U];
 #pragma unroll
-      for (int y = 1; y < TY; ++y) s += red[y * TR + r];
-      dst[r] = s;
+          for (int u = 0; u < U; ++u) v[u] = ld_stream<POLICY>(reinterpret_cast<const V*>(a + u * cstep), pol);
+#pragma unroll
+          for (int u = 0; u < U; ++u) fma_vec(acc, v[u], x[c + u * TY]);
+          a += U * cstep;
+        }
+        for (; c < cols; c += TY) {
+          V v = ld_stream<POLICY>(reinterpret_cast<const V*>(a), pol);
+          fma_vec(acc, v, x[c]);
+          a += cstep;
+        }
+      }
     }
-  } else {
+    {
+      const DenseTile& t = tiles[cur];
+      const int rows = t.rows;
+      T* dst = (t.direct ? out : W) + t.wout;
+      if (TY > 1) {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k)
-      if (r0 + k < rows) dst[r0 + k] = acc[k];
+        for (int k = 0; k < VEC; ++k) red[ty * TR + r0 + k] = acc[k];
+        __syncthreads();
+        for (int r = tid; r < rows; r += kThreads) {  // rows <= TR
+          T sum = red[r];
+#pragma unroll
+          for (int y = 1; y < TY; ++y) sum += red[y * TR + r];
+          dst[r] = sum;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          if (r0 + k < rows) dst[r0 + k] = acc[k];
+      }
+      const int fin = t.fin;
+      if (fin >= 0) fused_finish<T>(fin, ff, in, W, out);
+    }
+    trace_stamp(pf.trace, cur, 3);
+    if (tid == 0) {
+      s_next[(it + 1) & 1] = draw;
+      // every CTA makes two draws past the table: ntiles + gridDim.x draws per launch, the last one rearms the queue
+      if (draw == 2 * (int)gridDim.x + q.ntiles - 1) *q.counter = 0u;
+    }
+    if (!more) break;
+    __syncthreads();  // `red` and the finished tile's x buffer are free again
+    cur = nxt;
+    state ^= 1u;
+    trace_stamp(pf.trace, cur, 0);
+    trace_stamp(pf.trace, cur, 1);
   }
-  if (t.fin >= 0) fused_finish<T>(t, ff, in, W, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -345,138 +441,196 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(const DenseTile* __res
 // streams down them with 128-bit loads (each lane VEC rows, 32 lanes = 512 contiguous bytes per
 // column), RU row chunks unrolled -> CW*RU = 16 independent loads in flight per lane whatever the
 // column height: (RU,CW) = (4,4) for tall columns, (2,8) and (1,16) for short ones; the y slice is
-// staged once per CTA in shared memory and each 128-bit LDS of y is reused for the CW columns; the
-// per-lane sums are combined with a column-halving shuffle butterfly.
+// staged once per tile in shared memory (double-buffered across tiles) and each 128-bit LDS of y is
+// reused for the CW columns; the per-lane sums are combined with a column-halving shuffle butterfly.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int RU, int CW, int POLICY>
-__global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __restrict__ tiles,
+__global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __restrict__ tiles, TileQueue q,
                                                              const T* __restrict__ in, T* W, T* __restrict__ out,
-                                                             FusedFinish ff) {
+                                                             FusedFinish ff, Prefetch pf) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   constexpr int S = 32 * VEC;  // rows one warp covers with one load per lane
-  __shared__ __align__(128) T ys[kAdjMaxTRBytes / sizeof(T)];
-  __shared__ __align__(8) uint64_t bar;
+  constexpr int YN = kAdjMaxTRBytes / sizeof(T);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* ys0 = reinterpret_cast<T*>(smem_raw);
+  T* ys1 = ys0 + YN;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(ys1 + YN);
+  int* s_next = reinterpret_cast<int*>(bar + 2);
 
   griddep_launch_dependents();
-  const DenseTile t = tiles[blockIdx.x];
+  int cur = blockIdx.x;
+  trace_stamp(pf.trace, cur, 0);
+  DenseTile t = tiles[cur];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rows = t.rows, cols = t.cols;
-  const int rowsv = (rows + VEC - 1) / VEC * VEC;  // pad rows of A are zero; pad y with zeros too
+  if ((int)blockIdx.x < pf.ctas) {
+    // the columns of the first pass over the warps, below the first batch of loads: one run per column
+    const int rowsv = (t.rows + VEC - 1) / VEC * VEC;
+    const int ncol = min(t.cols, (kThreads / 32) * CW);
+    const int below = rowsv - RU * S;
+    const uint32_t want = ncol ? (uint32_t)(pf.bytes / ncol) & ~15u : 0u;
+    const uint32_t run = below > 0 ? min(want, ((uint32_t)below * (uint32_t)sizeof(T)) & ~15u) : 0u;
+    const T* base = reinterpret_cast<const T*>(t.A) + RU * S;
+    if (run)
+      for (int cc = tid; cc < ncol; cc += kThreads) prefetch_l2_bulk(base + (long long)cc * t.ld, run);
+  }
+  if (tid == 0) {
+    mbar_init(&bar[0]);
+    mbar_init(&bar[1]);
+    mbar_fence_init();
+  }
   griddep_wait();
-  stage_vector<T>(ys, in + t.vin, rows, rowsv, &bar);
+  trace_stamp(pf.trace, cur, 1);
+  __syncthreads();  // barriers initialised
 
   uint64_t pol = 0;
   if (POLICY == 1) pol = make_evict_first_policy();
 
-  const long long ld = t.ld;
-  const T* A = reinterpret_cast<const T*>(t.A);
-  T* dst = (t.direct ? out : W) + t.wout;
-  const int ngroups = (cols + CW - 1) / CW;
+  int rowsv = (t.rows + VEC - 1) / VEC * VEC;  // pad rows of A are zero; pad y with zeros too
+  bool bulk = stage_issue<T>(ys0, in + t.vin, t.rows, rowsv, &bar[0]);
+  uint32_t par = 0u;  // bit b: phase parity of bar[b]
+  int buf = 0;
 
-  for (int g = warp; g < ngroups; g += kThreads / 32) {
-    const int c0 = g * CW;
-    const int last = cols - 1 - c0;  // columns past the tile edge re-read the last one and are not stored
-    const T* base = A + (long long)c0 * ld + lane * VEC;
-    T acc[CW];
-#pragma unroll
-    for (int k = 0; k < CW; ++k) acc[k] = T(0);
+  if (tid == 0) s_next[0] = (int)gridDim.x + (int)atomicAdd(q.counter, 1u);  // two draws ahead, as in the forward kernel
+  int draw = 0;
 
-    int rb = 0;
-    for (; rb + RU * S <= rowsv; rb += RU * S) {
-      V a[RU][CW];
-#pragma unroll
-      for (int u = 0; u < RU; ++u)
-#pragma unroll
-        for (int k = 0; k < CW; ++k)
-          a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
-#pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
-#pragma unroll
-        for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[u][k], y);
-      }
+  for (int it = 0;; ++it) {
+    T* ys = buf ? ys1 : ys0;
+    if (tid == 0) draw = (int)gridDim.x + (int)atomicAdd(q.counter, 1u);
+    stage_wait<T>(bulk, ys, in + t.vin, t.rows, rowsv, &bar[buf], (par >> buf) & 1u);
+    if (bulk) par ^= 1u << buf;
+    trace_stamp(pf.trace, cur, 2);
+    const int nxt = s_next[it & 1];
+    const bool more = nxt < q.ntiles;
+    bool bulk_n = false;
+    if (more) {
+      const DenseTile& g = tiles[nxt];
+      bulk_n = stage_issue<T>(buf ? ys0 : ys1, in + g.vin, g.rows, (g.rows + VEC - 1) / VEC * VEC, &bar[buf ^ 1]);
     }
-    if (CW == 4) {
-      // tall columns: the remainder is at most RU-1 chunks: pairs of chunks first, then a guarded last one
-      if (RU > 2) {
-        for (; rb + 2 * S <= rowsv; rb += 2 * S) {
-          V a[2][CW];
+
+    const int cols = t.cols;
+    const long long ld = t.ld;
+    const T* A = reinterpret_cast<const T*>(t.A);
+    T* dst = (t.direct ? out : W) + t.wout;
+    const int ngroups = (cols + CW - 1) / CW;
+
+    for (int g = warp; g < ngroups; g += kThreads / 32) {
+      const int c0 = g * CW;
+      const int last = cols - 1 - c0;  // columns past the tile edge re-read the last one and are not stored
+      const T* base = A + (long long)c0 * ld + lane * VEC;
+      T acc[CW];
 #pragma unroll
-          for (int u = 0; u < 2; ++u)
+      for (int k = 0; k < CW; ++k) acc[k] = T(0);
+
+      int rb = 0;
+      for (; rb + RU * S <= rowsv; rb += RU * S) {
+        V av[RU][CW];
 #pragma unroll
-            for (int k = 0; k < CW; ++k)
-              a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
-#pragma unroll
-            for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[u][k], y);
-          }
-        }
-      }
-      for (; rb < rowsv; rb += S) {
-        if (rb + lane * VEC < rowsv) {
-          V a[CW];
+        for (int u = 0; u < RU; ++u)
 #pragma unroll
           for (int k = 0; k < CW; ++k)
-            a[k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb), pol);
-          const V y = *reinterpret_cast<const V*>(ys + rb + lane * VEC);
+            av[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
 #pragma unroll
-          for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[k], y);
-        }
-      }
-    } else if (rb < rowsv) {
-      // short columns: the remainder IS most of the column -- one guarded batch, CW*RU loads in flight
-      V a[RU][CW];
-#pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        const bool ok = rb + u * S + lane * VEC < rowsv;
-#pragma unroll
-        for (int k = 0; k < CW; ++k) {
-          if (ok)
-            a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        if (rb + u * S + lane * VEC < rowsv) {
+        for (int u = 0; u < RU; ++u) {
           const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
 #pragma unroll
-          for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[u][k], y);
+          for (int k = 0; k < CW; ++k) dot_vec(acc[k], av[u][k], y);
         }
       }
-    }
-    // Warp reduction of CW columns at once: while more than one column is live, each butterfly step
-    // also halves the columns a lane keeps (the lanes with the offset bit set keep the upper half), so
-    // CW columns cost CW-1 + (5 - log2 CW) shuffles instead of 5*CW.  The pattern is fixed: deterministic.
-    int width = CW;
+      if (CW == 4) {
+        // tall columns: the remainder is at most RU-1 chunks: pairs of chunks first, then a guarded last one
+        if (RU > 2) {
+          for (; rb + 2 * S <= rowsv; rb += 2 * S) {
+            V av[2][CW];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      if (width > 1) {
-        width >>= 1;
-        const bool upper = (lane & o) != 0;
+            for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int k = 0; k < CW / 2; ++k) {
-          if (k < width) {
-            const T send = upper ? acc[k] : acc[k + width];
-            const T keep = upper ? acc[k + width] : acc[k];
-            acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              for (int k = 0; k < CW; ++k)
+                av[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
+#pragma unroll
+              for (int k = 0; k < CW; ++k) dot_vec(acc[k], av[u][k], y);
+            }
           }
         }
-      } else {
-        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
-      }
-    }
-    // lane bits 16, 8, ... (one per halving step) spell the column a lane ended up with
-    constexpr int kHalvings = (CW == 16) ? 4 : (CW == 8) ? 3 : (CW == 4) ? 2 : (CW == 2) ? 1 : 0;
-    int mycol = 0;
+        for (; rb < rowsv; rb += S) {
+          if (rb + lane * VEC < rowsv) {
+            V av[CW];
 #pragma unroll
-    for (int h = 0; h < kHalvings; ++h) mycol |= ((lane >> (4 - h)) & 1) << (kHalvings - 1 - h);
-    const bool writer = (lane & ((32 >> kHalvings) - 1)) == 0;
-    if (writer && c0 + mycol < cols) dst[c0 + mycol] = acc[0];
+            for (int k = 0; k < CW; ++k)
+              av[k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb), pol);
+            const V y = *reinterpret_cast<const V*>(ys + rb + lane * VEC);
+#pragma unroll
+            for (int k = 0; k < CW; ++k) dot_vec(acc[k], av[k], y);
+          }
+        }
+      } else if (rb < rowsv) {
+        // short columns: the remainder IS most of the column -- one guarded batch, CW*RU loads in flight
+        V av[RU][CW];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          const bool ok = rb + u * S + lane * VEC < rowsv;
+#pragma unroll
+          for (int k = 0; k < CW; ++k) {
+            if (ok)
+              av[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          if (rb + u * S + lane * VEC < rowsv) {
+            const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
+#pragma unroll
+            for (int k = 0; k < CW; ++k) dot_vec(acc[k], av[u][k], y);
+          }
+        }
+      }
+      // Warp reduction of CW columns at once: while more than one column is live, each butterfly step
+      // also halves the columns a lane keeps (the lanes with the offset bit set keep the upper half), so
+      // CW columns cost CW-1 + (5 - log2 CW) shuffles instead of 5*CW.  The pattern is fixed: deterministic.
+      int width = CW;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        if (width > 1) {
+          width >>= 1;
+          const bool upper = (lane & o) != 0;
+#pragma unroll
+          for (int k = 0; k < CW / 2; ++k) {
+            if (k < width) {
+              const T send = upper ? acc[k] : acc[k + width];
+              const T keep = upper ? acc[k + width] : acc[k];
+              acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+        } else {
+          acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+        }
+      }
+      // lane bits 16, 8, ... (one per halving step) spell the column a lane ended up with
+      constexpr int kHalvings = (CW == 16) ? 4 : (CW == 8) ? 3 : (CW == 4) ? 2 : (CW == 2) ? 1 : 0;
+      int mycol = 0;
+#pragma unroll
+      for (int h = 0; h < kHalvings; ++h) mycol |= ((lane >> (4 - h)) & 1) << (kHalvings - 1 - h);
+      const bool writer = (lane & ((32 >> kHalvings) - 1)) == 0;
+      if (writer && c0 + mycol < cols) dst[c0 + mycol] = acc[0];
+    }
+    if (t.fin >= 0) fused_finish<T>(t.fin, ff, in, W, out);
+    trace_stamp(pf.trace, cur, 3);
+    if (tid == 0) {
+      s_next[(it + 1) & 1] = draw;
+      if (draw == 2 * (int)gridDim.x + q.ntiles - 1) *q.counter = 0u;  // the last draw of the launch rearms the queue
+    }
+    if (!more) break;
+    t = tiles[nxt];
+    bulk = bulk_n;
+    rowsv = (t.rows + VEC - 1) / VEC * VEC;
+    cur = nxt;
+    buf ^= 1;
+    trace_stamp(pf.trace, cur, 0);
+    trace_stamp(pf.trace, cur, 1);
   }
-  if (t.fin >= 0) fused_finish<T>(t, ff, in, W, out);
 }
 
 // Loose items: block rows / columns with no dense tile on this rank (diagonal-only: the fused
@@ -596,9 +750,6 @@ __global__ void __launch_bounds__(kThreads) reduce_stage2(const double* __restri
 }
 
 int reduce_max_ctas() { return 148 * 8; }
-
-static int g_pdl = 1;
-void set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
 template <typename T, int KIND>
 static cudaError_t launch_reduce_k(const void* x, const void* y, long long n, double param, double* partials,
@@ -824,70 +975,128 @@ cudaError_t launch_binary(int dtype, int op, void* dest, const void* a, const vo
 // ------------------------------------------------------------------------------------------------
 // launch dispatch for the tile kernels
 // ------------------------------------------------------------------------------------------------
+constexpr size_t kAdjSmemBytes = 2 * kAdjMaxTRBytes + 2 * sizeof(uint64_t) + 2 * sizeof(int);
+
+// Kernels that need more than 48 KB of dynamic shared memory opt in once per (kernel, device).
+static cudaError_t allow_smem(const void* kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (done.count({kernel, dev})) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) done.insert({kernel, dev});
+  return e;
+}
+
 template <typename... Args>
-static cudaError_t launch_tiles(void (*kernel)(Args...), int grid, cudaStream_t stream, Args... args) {
+static cudaError_t launch_tiles(void (*kernel)(Args...), int grid, size_t smem, int pdl, cudaStream_t stream,
+                                Args... args) {
+  cudaError_t e = allow_smem(reinterpret_cast<const void*>(kernel), smem);
+  if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 template <typename T, int POLICY>
-static cudaError_t launch_gemv_n_t(int fwd_tx, const DenseTile* tiles, int ntiles, const void* in, void* W, void* out,
-                                   FusedFinish ff, cudaStream_t stream) {
+static cudaError_t launch_gemv_n_t(int fwd_tx, const DenseTile* tiles, int ntiles, int grid, unsigned* counter,
+                                   const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                                   cudaStream_t stream) {
+  const TileQueue q{ntiles, counter};
   const T* i = reinterpret_cast<const T*>(in);
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
   switch (fwd_tx) {
-    case 32: return launch_tiles(gemv_n_kernel<T, 32, POLICY>, ntiles, stream, tiles, i, w, o, ff);
-    case 64: return launch_tiles(gemv_n_kernel<T, 64, POLICY>, ntiles, stream, tiles, i, w, o, ff);
-    case 128: return launch_tiles(gemv_n_kernel<T, 128, POLICY>, ntiles, stream, tiles, i, w, o, ff);
-    case 256: return launch_tiles(gemv_n_kernel<T, 256, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+    case 32: return launch_tiles(gemv_n_kernel<T, 32, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    case 64: return launch_tiles(gemv_n_kernel<T, 64, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    case 128: return launch_tiles(gemv_n_kernel<T, 128, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    case 256: return launch_tiles(gemv_n_kernel<T, 256, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 
-cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
-                          void* W, void* out, FusedFinish ff, cudaStream_t stream) {
+cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, int ntiles, int grid,
+                          unsigned* counter, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                          cudaStream_t stream) {
   if (ntiles <= 0) return cudaSuccess;
   if (dtype == 0)
-    return ld_policy ? launch_gemv_n_t<float, 1>(fwd_tx, tiles, ntiles, in, W, out, ff, stream)
-                     : launch_gemv_n_t<float, 0>(fwd_tx, tiles, ntiles, in, W, out, ff, stream);
-  return ld_policy ? launch_gemv_n_t<double, 1>(fwd_tx, tiles, ntiles, in, W, out, ff, stream)
-                   : launch_gemv_n_t<double, 0>(fwd_tx, tiles, ntiles, in, W, out, ff, stream);
+    return ld_policy ? launch_gemv_n_t<float, 1>(fwd_tx, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream)
+                     : launch_gemv_n_t<float, 0>(fwd_tx, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream);
+  return ld_policy ? launch_gemv_n_t<double, 1>(fwd_tx, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream)
+                   : launch_gemv_n_t<double, 0>(fwd_tx, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream);
 }
 
 template <typename T, int POLICY>
-static cudaError_t launch_gemv_t_t(int adj_ru, int adj_cw, const DenseTile* tiles, int ntiles, const void* in, void* W,
-                                   void* out, FusedFinish ff, cudaStream_t stream) {
+static cudaError_t launch_gemv_t_t(int adj_ru, int adj_cw, const DenseTile* tiles, int ntiles, int grid,
+                                   unsigned* counter, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                                   cudaStream_t stream) {
+  const TileQueue q{ntiles, counter};
   const T* i = reinterpret_cast<const T*>(in);
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
   // (rows unrolled, columns per warp): tall columns stream down 4 columns, short ones fan out over 16
-  if (adj_cw == 16 && adj_ru == 1) return launch_tiles(gemv_t_kernel<T, 1, 16, POLICY>, ntiles, stream, tiles, i, w, o, ff);
-  if (adj_cw == 8 && adj_ru == 2) return launch_tiles(gemv_t_kernel<T, 2, 8, POLICY>, ntiles, stream, tiles, i, w, o, ff);
-  if (adj_cw == 4 && adj_ru == 4) return launch_tiles(gemv_t_kernel<T, 4, 4, POLICY>, ntiles, stream, tiles, i, w, o, ff);
-  if (adj_cw == 4 && adj_ru == 2) return launch_tiles(gemv_t_kernel<T, 2, 4, POLICY>, ntiles, stream, tiles, i, w, o, ff);
-  if (adj_cw == 4 && adj_ru == 1) return launch_tiles(gemv_t_kernel<T, 1, 4, POLICY>, ntiles, stream, tiles, i, w, o, ff);
+  if (adj_cw == 16 && adj_ru == 1) return launch_tiles(gemv_t_kernel<T, 1, 16, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+  if (adj_cw == 8 && adj_ru == 2) return launch_tiles(gemv_t_kernel<T, 2, 8, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+  if (adj_cw == 4 && adj_ru == 4) return launch_tiles(gemv_t_kernel<T, 4, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+  if (adj_cw == 4 && adj_ru == 2) return launch_tiles(gemv_t_kernel<T, 2, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+  if (adj_cw == 4 && adj_ru == 1) return launch_tiles(gemv_t_kernel<T, 1, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
   return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_gemv_t(int dtype, int adj_ru, int adj_cw, int ld_policy, const DenseTile* tiles, int ntiles,
-                          const void* in, void* W, void* out, FusedFinish ff, cudaStream_t stream) {
+                          int grid, unsigned* counter, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                          cudaStream_t stream) {
   if (ntiles <= 0) return cudaSuccess;
   if (dtype == 0)
-    return ld_policy ? launch_gemv_t_t<float, 1>(adj_ru, adj_cw, tiles, ntiles, in, W, out, ff, stream)
-                     : launch_gemv_t_t<float, 0>(adj_ru, adj_cw, tiles, ntiles, in, W, out, ff, stream);
-  return ld_policy ? launch_gemv_t_t<double, 1>(adj_ru, adj_cw, tiles, ntiles, in, W, out, ff, stream)
-                   : launch_gemv_t_t<double, 0>(adj_ru, adj_cw, tiles, ntiles, in, W, out, ff, stream);
+    return ld_policy ? launch_gemv_t_t<float, 1>(adj_ru, adj_cw, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream)
+                     : launch_gemv_t_t<float, 0>(adj_ru, adj_cw, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream);
+  return ld_policy ? launch_gemv_t_t<double, 1>(adj_ru, adj_cw, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream)
+                   : launch_gemv_t_t<double, 0>(adj_ru, adj_cw, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream);
+}
+
+template <typename K>
+static int resident_ctas(K kernel, size_t smem = 0) {
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (allow_smem(reinterpret_cast<const void*>(kernel), smem) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess) return 0;
+  return sms * per_sm;
+}
+
+template <typename T, int POLICY>
+static int resident_t(int adjoint, int shape, int adj_cw) {
+  if (!adjoint) {
+    switch (shape) {
+      case 32: return resident_ctas(gemv_n_kernel<T, 32, POLICY>);
+      case 64: return resident_ctas(gemv_n_kernel<T, 64, POLICY>);
+      case 128: return resident_ctas(gemv_n_kernel<T, 128, POLICY>);
+      case 256: return resident_ctas(gemv_n_kernel<T, 256, POLICY>);
+    }
+    return 0;
+  }
+  if (adj_cw == 16 && shape == 1) return resident_ctas(gemv_t_kernel<T, 1, 16, POLICY>, kAdjSmemBytes);
+  if (adj_cw == 8 && shape == 2) return resident_ctas(gemv_t_kernel<T, 2, 8, POLICY>, kAdjSmemBytes);
+  if (adj_cw == 4 && shape == 4) return resident_ctas(gemv_t_kernel<T, 4, 4, POLICY>, kAdjSmemBytes);
+  if (adj_cw == 4 && shape == 2) return resident_ctas(gemv_t_kernel<T, 2, 4, POLICY>, kAdjSmemBytes);
+  if (adj_cw == 4 && shape == 1) return resident_ctas(gemv_t_kernel<T, 1, 4, POLICY>, kAdjSmemBytes);
+  return 0;
+}
+
+int gemv_resident_ctas(int dtype, int adjoint, int shape, int adj_cw, int ld_policy) {
+  if (dtype == 0) return ld_policy ? resident_t<float, 1>(adjoint, shape, adj_cw) : resident_t<float, 0>(adjoint, shape, adj_cw);
+  return ld_policy ? resident_t<double, 1>(adjoint, shape, adj_cw) : resident_t<double, 0>(adjoint, shape, adj_cw);
 }
 
 cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,

@@ -50,15 +50,26 @@ struct FusedFinish {
   const DiagTerm* diags;
   unsigned* tickets;  // one per item, zero between launches
 };
-cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, int ntiles, const void* in,
-                          void* W, void* out, FusedFinish ff, cudaStream_t stream);
+// L2 prefetch ahead of the dependency wait: the first `ctas` CTAs of a launch each pull `bytes` of their
+// tile (beyond what their first batch of loads covers) towards L2 while the predecessor kernel drains.
+struct Prefetch {
+  int ctas;
+  int bytes;
+  int pdl;  // launch attribute: programmatic dependent launch on / off (a context parameter)
+  unsigned long long* trace;  // debugging (DJETS_TRACE): 4 globaltimer stamps per CTA of this launch, or nullptr
+};
+// `grid` CTAs (<= ntiles) walk the tile table: CTA b takes tile b, further tiles are drawn from `counter`
+// (one unsigned, zero between launches; rearmed by the launch itself).  grid == ntiles: one tile per CTA.
+cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, int ntiles, int grid,
+                          unsigned* counter, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                          cudaStream_t stream);
 cudaError_t launch_gemv_t(int dtype, int adj_ru, int adj_cw, int ld_policy, const DenseTile* tiles, int ntiles,
-                          const void* in, void* W, void* out, FusedFinish ff, cudaStream_t stream);
+                          int grid, unsigned* counter, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                          cudaStream_t stream);
+// CTAs of the tile kernel variant that fit on the current device at once (occupancy x SM count).
+int gemv_resident_ctas(int dtype, int adjoint, int shape /* fwd_tx | adj_ru */, int adj_cw, int ld_policy);
 cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,
                           const void* W, const void* R, void* out, cudaStream_t stream);
-
-// Programmatic dependent launch of the tile kernels on / off (process-wide tuning switch).
-void set_pdl(int on);
 
 // Elementwise: dest[i] = sum_k coef[k] * x_k[i]; dtypes per operand; compute in double if wide.
 struct LincombArgs {
@@ -71,6 +82,29 @@ cudaError_t launch_lincomb(int ddtype, void* dest, const LincombArgs& a, long lo
 cudaError_t launch_fill(int dtype, void* dest, double a, long long n, cudaStream_t stream);
 cudaError_t launch_binary(int dtype, int op, void* dest, const void* a, const void* b, long long n,
                           cudaStream_t stream);
+
+// Closed elementwise program (djets_vec_eval): postfix byte-code, see DJETS_EV_* in include/djets.h.
+enum {
+  EV_IN = 1, EV_SC = 2,
+  EV_ADD = 3, EV_SUB = 4, EV_MUL = 5, EV_DIV = 6, EV_POW = 7, EV_MIN = 8, EV_MAX = 9,           // pop b, pop a, push a op b
+  EV_NEG = 10, EV_ABS = 11, EV_SQRT = 12, EV_SQUARE = 13, EV_CUBE = 14, EV_EXP = 15, EV_LOG = 16,  // top = f(top)
+  EV_ADDS = 17, EV_SUBS = 18, EV_RSUBS = 19, EV_MULS = 20, EV_RMULS = 21, EV_DIVS = 22, EV_RDIVS = 23,
+  EV_POWS = 24, EV_MINS = 25, EV_MAXS = 26                                                         // top = top op scalar[arg]
+};
+constexpr int kEvalMaxOps = 48, kEvalMaxIn = 8, kEvalMaxScalars = 16, kEvalMaxDepth = 8;
+struct EvalArgs {
+  unsigned char op[kEvalMaxOps], arg[kEvalMaxOps];
+  int nops;
+  const void* in[kEvalMaxIn];
+  int in_dtype[kEvalMaxIn];
+  int nin;
+  double sc[kEvalMaxScalars];          // host value of scalar k ...
+  const double* dsc[kEvalMaxScalars];  // ... unless this is non-null: device-resident scalar read by the kernel
+  int nsc;
+};
+// Validates a program; returns its stack depth (>= 1) or -1 with *why set.
+int eval_check(const EvalArgs& a, const char** why);
+cudaError_t launch_eval(int ddtype, void* dest, const EvalArgs& a, long long n, int wide, cudaStream_t stream);
 
 // Reductions: two deterministic stages.  `partials` holds at least reduce_max_ctas() doubles;
 // `result` is one double (device).  kind: DJETS_RED_* or RED_DOT (100).

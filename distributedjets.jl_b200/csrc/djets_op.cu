@@ -17,6 +17,7 @@ struct DirPlan {
   FinishItem* d_items = nullptr;  // loose items first (finish_kernel), then the fused ones
   int nitems = 0, nloose = 0;
   unsigned* d_tickets = nullptr;  // one per item
+  unsigned* d_counter = nullptr;  // tile queue of the persistent kernels (zero between launches)
   DiagTerm* d_diags = nullptr;
   char* W = nullptr;
   char* stage_in = nullptr;   // input slice received from its owner
@@ -24,6 +25,7 @@ struct DirPlan {
   char* R = nullptr;          // planes received from the other cells of the grid row / column
   int adj_ru = 4, adj_cw = 4;  // adjoint kernel shape chosen for this cell (rows unrolled, columns per warp)
   int fwd_tx = 64;             // forward kernel shape chosen for this cell (threads along the rows)
+  int wave = 0;                // CTAs of this cell's tile kernel that are resident at once (first wave)
 };
 
 struct Cell {
@@ -58,6 +60,7 @@ struct djets_op_s {
   std::vector<GraphEntry> graphs[2];
   std::vector<std::vector<const void*>> seen[2];
   uint64_t graph_clock = 0;
+  uint64_t graph_epoch = 0;  // context parameter epoch the cached graphs were captured under
   bool graphs_broken = false;
   bool perfstat = false;  // time every cell's share of each apply (replaces Jets.perfstat, src:723-745)
   int enqueue_ops[2] = {0, 0};  // launches + copies of one apply, counted on the first direct run
@@ -131,6 +134,7 @@ void free_plan(DirPlan& p) {
   cudaFree(p.d_tiles);
   cudaFree(p.d_items);
   cudaFree(p.d_tickets);
+  cudaFree(p.d_counter);
   cudaFree(p.d_diags);
   cudaFree(p.W);
   cudaFree(p.stage_in);
@@ -265,6 +269,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   } else {
     plan.fwd_tx = (int)fwd_tx;
   }
+  plan.wave = gemv_resident_ctas(op->dtype, adjoint ? 1 : 0, adjoint ? adj_ru : (int)fwd_tx, adj_cw, (int)op->p_ld_policy);
   std::vector<DenseTile> tiles;
   std::vector<FinishItem> loose, fused;
   std::vector<DiagTerm> diags;
@@ -391,6 +396,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   plan.d_tiles = upload(tiles);
   plan.d_items = upload(items);
   plan.d_tickets = reinterpret_cast<unsigned*>(dalloc(items.size() * sizeof(unsigned)));
+  plan.d_counter = reinterpret_cast<unsigned*>(dalloc(sizeof(unsigned)));
   plan.d_diags = upload(diags);
   plan.W = dalloc((size_t)wtotal * es);
   // exchange buffers
@@ -481,6 +487,13 @@ void perfstat_mark(djets_op op, bool begin) {
 
 int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint);
 
+// CTAs launched for a cell's tile kernel: one resident wave that walks the tile table (persistent), or one
+// CTA per tile.
+int tile_grid(djets_ctx ctx, const DirPlan& plan) {
+  if (!ctx->persistent || plan.wave <= 0) return plan.ntiles;
+  return std::min(plan.ntiles, plan.wave);
+}
+
 int apply_enqueue_timed(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   perfstat_mark(op, true);
   const int n = apply_enqueue(op, out, in, adjoint);
@@ -561,13 +574,19 @@ int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
         ++nops;
         if (!adjoint)
           launch_counted(ctx, *rc, DJETS_K_GEMV_N, [&] {
-            return launch_gemv_n(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles, inp,
-                                 plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets}, rc->stream);
+            return launch_gemv_n(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles,
+                                 tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets},
+                                 Prefetch{plan.wave, (int)ctx->prefetch, (int)ctx->pdl,
+                                          trace_slot(*rc, DJETS_K_GEMV_N, plan.ntiles)},
+                                 rc->stream);
           });
         else
           launch_counted(ctx, *rc, DJETS_K_GEMV_T, [&] {
             return launch_gemv_t(op->dtype, plan.adj_ru, plan.adj_cw, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles,
-                                 inp, plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets}, rc->stream);
+                                 tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets},
+                                 Prefetch{plan.wave, (int)ctx->prefetch, (int)ctx->pdl,
+                                          trace_slot(*rc, DJETS_K_GEMV_T, plan.ntiles)},
+                                 rc->stream);
           });
       }
       if (!owner && plan.nloose > 0) {
@@ -649,6 +668,10 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   check_vec(op, in, adjoint, adjoint ? "mul!(m, A', d): d" : "mul!(d, A, m): m");
   REQUIRE(out != in, DJETS_ERR_INVALID, "mul!: output aliases input");
   finalize_op(op);
+  if (op->graph_epoch != ctx->epoch) {  // a tuning parameter changed since the graphs were captured
+    clear_graphs(op);
+    op->graph_epoch = ctx->epoch;
+  }
   const int dir = adjoint ? 1 : 0;
   // Graph replay pays when an apply is a chain of many small launches and copies (grids on few GPUs,
   // small blocks).  It needs every rank of the operator in this process (NCCL stays outside graphs)
