@@ -18,6 +18,11 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_MISMATCH, ERR_UNSUPPORTED, ERR_NOT_LOCA
 (RED_SUM, RED_MIN, RED_MAX, RED_ABSSUM, RED_ABSMAX, RED_ABSMIN, RED_SUMSQ, RED_NNZ, RED_SUMPOW,
  RED_SUMSQ_SHIFT) = range(10)
 K_GEMV_N, K_GEMV_T, K_FINISH, K_REDUCE, K_ELTWISE, K_COUNT = range(6)
+# operation codes of djets_vec_eval (DJETS_EV_*) and djets_scalar_op (DJETS_SC_*)
+(EV_IN, EV_SC, EV_ADD, EV_SUB, EV_MUL, EV_DIV, EV_POW, EV_MIN, EV_MAX, EV_NEG, EV_ABS, EV_SQRT, EV_SQUARE, EV_CUBE,
+ EV_EXP, EV_LOG, EV_ADDS, EV_SUBS, EV_RSUBS, EV_MULS, EV_RMULS, EV_DIVS, EV_RDIVS, EV_POWS, EV_MINS,
+ EV_MAXS) = range(1, 27)
+SC_ADD, SC_SUB, SC_MUL, SC_DIV, SC_NEG, SC_SQRT, SC_COPY, SC_ABS, SC_MAX, SC_MIN = range(10)
 KERNEL_NAMES = {K_GEMV_N: "gemv_n", K_GEMV_T: "gemv_t", K_FINISH: "finish", K_REDUCE: "reduce",
                 K_ELTWISE: "eltwise"}
 
@@ -89,6 +94,23 @@ SIGNATURES = {
     "djets_vec_norm": [vp, f64, p_f64],
     "djets_vec_reduce": [vp, i32, f64, p_f64],
     "djets_vec_reduce_parts": [vp, i32, f64, p_f64],
+    "djets_vec_scatter_async": [vp, vp],
+    "djets_vec_collect_async": [vp, vp],
+    "djets_vec_eval": [vp, C.POINTER(C.c_uint8), i32, p_vp, i32, p_f64, p_vp, i32, i32],
+    "djets_vec_dot_s": [vp, vp, vp],
+    "djets_vec_norm_s": [vp, f64, vp],
+    "djets_vec_reduce_s": [vp, i32, f64, vp],
+    "djets_ctx_mark": [vp, i32],
+    "djets_ctx_wait_mark": [vp, i32],
+    "djets_ctx_capture_begin": [vp],
+    "djets_ctx_capture_end": [vp, p_vp],
+    "djets_graph_launch": [vp],
+    "djets_graph_destroy": [vp],
+    "djets_scalar_create": [vp, p_vp],
+    "djets_scalar_destroy": [vp],
+    "djets_scalar_set": [vp, f64],
+    "djets_scalar_get": [vp, p_f64],
+    "djets_scalar_op": [vp, i32, vp, vp, i32],
     "djets_op_create": [vp, i32, i64, i64, p_i64, p_i64, i32, i32, p_i32, p_i64, p_i64, i32, p_vp],
     "djets_op_set_dense": [vp, i64, i64, vp, i64],
     "djets_op_set_diag": [vp, i64, i64, vp],

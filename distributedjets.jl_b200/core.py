@@ -102,10 +102,118 @@ class Context:
     def reset_stats(self) -> None:
         _lib.call("djets_ctx_reset_stats", self.h)
 
+    # stream marks and captured sequences -------------------------------------------------------------
+    def mark(self, slot: int = 0) -> None:
+        """Record mark ``slot`` (0..7) on every local rank's stream."""
+        _lib.call("djets_ctx_mark", self.h, int(slot))
+
+    def wait_mark(self, slot: int = 0) -> None:
+        """Block until everything enqueued before mark ``slot`` has finished (later work keeps running)."""
+        _lib.call("djets_ctx_wait_mark", self.h, int(slot))
+
+    def capture(self) -> "_Capture":
+        """``with ctx.capture() as g: ...`` records the stream-ordered calls made inside (mul!, adjoint,
+        ``dot_s`` / ``norm_s``, scalar arithmetic, broadcasts) instead of running them; ``g.launch()``
+        replays the whole sequence with one launch -- a solver iteration without host round trips."""
+        return _Capture(self)
+
     def close(self) -> None:
         if self.h:
             _lib.call("djets_ctx_destroy", self.h)
             self.h = None
+
+
+class Graph:
+    """A captured sequence of calls (djets_graph)."""
+
+    def __init__(self, ctx: "Context"):
+        self.ctx, self.h = ctx, None
+
+    def launch(self) -> None:
+        _lib.call("djets_graph_launch", self.h)
+
+    def close(self) -> None:
+        h, self.h = self.h, None
+        if h and getattr(self.ctx, "h", None):
+            _lib.lib.djets_graph_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Capture:
+    def __init__(self, ctx: "Context"):
+        self.ctx, self.graph = ctx, Graph(ctx)
+
+    def __enter__(self) -> Graph:
+        _lib.call("djets_ctx_capture_begin", self.ctx.h)
+        return self.graph
+
+    def __exit__(self, exc_type, exc, tb):
+        h = C.c_void_p()
+        status = _lib.lib.djets_ctx_capture_end(self.ctx.h, C.byref(h))
+        if exc_type is None:
+            _lib.check(status)
+            self.graph.h = h
+        return False
+
+
+class Scalar:
+    """A scalar resident on the devices (one replica per rank): the result of ``dot_s`` / ``norm_s``, a solver
+    coefficient.  Arithmetic between Scalars runs on the devices, rounded to ``dtype`` like the reference's
+    element-type scalars; ``float(s)`` synchronises."""
+
+    def __init__(self, value: Optional[float] = None, dtype=np.float64, ctx: Optional["Context"] = None):
+        self.ctx = ctx or context()
+        self.dtype = np.dtype(dtype)
+        h = C.c_void_p()
+        _lib.call("djets_scalar_create", self.ctx.h, C.byref(h))
+        self.h = h
+        if value is not None:
+            self.set(value)
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h and getattr(self.ctx, "h", None):
+            try:
+                _lib.lib.djets_scalar_destroy(h)
+            except Exception:
+                pass
+
+    def set(self, v: float) -> "Scalar":
+        _lib.call("djets_scalar_set", self.h, float(self.dtype.type(v)))
+        return self
+
+    def get(self):
+        out = C.c_double()
+        _lib.call("djets_scalar_get", self.h, C.byref(out))
+        return self.dtype.type(out.value)
+
+    def __float__(self):
+        return float(self.get())
+
+    def assign(self, op: int, a: "Scalar", b: Optional["Scalar"] = None) -> "Scalar":
+        """``self = a op b`` on the devices (``_lib.SC_*``), in place."""
+        _lib.call("djets_scalar_op", self.h, int(op), a.h, b.h if b is not None else None, _dt(self.dtype))
+        return self
+
+    def _new(self, op: int, other=None) -> "Scalar":
+        if isinstance(other, (Expr, DBArray, LinExpr)):
+            return NotImplemented                          # scalar (op) lazy vector expression: the Expr side lowers it
+        if other is not None and not isinstance(other, Scalar):
+            other = Scalar(other, self.dtype, self.ctx)
+        return Scalar(None, self.dtype, self.ctx).assign(op, self, other)
+
+    def __add__(self, o): return self._new(_lib.SC_ADD, o)
+    def __sub__(self, o): return self._new(_lib.SC_SUB, o)
+    def __mul__(self, o): return self._new(_lib.SC_MUL, o)
+    def __truediv__(self, o): return self._new(_lib.SC_DIV, o)
+    def __neg__(self): return self._new(_lib.SC_NEG)
+    def sqrt(self): return self._new(_lib.SC_SQRT)
+    def copy(self): return self._new(_lib.SC_COPY)
 
 
 _default_ctx: Optional[Context] = None
@@ -461,6 +569,19 @@ class DBArray:
         _lib.call("djets_vec_scatter", self.h, flat.ctypes.data_as(C.c_void_p))
         return self
 
+    def scatter_async(self, flat: np.ndarray) -> "DBArray":
+        """Stream-ordered ``scatter``: returns at once; ``flat`` (page-locked) must stay unmodified until the
+        next synchronising call."""
+        assert flat.dtype == self.dtype and flat.size == len(self) and flat.flags.c_contiguous
+        _lib.call("djets_vec_scatter_async", self.h, flat.ctypes.data_as(C.c_void_p))
+        return self
+
+    def to_array_async(self, out: np.ndarray) -> np.ndarray:
+        """Stream-ordered ``to_array`` into a page-locked buffer: valid after ``ctx.sync()`` / ``wait_mark``."""
+        assert out.dtype == self.dtype and out.size == len(self) and out.flags.c_contiguous
+        _lib.call("djets_vec_collect_async", self.h, out.ctypes.data_as(C.c_void_p))
+        return out
+
     # fill! and broadcasting (src:332-376) ---------------------------------------------------------------------
     def fill(self, a) -> "DBArray":
         _lib.call("djets_vec_fill", self.h, float(a))
@@ -484,7 +605,26 @@ class DBArray:
             return self.lincomb_([1.0], [src])
         if isinstance(src, LinExpr):
             return self.lincomb_(src.coefs, src.vecs, wide=True if src.float64_scalars else None)
+        if isinstance(src, Expr):
+            return self.eval_(src)
+        if isinstance(src, Scalar):
+            return self.eval_(Expr("sc", src))
         return self.fill(src)
+
+    def eval_(self, expr: "Expr", wide: Optional[bool] = None) -> "DBArray":
+        """``self .= expr`` for any expression over the closed operator set (src:363-375): lowered to a
+        postfix program and evaluated by one streaming kernel.  ``wide``: compute in Float64 although every
+        array is Float32 (default: when a Float64 scalar takes part, as Julia's promotion does)."""
+        prog, vecs, scal, dscal, any64 = _lower(expr)
+        if wide is None:
+            wide = any64
+        n = len(prog) // 2
+        pbuf = (C.c_uint8 * len(prog))(*prog)
+        varr = (C.c_void_p * max(len(vecs), 1))(*[v.h for v in vecs])
+        sarr = (C.c_double * max(len(scal), 1))(*scal)
+        darr = (C.c_void_p * max(len(dscal), 1))(*[d.h if d is not None else None for d in dscal])
+        _lib.call("djets_vec_eval", self.h, pbuf, n, varr, len(vecs), sarr, darr, len(scal), 1 if wide else 0)
+        return self
 
     def mul_(self, a: "DBArray", b: "DBArray") -> "DBArray":
         """``self .= a .* b``."""
@@ -498,15 +638,39 @@ class DBArray:
 
     # non-dotted arithmetic allocates like Julia's (similar(bc) ignores the element type: src:353-356)
     def __rmul__(self, a):
+        if isinstance(a, (DBArray, Expr, Scalar)):
+            return self.similar().eval_(lazy(self) * a)
         return self.similar().lincomb_([a], [self], wide=True)
 
     __mul__ = __rmul__
 
-    def __add__(self, other: "DBArray"):
+    def __add__(self, other):
+        if not isinstance(other, DBArray):
+            return self.similar().eval_(lazy(self) + other)
         return self.similar().lincomb_([1.0, 1.0], [self, other])
 
-    def __sub__(self, other: "DBArray"):
+    def __radd__(self, other):
+        return self.similar().eval_(other + lazy(self))
+
+    def __sub__(self, other):
+        if not isinstance(other, DBArray):
+            return self.similar().eval_(lazy(self) - other)
         return self.similar().lincomb_([1.0, -1.0], [self, other])
+
+    def __rsub__(self, other):
+        return self.similar().eval_(other - lazy(self))
+
+    def __truediv__(self, other):
+        return self.similar().eval_(lazy(self) / other)
+
+    def __rtruediv__(self, other):
+        return self.similar().eval_(other / lazy(self))
+
+    def __pow__(self, p):
+        return self.similar().eval_(lazy(self) ** p)
+
+    def __abs__(self):
+        return self.similar().eval_(abs(lazy(self)))
 
     def __neg__(self):
         return self.similar().lincomb_([-1.0], [self])
@@ -534,6 +698,23 @@ class DBArray:
         out = C.c_double()
         _lib.call("djets_vec_dot", self.h, other.h, C.byref(out))
         return self.dtype.type(out.value)
+
+    def dot_s(self, other: "DBArray", out: Optional[Scalar] = None) -> Scalar:
+        """``dot(x, y)`` left on the devices (no host synchronisation)."""
+        out = out or Scalar(None, self.dtype, self.ctx)
+        _lib.call("djets_vec_dot_s", self.h, other.h, out.h)
+        return out
+
+    def norm_s(self, p: float = 2, out: Optional[Scalar] = None) -> Scalar:
+        """``norm(x, p)`` left on the devices."""
+        out = out or Scalar(None, self.dtype, self.ctx)
+        _lib.call("djets_vec_norm_s", self.h, float(p), out.h)
+        return out
+
+    def reduce_s(self, kind: int, param: float = 0.0, out: Optional[Scalar] = None) -> Scalar:
+        out = out or Scalar(None, self.dtype, self.ctx)
+        _lib.call("djets_vec_reduce_s", self.h, int(kind), float(param), out.h)
+        return out
 
     def sum(self):
         return self.dtype.type(self._reduce(_lib.RED_SUM))
@@ -587,6 +768,150 @@ class LinExpr:
 def dotted(a: float, x: DBArray) -> LinExpr:
     """``a .* x`` as a lazy term: ``d.assign(dotted(a1, d1) + dotted(a2, d2))``."""
     return LinExpr([a], [x])
+
+
+# ------------------------------------------------------------------------------------------------------
+# general lazy broadcast expressions (the dotted forms of src:363-375) and their lowering to the closed
+# elementwise program of djets_vec_eval
+# ------------------------------------------------------------------------------------------------------
+class Expr:
+    """Node of a lazy elementwise expression: ``lazy(x) * 2.0 + abs(lazy(y)) ** 2`` ...; evaluated by
+    ``dest.assign(expr)`` in one pass over the operands."""
+    __array_ufunc__ = None
+    __slots__ = ("kind", "a")
+
+    def __init__(self, kind: str, *a):
+        self.kind, self.a = kind, a
+
+    @staticmethod
+    def wrap(v) -> "Expr":
+        if isinstance(v, Expr):
+            return v
+        if isinstance(v, DBArray):
+            return Expr("in", v)
+        if isinstance(v, LinExpr):
+            e = None
+            for c, x in zip(v.coefs, v.vecs):
+                t = Expr("bin", "*", Expr("sc", c), Expr("in", x))
+                e = t if e is None else Expr("bin", "+", e, t)
+            return e
+        if isinstance(v, (Scalar, int, float, np.integer, np.floating)):
+            return Expr("sc", v)
+        raise DJetsError(_lib.ERR_UNSUPPORTED, f"broadcast operand of type {type(v).__name__} is outside the closed set")
+
+    def _bin(self, op, other, swap=False):
+        o = Expr.wrap(other)
+        return Expr("bin", op, o, self) if swap else Expr("bin", op, self, o)
+
+    def __add__(self, o): return self._bin("+", o)
+    def __radd__(self, o): return self._bin("+", o, True)
+    def __sub__(self, o): return self._bin("-", o)
+    def __rsub__(self, o): return self._bin("-", o, True)
+    def __mul__(self, o): return self._bin("*", o)
+    def __rmul__(self, o): return self._bin("*", o, True)
+    def __truediv__(self, o): return self._bin("/", o)
+    def __rtruediv__(self, o): return self._bin("/", o, True)
+    def __pow__(self, o): return self._bin("^", o)
+    def __neg__(self): return Expr("un", "neg", self)
+    def __abs__(self): return Expr("un", "abs", self)
+
+
+def lazy(x) -> Expr:
+    """Mark ``x`` (a DBArray, a number, a device ``Scalar``) as a lazy broadcast operand."""
+    return Expr.wrap(x)
+
+
+def bc_abs(x) -> Expr: return Expr("un", "abs", Expr.wrap(x))
+def bc_sqrt(x) -> Expr: return Expr("un", "sqrt", Expr.wrap(x))
+def bc_exp(x) -> Expr: return Expr("un", "exp", Expr.wrap(x))
+def bc_log(x) -> Expr: return Expr("un", "log", Expr.wrap(x))
+def bc_max(a, b) -> Expr: return Expr("bin", "max", Expr.wrap(a), Expr.wrap(b))
+def bc_min(a, b) -> Expr: return Expr("bin", "min", Expr.wrap(a), Expr.wrap(b))
+
+
+_BIN = {"+": _lib.EV_ADD, "-": _lib.EV_SUB, "*": _lib.EV_MUL, "/": _lib.EV_DIV, "^": _lib.EV_POW, "min": _lib.EV_MIN,
+        "max": _lib.EV_MAX}
+_BIN_S = {"+": _lib.EV_ADDS, "-": _lib.EV_SUBS, "*": _lib.EV_MULS, "/": _lib.EV_DIVS, "^": _lib.EV_POWS,
+          "min": _lib.EV_MINS, "max": _lib.EV_MAXS}
+_BIN_RS = {"+": _lib.EV_ADDS, "-": _lib.EV_RSUBS, "*": _lib.EV_RMULS, "/": _lib.EV_RDIVS, "min": _lib.EV_MINS,
+           "max": _lib.EV_MAXS}
+_UN = {"neg": _lib.EV_NEG, "abs": _lib.EV_ABS, "sqrt": _lib.EV_SQRT, "exp": _lib.EV_EXP, "log": _lib.EV_LOG}
+
+
+def _is_f64_scalar(v) -> bool:
+    if isinstance(v, Scalar):
+        return v.dtype == np.float64
+    return isinstance(v, (float, np.float64)) and not isinstance(v, np.float32)
+
+
+def _lower(expr: Expr):
+    """Expression tree -> (program bytes, input vectors, host scalars, device scalars, any Float64 operand)."""
+    prog: List[int] = []
+    vecs: List[DBArray] = []
+    scal: List[float] = []
+    dscal: List[Optional[Scalar]] = []
+    state = {"f64": False}
+
+    def vec_index(v: DBArray) -> int:
+        for k, w in enumerate(vecs):
+            if w is v:
+                return k
+        vecs.append(v)
+        if v.dtype == np.float64:
+            state["f64"] = True
+        return len(vecs) - 1
+
+    def scalar_index(v) -> int:
+        if _is_f64_scalar(v):
+            state["f64"] = True
+        if isinstance(v, Scalar):
+            for k, d in enumerate(dscal):
+                if d is v:
+                    return k
+            scal.append(0.0)
+            dscal.append(v)
+        else:
+            scal.append(float(v))
+            dscal.append(None)
+        return len(scal) - 1
+
+    def is_sc(e: Expr) -> bool:
+        return e.kind == "sc"
+
+    def fold(op, x, y):
+        return {"+": x + y, "-": x - y, "*": x * y, "/": x / y, "^": x ** y, "min": min(x, y), "max": max(x, y)}[op]
+
+    def emit(e: Expr) -> None:
+        if e.kind == "in":
+            prog.extend((_lib.EV_IN, vec_index(e.a[0])))
+        elif e.kind == "sc":
+            prog.extend((_lib.EV_SC, scalar_index(e.a[0])))
+        elif e.kind == "un":
+            emit(e.a[1])
+            prog.extend((_UN[e.a[0]], 0))
+        else:
+            op, l, r = e.a
+            if is_sc(l) and is_sc(r) and not isinstance(l.a[0], Scalar) and not isinstance(r.a[0], Scalar):
+                emit(Expr("sc", fold(op, l.a[0], r.a[0])))          # scalar (op) scalar: folded like Julia does per element
+            elif is_sc(r) and not is_sc(l):
+                emit(l)
+                v = r.a[0]
+                if op == "^" and not isinstance(v, Scalar) and float(v) == 2.0:
+                    prog.extend((_lib.EV_SQUARE, 0))                # Julia's literal_pow: x^2 = x*x
+                elif op == "^" and not isinstance(v, Scalar) and float(v) == 3.0:
+                    prog.extend((_lib.EV_CUBE, 0))                  # x^3 = x*x*x
+                else:
+                    prog.extend((_BIN_S[op], scalar_index(v)))
+            elif is_sc(l) and not is_sc(r) and op in _BIN_RS:
+                emit(r)
+                prog.extend((_BIN_RS[op], scalar_index(l.a[0])))
+            else:
+                emit(l)
+                emit(r)
+                prog.extend((_BIN[op], 0))
+
+    emit(expr)
+    return prog, vecs, scal, dscal, state["f64"]
 
 
 # free-function spellings used by the reference's tests ---------------------------------------------------------

@@ -37,6 +37,29 @@ void drain_events(RankCtx& rc) {
   rc.pending.clear();
 }
 
+void flush_vec_caches(djets_ctx ctx) {
+  for (RankCtx& rc : ctx->ranks) {
+    if (rc.vec_cache.empty()) continue;
+    cudaSetDevice(rc.device);
+    cudaStreamSynchronize(rc.stream);
+    for (auto& kv : rc.vec_cache) cudaFree(kv.second);
+    rc.vec_cache.clear();
+    rc.vec_cache_bytes = 0;
+  }
+}
+
+cudaError_t device_alloc(djets_ctx ctx, void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaErrorMemoryAllocation) return e;
+  (void)cudaGetLastError();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!ctx) return cudaErrorMemoryAllocation;
+  flush_vec_caches(ctx);  // freed DBArray parts held for reuse, on every rank of this process
+  cudaSetDevice(dev);
+  return cudaMalloc(p, bytes);
+}
+
 unsigned long long* trace_slot(RankCtx& rc, int kind, int ctas) {
   static const char* prefix = getenv("DJETS_TRACE");
   if (!prefix || rc.trace_launches >= kTraceLaunches || ctas > kTraceCtas) return nullptr;
@@ -165,7 +188,13 @@ int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ran
       CK(cudaEventCreate(&rc.t0));
       CK(cudaEventCreate(&rc.t1));
       CK(cudaMalloc(&rc.d_partials, sizeof(double) * reduce_max_ctas()));
+      CK(cudaMalloc(&rc.d_ticket, sizeof(unsigned)));
+      CK(cudaMemset(rc.d_ticket, 0, sizeof(unsigned)));
       CK(cudaMalloc(&rc.d_result, sizeof(double) * 2 * kMaxParts));
+      CK(cudaMalloc(&rc.d_gather, sizeof(double) * kMaxParts));
+      CK(cudaMalloc(&rc.d_scalars, sizeof(double) * kMaxScalars));
+      CK(cudaMemset(rc.d_scalars, 0, sizeof(double) * kMaxScalars));
+      for (cudaEvent_t& e : rc.marks) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       CK(cudaHostAlloc(&rc.h_result, sizeof(double) * 2 * kMaxParts, cudaHostAllocPortable));
     }
     // peer access between the GPUs this process drives: local->local exchange is in-place peer
@@ -220,6 +249,11 @@ int32_t djets_ctx_destroy(djets_ctx ctx) {
       for (auto e : rc.pool) cudaEventDestroy(e);
       for (auto& kv : rc.vec_cache) cudaFree(kv.second);
       cudaFree(rc.d_partials);
+      cudaFree(rc.d_ticket);
+      cudaFree(rc.d_gather);
+      cudaFree(rc.d_scalars);
+      for (cudaEvent_t e : rc.marks)
+        if (e) cudaEventDestroy(e);
       cudaFree(rc.d_result);
       cudaFreeHost(rc.h_result);
       cudaEventDestroy(rc.ev);
@@ -235,6 +269,7 @@ int32_t djets_ctx_destroy(djets_ctx ctx) {
 int32_t djets_ctx_sync(djets_ctx ctx) {
   return guard([&] {
     REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    no_sync_in_capture(ctx, "djets_ctx_sync");
     for (RankCtx& rc : ctx->ranks) {
       use(rc);
       CK(cudaStreamSynchronize(rc.stream));
@@ -322,6 +357,181 @@ int32_t djets_ctx_reset_stats(djets_ctx ctx) {
         rc.launches[k] = 0;
         rc.ms[k] = 0.0;
       }
+    }
+  });
+}
+
+
+// ---- stream marks: wait for a point of the stream without draining what was enqueued after it ----------
+int32_t djets_ctx_mark(djets_ctx ctx, int32_t slot) {
+  return guard([&] {
+    REQUIRE(ctx && slot >= 0 && slot < 8, DJETS_ERR_INVALID, "mark: slot in 0..7");
+    REQUIRE(!ctx->capturing, DJETS_ERR_INVALID, "mark inside a captured sequence");
+    for (RankCtx& rc : ctx->ranks) CK(cudaEventRecord(rc.marks[slot], rc.stream));
+  });
+}
+
+int32_t djets_ctx_wait_mark(djets_ctx ctx, int32_t slot) {
+  return guard([&] {
+    REQUIRE(ctx && slot >= 0 && slot < 8, DJETS_ERR_INVALID, "wait_mark: slot in 0..7");
+    no_sync_in_capture(ctx, "djets_ctx_wait_mark");
+    for (RankCtx& rc : ctx->ranks) CK(cudaEventSynchronize(rc.marks[slot]));
+  });
+}
+
+// ---- captured sequences -----------------------------------------------------------------------------------
+int32_t djets_ctx_capture_begin(djets_ctx ctx) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    REQUIRE(!ctx->capturing, DJETS_ERR_INVALID, "capture_begin: a capture is already open");
+    REQUIRE((int)ctx->ranks.size() == ctx->world, DJETS_ERR_UNSUPPORTED,
+            "capture needs every rank of the job in this process (NCCL exchanges stay outside graphs)");
+    REQUIRE(!ctx->timing, DJETS_ERR_INVALID, "capture_begin: per-kernel timing is on");
+    RankCtx& origin = ctx->ranks.front();
+    use(origin);
+    for (size_t k = 1; k < ctx->ranks.size(); ++k) stream_after(ctx->ranks[k], origin);  // earlier work of the other ranks
+    CK(cudaStreamBeginCapture(origin.stream, cudaStreamCaptureModeRelaxed));
+    ctx->capturing = true;
+    try {
+      CK(cudaEventRecord(origin.ev_fork, origin.stream));
+      for (size_t k = 1; k < ctx->ranks.size(); ++k) CK(cudaStreamWaitEvent(ctx->ranks[k].stream, origin.ev_fork, 0));
+    } catch (...) {
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(origin.stream, &g);
+      if (g) cudaGraphDestroy(g);
+      (void)cudaGetLastError();
+      ctx->capturing = false;
+      throw;
+    }
+    for (RankCtx& rc : ctx->ranks)
+      for (int k = 0; k < DJETS_K_COUNT; ++k) rc.launches_mark[k] = rc.launches[k];
+  });
+}
+
+int32_t djets_ctx_capture_end(djets_ctx ctx, djets_graph* out) {
+  return guard([&] {
+    REQUIRE(ctx && out, DJETS_ERR_INVALID, "capture_end: null argument");
+    REQUIRE(ctx->capturing, DJETS_ERR_INVALID, "capture_end without capture_begin");
+    RankCtx& origin = ctx->ranks.front();
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaSuccess;
+    for (size_t k = 1; k < ctx->ranks.size() && e == cudaSuccess; ++k) {
+      e = cudaEventRecord(ctx->ranks[k].ev_fork, ctx->ranks[k].stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(origin.stream, ctx->ranks[k].ev_fork, 0);
+    }
+    use(origin);
+    cudaError_t e2 = cudaStreamEndCapture(origin.stream, &graph);
+    ctx->capturing = false;
+    auto g = std::make_unique<djets_graph_s>();
+    g->ctx = ctx;
+    for (RankCtx& rc : ctx->ranks)  // the capture launched nothing: the counters go to the graph, to be added per replay
+      for (int k = 0; k < DJETS_K_COUNT; ++k) {
+        g->launches[k] += rc.launches[k] - rc.launches_mark[k];
+        rc.launches[k] = rc.launches_mark[k];
+      }
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+      CK(e != cudaSuccess ? e : e2);
+    }
+    e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CK(e);
+    *out = g.release();
+  });
+}
+
+int32_t djets_graph_launch(djets_graph g) {
+  return guard([&] {
+    REQUIRE(g && g->exec, DJETS_ERR_INVALID, "null graph");
+    djets_ctx ctx = g->ctx;
+    REQUIRE(!ctx->capturing, DJETS_ERR_INVALID, "graph_launch inside a capture");
+    RankCtx& origin = ctx->ranks.front();
+    for (size_t k = 1; k < ctx->ranks.size(); ++k) stream_after(ctx->ranks[k], origin);
+    use(origin);
+    CK(cudaGraphLaunch(g->exec, origin.stream));
+    if (ctx->ranks.size() > 1) {
+      CK(cudaEventRecord(origin.ev_fork, origin.stream));
+      for (size_t k = 1; k < ctx->ranks.size(); ++k) CK(cudaStreamWaitEvent(ctx->ranks[k].stream, origin.ev_fork, 0));
+    }
+    for (int k = 0; k < DJETS_K_COUNT; ++k) origin.launches[k] += g->launches[k];
+  });
+}
+
+int32_t djets_graph_destroy(djets_graph g) {
+  return guard([&] {
+    if (!g) return;
+    if (g->exec) {
+      cudaSetDevice(g->ctx->ranks.front().device);
+      cudaStreamSynchronize(g->ctx->ranks.front().stream);
+      cudaGraphExecDestroy(g->exec);
+    }
+    delete g;
+  });
+}
+
+// ---- device-resident scalars ------------------------------------------------------------------------------
+int32_t djets_scalar_create(djets_ctx ctx, djets_scalar* out) {
+  return guard([&] {
+    REQUIRE(ctx && out, DJETS_ERR_INVALID, "scalar_create: null argument");
+    int slot;
+    if (!ctx->free_scalars.empty()) {
+      slot = ctx->free_scalars.back();
+      ctx->free_scalars.pop_back();
+    } else {
+      REQUIRE(ctx->next_scalar < kMaxScalars, DJETS_ERR_INVALID, "scalar_create: too many live scalars");
+      slot = ctx->next_scalar++;
+    }
+    auto s = std::make_unique<djets_scalar_s>();
+    s->ctx = ctx;
+    s->slot = slot;
+    *out = s.release();
+  });
+}
+
+int32_t djets_scalar_destroy(djets_scalar s) {
+  return guard([&] {
+    if (!s) return;
+    s->ctx->free_scalars.push_back(s->slot);
+    delete s;
+  });
+}
+
+int32_t djets_scalar_set(djets_scalar s, double v) {
+  return guard([&] {
+    REQUIRE(s, DJETS_ERR_INVALID, "null scalar");
+    for (RankCtx& rc : s->ctx->ranks) {
+      use(rc);
+      launch_counted(s->ctx, rc, DJETS_K_REDUCE, [&] { return launch_scalar_set(v, rc.d_scalars + s->slot, rc.stream); });
+    }
+  });
+}
+
+int32_t djets_scalar_get(djets_scalar s, double* out) {
+  return guard([&] {
+    REQUIRE(s && out, DJETS_ERR_INVALID, "scalar_get: null argument");
+    no_sync_in_capture(s->ctx, "djets_scalar_get");
+    RankCtx& rc = s->ctx->ranks.front();
+    use(rc);
+    CK(cudaMemcpyAsync(out, rc.d_scalars + s->slot, sizeof(double), cudaMemcpyDeviceToHost, rc.stream));
+    CK(cudaStreamSynchronize(rc.stream));
+  });
+}
+
+int32_t djets_scalar_op(djets_scalar out, int32_t op, djets_scalar a, djets_scalar b, int32_t dtype) {
+  return guard([&] {
+    REQUIRE(out && a, DJETS_ERR_INVALID, "scalar_op: null argument");
+    REQUIRE(op >= SC_ADD && op <= SC_MIN, DJETS_ERR_INVALID, "scalar_op: unknown operation");
+    REQUIRE(dtype == DJETS_F32 || dtype == DJETS_F64, DJETS_ERR_INVALID, "scalar_op: dtype");
+    REQUIRE(a->ctx == out->ctx && (!b || b->ctx == out->ctx), DJETS_ERR_INVALID, "scalar_op: scalars of different contexts");
+    const bool binary = op <= SC_DIV || op >= SC_MAX;
+    REQUIRE(!binary || b, DJETS_ERR_INVALID, "scalar_op: binary operation needs two operands");
+    for (RankCtx& rc : out->ctx->ranks) {  // every replica repeats the same arithmetic: no exchange
+      use(rc);
+      launch_counted(out->ctx, rc, DJETS_K_REDUCE, [&] {
+        return launch_scalar_op(dtype, op, rc.d_scalars + a->slot, b ? rc.d_scalars + b->slot : nullptr,
+                                rc.d_scalars + out->slot, rc.stream);
+      });
     }
   });
 }

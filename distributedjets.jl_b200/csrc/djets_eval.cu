@@ -342,4 +342,83 @@ cudaError_t launch_eval(int ddtype, void* dest, const EvalArgs& a, long long n, 
   return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident scalars: the master-side folds of the reference's reductions and the scalar arithmetic
+// of a solver step (alpha = gamma / delta ...) as one-thread kernels, so that a CG-type iteration needs
+// no host round trip and can be captured in a CUDA graph.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ double round_to(int dtype, double v) { return dtype == 0 ? (double)(float)v : v; }
+
+__global__ void fold_kernel(int dtype, int mode, double p, const double* __restrict__ parts, int nparts, double* out,
+                            ScalarPeers peers) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double r;
+  if (mode == FOLD_MIN || mode == FOLD_MAX) {
+    r = mode == FOLD_MIN ? INFINITY : -INFINITY;
+    for (int k = 0; k < nparts; ++k) {
+      const double z = round_to(dtype, parts[k]);
+      r = (r != r || z != z) ? NAN : (mode == FOLD_MIN ? fmin(r, z) : fmax(r, z));
+    }
+  } else if (mode == FOLD_SUM) {
+    r = 0.0;
+    for (int k = 0; k < nparts; ++k) r = round_to(dtype, r + round_to(dtype, parts[k]));
+  } else {  // src:206-209: per-worker norms z, then (sum z^p)^(1/p) in float(real(T))
+    const bool two = mode == FOLD_NORM2;
+    const double pp = round_to(dtype, p);
+    double sum = 0.0;
+    for (int k = 0; k < nparts; ++k) {
+      const double zk = round_to(dtype, two ? sqrt(parts[k]) : pow(parts[k], 1.0 / pp));
+      sum = round_to(dtype, sum + round_to(dtype, two ? zk * zk : pow(zk, pp)));
+    }
+    r = round_to(dtype, two ? sqrt(sum) : pow(sum, round_to(dtype, 1.0 / pp)));
+  }
+  out[0] = r;
+  for (int k = 0; k < peers.n; ++k) peers.p[k][0] = r;
+}
+
+__global__ void scalar_op_kernel(int dtype, int op, const double* a, const double* b, double* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double x = a ? a[0] : 0.0, y = b ? b[0] : 0.0;
+  double r = 0.0;
+  switch (op) {
+    case SC_ADD: r = x + y; break;
+    case SC_SUB: r = x - y; break;
+    case SC_MUL: r = x * y; break;
+    case SC_DIV: r = x / y; break;
+    case SC_NEG: r = -x; break;
+    case SC_SQRT: r = sqrt(x); break;
+    case SC_COPY: r = x; break;
+    case SC_ABS: r = fabs(x); break;
+    case SC_MAX: r = (x != x || y != y) ? NAN : fmax(x, y); break;
+    case SC_MIN: r = (x != x || y != y) ? NAN : fmin(x, y); break;
+  }
+  out[0] = round_to(dtype, r);
+}
+
+__global__ void scalar_set_kernel(double v, double* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = v;
+}
+
+}  // namespace
+
+cudaError_t launch_fold(int dtype, int mode, double p, const double* parts, int nparts, double* out, ScalarPeers peers,
+                        cudaStream_t stream) {
+  fold_kernel<<<1, 32, 0, stream>>>(dtype, mode, p, parts, nparts, out, peers);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scalar_op(int dtype, int op, const double* a, const double* b, double* out, cudaStream_t stream) {
+  if (op < SC_ADD || op > SC_MIN) return cudaErrorInvalidValue;
+  scalar_op_kernel<<<1, 32, 0, stream>>>(dtype, op, a, b, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scalar_set(double v, double* out, cudaStream_t stream) {
+  scalar_set_kernel<<<1, 32, 0, stream>>>(v, out);
+  return cudaGetLastError();
+}
+
 }  // namespace djets

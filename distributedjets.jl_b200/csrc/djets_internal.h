@@ -74,6 +74,7 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 constexpr int kMaxParts = 1024;
+constexpr int kMaxScalars = 4096;
 constexpr int kTraceLaunches = 16, kTraceCtas = 16384;
 
 }  // namespace djets
@@ -90,11 +91,16 @@ struct RankCtx {
   cudaEvent_t ev = nullptr;  // scratch event for cross-stream ordering
   cudaEvent_t ev_fork = nullptr;  // fork / join of a captured apply
   cudaEvent_t t0 = nullptr, t1 = nullptr;
-  double* d_partials = nullptr;  // reduce stage-1 partials
+  double* d_partials = nullptr;  // per-CTA partials of the reduction in flight
+  unsigned* d_ticket = nullptr;  // last-CTA ticket of the reduction kernel (zero between launches)
   double* d_result = nullptr;    // 2*kMaxParts doubles: per-part results, then the all-reduce buffer
   double* h_result = nullptr;    // pinned mirror
+  double* d_gather = nullptr;    // kMaxParts doubles: per-part partials gathered on the root rank of a device-side fold
+  double* d_scalars = nullptr;   // kMaxScalars doubles: this rank's replica of every device-resident scalar
+  cudaEvent_t marks[8] = {};     // djets_ctx_mark / djets_ctx_wait_mark
   ncclComm_t comm = nullptr;
   int64_t launches[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
+  int64_t launches_mark[DJETS_K_COUNT] = {0, 0, 0, 0, 0};  // counters at djets_ctx_capture_begin
   double ms[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
   std::vector<KernelEvent> pending;
   std::vector<cudaEvent_t> pool;
@@ -127,6 +133,9 @@ struct djets_ctx_s {
   int64_t persistent = 0;
   int64_t prefetch = 32768;  // bytes each first-wave CTA prefetches to L2 ahead of the dependency wait
   uint64_t epoch = 0;  // bumped by every set_param: captured graphs of an older epoch are dropped
+  bool capturing = false;  // between djets_ctx_capture_begin and _end: every call is recorded, nothing may synchronise
+  std::vector<int> free_scalars;  // slots of d_scalars not in use
+  int next_scalar = 0;
   std::vector<char> peer;  // peer[a * ndev + b]: device a can address device b's memory
   int ndev = 0;
   bool can_address(const RankCtx& a, const RankCtx& b) const {
@@ -147,6 +156,12 @@ cudaEvent_t pool_event(RankCtx& rc);
 void drain_events(RankCtx& rc);
 void stream_after(RankCtx& src, RankCtx& dst);  // dst stream waits for everything enqueued so far on src stream
 unsigned long long* trace_slot(RankCtx& rc, int kind, int ctas);  // nullptr unless DJETS_TRACE is set
+// cudaMalloc that gives the per-rank caches of freed vector parts back to the driver and retries once on OOM
+cudaError_t device_alloc(djets_ctx ctx, void** p, size_t bytes);
+void flush_vec_caches(djets_ctx ctx);
+inline void no_sync_in_capture(djets_ctx ctx, const char* what) {
+  if (ctx->capturing) fail(DJETS_ERR_INVALID, std::string(what) + " synchronises with the host: not allowed between djets_ctx_capture_begin and _end");
+}
 
 template <class F>
 void launch_counted(djets_ctx ctx, RankCtx& rc, int kind, F&& f) {
@@ -164,6 +179,19 @@ void launch_counted(djets_ctx ctx, RankCtx& rc, int kind, F&& f) {
 }
 
 }  // namespace djets
+
+// A scalar that lives on the devices: one slot of every local rank's d_scalars (replicas hold the same value).
+struct djets_scalar_s {
+  djets_ctx ctx = nullptr;
+  int slot = 0;
+};
+
+// A captured sequence of calls (djets_ctx_capture_begin / _end) replayed with one launch.
+struct djets_graph_s {
+  djets_ctx ctx = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
+};
 
 // ---- DBArray --------------------------------------------------------------------------------------
 struct VecPart {

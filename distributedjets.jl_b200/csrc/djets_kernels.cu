@@ -644,8 +644,8 @@ __global__ void __launch_bounds__(kThreads) finish_kernel(const FinishItem* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// Reductions (dot, norms, extrema, sums): stage 1 = one partial per CTA, stage 2 = one CTA folds
-// the partials.  Grid shape depends only on n, the combine order is fixed -> deterministic.
+// Reductions (dot, norms, extrema, sums) in one launch: one partial per CTA, folded by the last CTA to
+// arrive.  Grid shape depends only on n, the combine order is fixed -> deterministic.
 // ------------------------------------------------------------------------------------------------
 enum { K_SUM = 0, K_MIN, K_MAX, K_ABSSUM, K_ABSMAX, K_ABSMIN, K_SUMSQ, K_NNZ, K_SUMPOW, K_SUMSQ_SHIFT, K_DOT };
 
@@ -656,10 +656,11 @@ __device__ __forceinline__ double red_identity() {
   if (KIND == K_ABSMAX) return 0.0;
   return 0.0;
 }
+// minimum / maximum propagate NaN like Julia's (src:200-203, 236); fmin / fmax would drop it
 template <int KIND>
 __device__ __forceinline__ double red_combine(double a, double b) {
-  if (KIND == K_MIN || KIND == K_ABSMIN) return fmin(a, b);
-  if (KIND == K_MAX || KIND == K_ABSMAX) return fmax(a, b);
+  if (KIND == K_MIN || KIND == K_ABSMIN) return (a != a || b != b) ? NAN : fmin(a, b);
+  if (KIND == K_MAX || KIND == K_ABSMAX) return (a != a || b != b) ? NAN : fmax(a, b);
   return a + b;
 }
 template <int KIND>
@@ -683,6 +684,7 @@ __device__ __forceinline__ double red_map(double x, double y, double param) {
 template <int KIND>
 __device__ __forceinline__ double block_fold(double v) {
   __shared__ double sh[kThreads / 32];
+  __syncthreads();  // a previous fold of this CTA has been read
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = red_combine<KIND>(v, __shfl_xor_sync(0xffffffffu, v, o));
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
@@ -696,9 +698,9 @@ __device__ __forceinline__ double block_fold(double v) {
 }
 
 template <typename T, int KIND>
-__global__ void __launch_bounds__(kThreads) reduce_stage1(const T* __restrict__ x, const T* __restrict__ y,
-                                                          long long n, double param,
-                                                          double* __restrict__ partials) {
+__global__ void __launch_bounds__(kThreads) reduce_kernel(const T* __restrict__ x, const T* __restrict__ y,
+                                                          long long n, double param, double* partials,
+                                                          unsigned* ticket, double* __restrict__ result) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   constexpr int U = 4;
@@ -737,55 +739,66 @@ __global__ void __launch_bounds__(kThreads) reduce_stage1(const T* __restrict__ 
   for (long long j = nvec * VEC + gtid; j < n; j += gstride)
     acc = red_combine<KIND>(acc, red_map<KIND>((double)x[j], KIND == K_DOT ? (double)y[j] : 0.0, param));
   const double r = block_fold<KIND>(acc);
-  if (threadIdx.x == 0) partials[blockIdx.x] = r;
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(kThreads) reduce_stage2(const double* __restrict__ partials, int np,
-                                                          double* __restrict__ result) {
-  double acc = red_identity<KIND>();
-  for (int i = threadIdx.x; i < np; i += kThreads) acc = red_combine<KIND>(acc, partials[i]);
-  const double r = block_fold<KIND>(acc);
-  if (threadIdx.x == 0) result[0] = r;
+  if (gridDim.x == 1) {
+    if (threadIdx.x == 0) result[0] = r;
+    return;
+  }
+  // One launch: every CTA publishes its partial and takes a ticket; the CTA holding the last ticket folds the
+  // partials in index order (the result does not depend on which CTA came last) and rearms the ticket.
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = r;
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) + 1u == gridDim.x) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double fold = red_identity<KIND>();
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) fold = red_combine<KIND>(fold, __ldcg(partials + i));
+  const double total = block_fold<KIND>(fold);
+  if (threadIdx.x == 0) {
+    result[0] = total;
+    *ticket = 0u;
+  }
 }
 
 int reduce_max_ctas() { return 148 * 8; }
 
 template <typename T, int KIND>
 static cudaError_t launch_reduce_k(const void* x, const void* y, long long n, double param, double* partials,
-                                   double* result, cudaStream_t stream) {
+                                   unsigned* ticket, double* result, cudaStream_t stream) {
   constexpr int VEC = VecT<T>::N;
   long long want = (n / VEC + (long long)kThreads * 4 - 1) / ((long long)kThreads * 4);
   int grid = (int)(want < 1 ? 1 : (want > reduce_max_ctas() ? reduce_max_ctas() : want));
-  reduce_stage1<T, KIND><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(y),
-                                                        n, param, partials);
-  reduce_stage2<KIND><<<1, kThreads, 0, stream>>>(partials, grid, result);
+  reduce_kernel<T, KIND><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(y),
+                                                        n, param, partials, ticket, result);
   return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t launch_reduce_t(int kind, const void* x, const void* y, long long n, double param,
-                                   double* partials, double* result, cudaStream_t stream) {
+                                   double* partials, unsigned* ticket, double* result, cudaStream_t stream) {
   switch (kind) {
-    case 0: return launch_reduce_k<T, K_SUM>(x, y, n, param, partials, result, stream);
-    case 1: return launch_reduce_k<T, K_MIN>(x, y, n, param, partials, result, stream);
-    case 2: return launch_reduce_k<T, K_MAX>(x, y, n, param, partials, result, stream);
-    case 3: return launch_reduce_k<T, K_ABSSUM>(x, y, n, param, partials, result, stream);
-    case 4: return launch_reduce_k<T, K_ABSMAX>(x, y, n, param, partials, result, stream);
-    case 5: return launch_reduce_k<T, K_ABSMIN>(x, y, n, param, partials, result, stream);
-    case 6: return launch_reduce_k<T, K_SUMSQ>(x, y, n, param, partials, result, stream);
-    case 7: return launch_reduce_k<T, K_NNZ>(x, y, n, param, partials, result, stream);
-    case 8: return launch_reduce_k<T, K_SUMPOW>(x, y, n, param, partials, result, stream);
-    case 9: return launch_reduce_k<T, K_SUMSQ_SHIFT>(x, y, n, param, partials, result, stream);
-    case RED_DOT: return launch_reduce_k<T, K_DOT>(x, y, n, param, partials, result, stream);
+    case 0: return launch_reduce_k<T, K_SUM>(x, y, n, param, partials, ticket, result, stream);
+    case 1: return launch_reduce_k<T, K_MIN>(x, y, n, param, partials, ticket, result, stream);
+    case 2: return launch_reduce_k<T, K_MAX>(x, y, n, param, partials, ticket, result, stream);
+    case 3: return launch_reduce_k<T, K_ABSSUM>(x, y, n, param, partials, ticket, result, stream);
+    case 4: return launch_reduce_k<T, K_ABSMAX>(x, y, n, param, partials, ticket, result, stream);
+    case 5: return launch_reduce_k<T, K_ABSMIN>(x, y, n, param, partials, ticket, result, stream);
+    case 6: return launch_reduce_k<T, K_SUMSQ>(x, y, n, param, partials, ticket, result, stream);
+    case 7: return launch_reduce_k<T, K_NNZ>(x, y, n, param, partials, ticket, result, stream);
+    case 8: return launch_reduce_k<T, K_SUMPOW>(x, y, n, param, partials, ticket, result, stream);
+    case 9: return launch_reduce_k<T, K_SUMSQ_SHIFT>(x, y, n, param, partials, ticket, result, stream);
+    case RED_DOT: return launch_reduce_k<T, K_DOT>(x, y, n, param, partials, ticket, result, stream);
   }
   return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_reduce(int dtype, int kind, const void* x, const void* y, long long n, double param,
-                          double* partials, double* result, cudaStream_t stream) {
-  return dtype == 0 ? launch_reduce_t<float>(kind, x, y, n, param, partials, result, stream)
-                    : launch_reduce_t<double>(kind, x, y, n, param, partials, result, stream);
+                          double* partials, unsigned* ticket, double* result, cudaStream_t stream) {
+  return dtype == 0 ? launch_reduce_t<float>(kind, x, y, n, param, partials, ticket, result, stream)
+                    : launch_reduce_t<double>(kind, x, y, n, param, partials, ticket, result, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -106,12 +106,27 @@ struct EvalArgs {
 int eval_check(const EvalArgs& a, const char** why);
 cudaError_t launch_eval(int ddtype, void* dest, const EvalArgs& a, long long n, int wide, cudaStream_t stream);
 
-// Reductions: two deterministic stages.  `partials` holds at least reduce_max_ctas() doubles;
-// `result` is one double (device).  kind: DJETS_RED_* or RED_DOT (100).
+// Reductions in one launch.  `partials` holds at least reduce_max_ctas() doubles, `ticket` one unsigned that is
+// zero between launches, `result` one double (device).  kind: DJETS_RED_* or RED_DOT (100).
 enum { RED_DOT = 100 };
 int reduce_max_ctas();
 cudaError_t launch_reduce(int dtype, int kind, const void* x, const void* y, long long n, double param,
-                          double* partials, double* result, cudaStream_t stream);
+                          double* partials, unsigned* ticket, double* result, cudaStream_t stream);
+
+// Master-side fold of per-part partials on the device (the reference folds them on the master, src:200-209,
+// 222, 236, 262, 276), leaving the scalar in device memory: out[0] on this rank and, when `peers` is given, in
+// the replicas other local ranks hold (peer stores).
+enum { FOLD_SUM = 0, FOLD_MIN = 1, FOLD_MAX = 2, FOLD_NORM2 = 3, FOLD_NORMP = 4 };
+struct ScalarPeers {
+  double* p[16];
+  int n;
+};
+cudaError_t launch_fold(int dtype, int mode, double p, const double* parts, int nparts, double* out, ScalarPeers peers,
+                        cudaStream_t stream);
+// Scalar arithmetic on device-resident scalars: out = a op b (b ignored by unary ops), rounded to `dtype`.
+enum { SC_ADD = 0, SC_SUB = 1, SC_MUL = 2, SC_DIV = 3, SC_NEG = 4, SC_SQRT = 5, SC_COPY = 6, SC_ABS = 7, SC_MAX = 8, SC_MIN = 9 };
+cudaError_t launch_scalar_op(int dtype, int op, const double* a, const double* b, double* out, cudaStream_t stream);
+cudaError_t launch_scalar_set(double v, double* out, cudaStream_t stream);
 
 // geometry helpers shared with the scheduler
 inline int vec_elems(int dtype) { return dtype == 0 ? 4 : 2; }

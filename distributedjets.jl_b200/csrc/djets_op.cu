@@ -143,11 +143,13 @@ void free_plan(DirPlan& p) {
   p = DirPlan();
 }
 
+djets_ctx g_alloc_ctx = nullptr;  // context whose vector caches an allocation may reclaim (set by build_plan)
+
 template <class T>
 T* upload(const std::vector<T>& v) {
   if (v.empty()) return nullptr;
   T* d = nullptr;
-  CK(cudaMalloc(&d, v.size() * sizeof(T)));
+  CK(device_alloc(g_alloc_ctx, reinterpret_cast<void**>(&d), v.size() * sizeof(T)));
   CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   return d;
 }
@@ -155,7 +157,7 @@ T* upload(const std::vector<T>& v) {
 char* dalloc(size_t bytes) {
   if (bytes == 0) return nullptr;
   char* d = nullptr;
-  CK(cudaMalloc(&d, bytes + 256));
+  CK(device_alloc(g_alloc_ctx, reinterpret_cast<void**>(&d), bytes + 256));
   CK(cudaMemset(d, 0, bytes + 256));
   return d;
 }
@@ -195,6 +197,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   RankCtx* rc = ctx->local(cell.rank);
   if (!rc) return;
   use(*rc);
+  g_alloc_ctx = ctx;
   DirPlan& plan = adjoint ? cell.adj : cell.fwd;
   free_plan(plan);
   const int es = elem_size(op->dtype);
@@ -667,6 +670,8 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   check_vec(op, out, !adjoint, adjoint ? "mul!(m, A', d): m" : "mul!(d, A, m): d");
   check_vec(op, in, adjoint, adjoint ? "mul!(m, A', d): d" : "mul!(d, A, m): m");
   REQUIRE(out != in, DJETS_ERR_INVALID, "mul!: output aliases input");
+  REQUIRE(!(ctx->capturing && (!op->finalized || op->perfstat)), DJETS_ERR_INVALID,
+          "mul! inside a captured sequence needs a finalised operator without perfstat");
   finalize_op(op);
   if (op->graph_epoch != ctx->epoch) {  // a tuning parameter changed since the graphs were captured
     clear_graphs(op);
@@ -683,7 +688,7 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   bool one_device = true;
   for (const Cell& c : op->cells)
     if (RankCtx* rc = ctx->local(c.rank)) one_device = one_device && rc->device == ctx->ranks.front().device;
-  const bool eligible = ctx->graphs && !ctx->timing && !op->perfstat && all_local && one_device &&
+  const bool eligible = ctx->graphs && !ctx->capturing && !ctx->timing && !op->perfstat && all_local && one_device &&
                         !op->graphs_broken && (op->enqueue_ops[dir] == 0 || op->enqueue_ops[dir] >= 3);
   if (!eligible) {
     op->enqueue_ops[dir] = apply_enqueue_timed(op, out, in, adjoint);
@@ -925,10 +930,13 @@ int32_t djets_op_set_dense(djets_op op, int64_t i, int64_t j, const void* host, 
     Block& b = op->block(i, j);
     release_block(b);
     const int es = elem_size(op->dtype);
+    const int64_t bld = round_up(std::max<int64_t>(m, 1), vec_elems(op->dtype));
+    const size_t bytes = (size_t)bld * std::max<int64_t>(n, 1) * es;
+    void* payload = nullptr;
+    CK(device_alloc(op->ctx, &payload, bytes + 256));  // the block changes kind only once its storage exists
     b.kind = DJETS_BLOCK_DENSE;
-    b.ld = round_up(std::max<int64_t>(m, 1), vec_elems(op->dtype));
-    const size_t bytes = (size_t)b.ld * std::max<int64_t>(n, 1) * es;
-    CK(cudaMalloc(&b.d, bytes + 256));
+    b.ld = bld;
+    b.d = reinterpret_cast<char*>(payload);
     if (b.ld != m) CK(cudaMemsetAsync(b.d, 0, bytes + 256, rc->stream));
     if (m * n > 0) {
       if (ld == b.ld)  // contiguous on both sides: one linear DMA (much faster than a pitched copy from pageable memory)
@@ -953,9 +961,11 @@ int32_t djets_op_set_diag(djets_op op, int64_t i, int64_t j, const void* host) {
     Block& b = op->block(i, j);
     release_block(b);
     const int es = elem_size(op->dtype);
+    void* payload = nullptr;
+    CK(device_alloc(op->ctx, &payload, (size_t)std::max<int64_t>(n, 1) * es + 256));
     b.kind = DJETS_BLOCK_DIAG;
     b.ld = n;
-    CK(cudaMalloc(&b.d, (size_t)std::max<int64_t>(n, 1) * es + 256));
+    b.d = reinterpret_cast<char*>(payload);
     if (n > 0) CK(cudaMemcpyAsync(b.d, host, (size_t)n * es, cudaMemcpyHostToDevice, rc->stream));
     CK(cudaStreamSynchronize(rc->stream));
   });

@@ -9,7 +9,7 @@ namespace {
 
 constexpr size_t kVecCacheLimit = size_t(32) << 30;  // bytes kept per rank before freed parts go back to the driver
 
-char* part_alloc(RankCtx& rc, size_t bytes) {
+char* part_alloc(djets_ctx ctx, RankCtx& rc, size_t bytes) {
   auto it = rc.vec_cache.find(bytes);
   if (it != rc.vec_cache.end()) {
     char* p = it->second;
@@ -17,18 +17,10 @@ char* part_alloc(RankCtx& rc, size_t bytes) {
     rc.vec_cache_bytes -= bytes;
     return p;  // every earlier use was ordered before the free on this rank's stream
   }
-  char* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytes);
-  if (e == cudaErrorMemoryAllocation && !rc.vec_cache.empty()) {  // give the cache back and retry
-    (void)cudaGetLastError();
-    CK(cudaStreamSynchronize(rc.stream));
-    for (auto& kv : rc.vec_cache) cudaFree(kv.second);
-    rc.vec_cache.clear();
-    rc.vec_cache_bytes = 0;
-    e = cudaMalloc(&p, bytes);
-  }
-  CK(e);
-  return p;
+  REQUIRE(!ctx->capturing, DJETS_ERR_INVALID, "allocating a DBArray inside a captured sequence: create the vectors first");
+  void* p = nullptr;
+  CK(device_alloc(ctx, &p, bytes));  // on OOM every local rank's cache goes back to the driver first
+  return reinterpret_cast<char*>(p);
 }
 
 void part_free(RankCtx& rc, char* p, size_t bytes) {
@@ -82,11 +74,21 @@ djets_vec make_vec(djets_ctx ctx, int dtype, int nparts, const int32_t* part_ran
     for (int64_t b = b0; b < b0 + part.blk_count; ++b) v->block_part[b] = p;
     b0 += part.blk_count;
     if (RankCtx* rc = ctx->local(part.rank)) {
-      use(*rc);
-      const size_t bytes = (size_t)round_up(part.elem_count * es + 256, 512);  // slack for 16-byte over-reads
-      part.d = part_alloc(*rc, bytes);
-      part.cap = bytes;
-      CK(cudaMemsetAsync(part.d, 0, bytes, rc->stream));
+      try {
+        use(*rc);
+        const size_t bytes = (size_t)round_up(part.elem_count * es + 256, 512);  // slack for 16-byte over-reads
+        part.d = part_alloc(ctx, *rc, bytes);
+        part.cap = bytes;
+        CK(cudaMemsetAsync(part.d, 0, bytes, rc->stream));
+      } catch (...) {  // give back what the earlier parts took
+        for (int q = 0; q <= p; ++q)
+          if (v->parts[q].d)
+            if (RankCtx* rq = ctx->local(v->parts[q].rank)) {
+              cudaSetDevice(rq->device);
+              part_free(*rq, v->parts[q].d, v->parts[q].cap);
+            }
+        throw;
+      }
     }
   }
   return v.release();
@@ -119,8 +121,24 @@ double round_to(int dtype, double v) { return dtype == DJETS_F32 ? (double)(floa
 
 // Per-part partial reductions: one result per part in out_parts (all parts, after the cross-process
 // exchange when some parts live elsewhere).
-void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_parts) {
+bool kind_is_min(int kind) { return kind == DJETS_RED_MIN || kind == DJETS_RED_ABSMIN; }
+bool kind_is_max(int kind) { return kind == DJETS_RED_MAX || kind == DJETS_RED_ABSMAX; }
+
+// minimum / maximum over a worker's empty local part is an error in the reference (Julia: "reducing over an
+// empty collection is not allowed"), not +-Inf
+void check_extrema_parts(djets_vec x, int kind) {
+  if (!kind_is_min(kind) && !kind_is_max(kind)) return;
+  for (const VecPart& part : x->parts)
+    REQUIRE(part.elem_count > 0, DJETS_ERR_INVALID,
+            "ArgumentError: reducing over an empty collection is not allowed (a worker's local part is empty)");
+}
+
+// `as_norm`: the partial of an empty local part is norm(empty) = 0 (Julia), whatever p; otherwise minimum /
+// maximum over an empty part is an error.
+void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_parts, bool as_norm = false) {
   djets_ctx ctx = x->ctx;
+  no_sync_in_capture(ctx, "a reduction returning its value to the host");
+  if (!as_norm) check_extrema_parts(x, kind);
   const int np = (int)x->parts.size();
   // Every process of a multi-process job makes the same calls, so the decision to exchange must not
   // depend on which parts happen to be local: with NCCL up, always all-reduce.
@@ -151,8 +169,8 @@ void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_
     use(*rc);
     const void* yp = y ? y->parts[p].d : nullptr;
     launch_counted(ctx, *rc, DJETS_K_REDUCE, [&] {
-      return launch_reduce(x->dtype, kind, part.d, yp, part.elem_count, param, rc->d_partials, rc->d_result + p,
-                           rc->stream);
+      return launch_reduce(x->dtype, kind, part.d, yp, part.elem_count, param, rc->d_partials, rc->d_ticket,
+                           rc->d_result + p, rc->stream);
     });
   }
   if (exchange) {
@@ -179,27 +197,135 @@ void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_
   for (int p = 0; p < np; ++p) {
     RankCtx* rc = ctx->local(x->parts[p].rank);
     out_parts[p] = rc ? rc->h_result[p] : involved.front()->h_result[p];
+    if (as_norm && x->parts[p].elem_count == 0) out_parts[p] = 0.0;
   }
 }
-
-bool kind_is_min(int kind) { return kind == DJETS_RED_MIN || kind == DJETS_RED_ABSMIN; }
-bool kind_is_max(int kind) { return kind == DJETS_RED_MAX || kind == DJETS_RED_ABSMAX; }
 
 // master-side fold over the per-worker partials in the element type (src:222, 236, 249, 262, 276)
 double fold_parts(int dtype, int kind, const double* z, int np) {
   if (kind_is_min(kind)) {
     double m = INFINITY;
-    for (int p = 0; p < np; ++p) m = fmin(m, round_to(dtype, z[p]));
+    for (int p = 0; p < np; ++p) {
+      const double v = round_to(dtype, z[p]);
+      m = (m != m || v != v) ? NAN : fmin(m, v);  // Julia's minimum / maximum propagate NaN
+    }
     return m;
   }
   if (kind_is_max(kind)) {
     double m = -INFINITY;
-    for (int p = 0; p < np; ++p) m = fmax(m, round_to(dtype, z[p]));
+    for (int p = 0; p < np; ++p) {
+      const double v = round_to(dtype, z[p]);
+      m = (m != m || v != v) ? NAN : fmax(m, v);
+    }
     return m;
   }
   double s = 0.0;
   for (int p = 0; p < np; ++p) s = round_to(dtype, s + round_to(dtype, z[p]));
   return s;
+}
+
+
+// Per-part partials folded ON THE DEVICE into a device-resident scalar (no host round trip): the partials of
+// all parts are gathered on the rank that owns part 0 (peer stores straight from the reduction kernels, or the
+// all-reduce buffer when parts live in other processes), one thread folds them with the reference's rules and
+// stores the result into every local rank's replica of the scalar.
+void reduce_to_scalar(djets_vec x, djets_vec y, int kind, double param, int fold_mode, double fold_p, djets_scalar out,
+                      bool as_norm = false) {
+  djets_ctx ctx = x->ctx;
+  REQUIRE(out && out->ctx == ctx, DJETS_ERR_INVALID, "reduction into a scalar of another context");
+  if (!as_norm) check_extrema_parts(x, kind);
+  // partial of one part into `res` on its owner's stream: the reduction kernel, or norm(empty) = 0
+  auto partial = [&](RankCtx& rc, int p, double* res) {
+    const void* yp = y ? y->parts[p].d : nullptr;
+    launch_counted(ctx, rc, DJETS_K_REDUCE, [&] {
+      if (as_norm && x->parts[p].elem_count == 0) return launch_scalar_set(0.0, res, rc.stream);
+      return launch_reduce(x->dtype, kind, x->parts[p].d, yp, x->parts[p].elem_count, param, rc.d_partials, rc.d_ticket,
+                           res, rc.stream);
+    });
+  };
+  const int np = (int)x->parts.size();
+  const bool multi_process = (int)ctx->ranks.size() < ctx->world;
+  if (multi_process) {
+    REQUIRE(ctx->has_nccl, DJETS_ERR_NCCL, "vector has parts in other processes but the context has no NCCL");
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      CK(cudaMemsetAsync(rc.d_result, 0, sizeof(double) * np, rc.stream));
+    }
+    for (int p = 0; p < np; ++p) {
+      RankCtx* rc = ctx->local(x->parts[p].rank);
+      if (!rc) continue;
+      use(*rc);
+      partial(*rc, p, rc->d_result + p);
+    }
+    const char* why = nullptr;
+    const NcclApi* api = nccl_api(&why);
+    REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
+    NCK(api, api->GroupStart());
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      NCK(api, api->AllReduce(rc.d_result, rc.d_result, np, ncclDouble, ncclSum, rc.comm, rc.stream));
+    }
+    NCK(api, api->GroupEnd());
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      launch_counted(ctx, rc, DJETS_K_REDUCE, [&] {
+        return launch_fold(x->dtype, fold_mode, fold_p, rc.d_result, np, rc.d_scalars + out->slot, ScalarPeers{{}, 0},
+                           rc.stream);
+      });
+    }
+    return;
+  }
+  RankCtx* root = ctx->local(x->parts[0].rank);
+  REQUIRE(root, DJETS_ERR_INVALID, "reduce: part 0 is not local");
+  // gather: each owner's reduction kernel stores its partial into the root's gather buffer (in place over NVLink
+  // when the devices can address each other, a peer copy otherwise)
+  for (int p = 0; p < np; ++p) {
+    RankCtx* rc = ctx->local(x->parts[p].rank);
+    const bool direct = ctx->can_address(*rc, *root);
+    if (rc != root) stream_after(*root, *rc);  // the root's previous fold has read the gather buffer
+    use(*rc);
+    double* res = direct ? root->d_gather + p : rc->d_result + p;
+    partial(*rc, p, res);
+    if (!direct)
+      CK(cudaMemcpyPeerAsync(root->d_gather + p, root->device, res, rc->device, sizeof(double), rc->stream));
+    if (rc != root) stream_after(*rc, *root);
+  }
+  // fold on the root, replicas on the other local ranks
+  ScalarPeers peers{{}, 0};
+  std::vector<RankCtx*> later;
+  for (RankCtx& rc : ctx->ranks) {
+    if (&rc == root) continue;
+    stream_after(rc, *root);  // earlier readers of the replica are done
+    if (ctx->can_address(*root, rc) && peers.n < 16)
+      peers.p[peers.n++] = rc.d_scalars + out->slot;
+    else
+      later.push_back(&rc);
+  }
+  use(*root);
+  launch_counted(ctx, *root, DJETS_K_REDUCE, [&] {
+    return launch_fold(x->dtype, fold_mode, fold_p, root->d_gather, np, root->d_scalars + out->slot, peers, root->stream);
+  });
+  for (RankCtx* rc : later)
+    CK(cudaMemcpyPeerAsync(rc->d_scalars + out->slot, rc->device, root->d_scalars + out->slot, root->device,
+                           sizeof(double), root->stream));
+  for (RankCtx& rc : ctx->ranks)
+    if (&rc != root) stream_after(*root, rc);
+}
+
+void bulk_copy_async(djets_vec x, void* host, bool to_device) {
+  REQUIRE(x, DJETS_ERR_INVALID, "null vector");
+  REQUIRE(host || x->length == 0, DJETS_ERR_INVALID, "null host pointer");
+  const int es = elem_size(x->dtype);
+  for (VecPart& p : x->parts) {
+    RankCtx* rc = x->ctx->local(p.rank);
+    if (!rc || p.elem_count == 0) continue;
+    use(*rc);
+    char* h = reinterpret_cast<char*>(host) + (size_t)p.elem_first * es;
+    if (to_device)
+      CK(cudaMemcpyAsync(p.d, h, (size_t)p.elem_count * es, cudaMemcpyHostToDevice, rc->stream));
+    else
+      CK(cudaMemcpyAsync(h, p.d, (size_t)p.elem_count * es, cudaMemcpyDeviceToHost, rc->stream));
+  }
 }
 
 }  // namespace
@@ -268,6 +394,7 @@ int32_t djets_vec_block_info(djets_vec x, int64_t iblock, int32_t* part, int64_t
 
 static void block_copy(djets_vec x, int64_t iblock, void* host, bool to_device) {
   REQUIRE(x && iblock >= 0 && iblock < (int64_t)x->block_len.size(), DJETS_ERR_INVALID, "block index out of range");
+  no_sync_in_capture(x->ctx, "getblock / setblock!");
   VecPart& p = x->parts[x->block_part[iblock]];
   RankCtx* rc = x->ctx->local(p.rank);
   if (!rc) {
@@ -322,6 +449,7 @@ int32_t djets_vec_getindex(djets_vec x, int64_t i, double* out) {
 
 static void bulk_copy(djets_vec x, void* host, bool to_device) {
   REQUIRE(x, DJETS_ERR_INVALID, "null vector");
+  no_sync_in_capture(x->ctx, "collect / scatter");
   REQUIRE(host || x->length == 0, DJETS_ERR_INVALID, "null host pointer");
   const int es = elem_size(x->dtype);
   for (VecPart& p : x->parts) {
@@ -444,10 +572,10 @@ int32_t djets_vec_norm(djets_vec x, double p, double* out) {
     const int dt = x->dtype;
     std::vector<double> z(np);
     if (p == INFINITY) {  // src:200-201
-      reduce_parts(x, nullptr, DJETS_RED_ABSMAX, 0.0, z.data());
+      reduce_parts(x, nullptr, DJETS_RED_ABSMAX, 0.0, z.data(), true);
       *out = fold_parts(dt, DJETS_RED_MAX, z.data(), np);
     } else if (p == -INFINITY) {  // src:202-203
-      reduce_parts(x, nullptr, DJETS_RED_ABSMIN, 0.0, z.data());
+      reduce_parts(x, nullptr, DJETS_RED_ABSMIN, 0.0, z.data(), true);
       *out = fold_parts(dt, DJETS_RED_MIN, z.data(), np);
     } else if (p == 0.0 || p == 1.0) {  // src:204-205
       reduce_parts(x, nullptr, p == 0.0 ? DJETS_RED_NNZ : DJETS_RED_ABSSUM, 0.0, z.data());
@@ -461,6 +589,93 @@ int32_t djets_vec_norm(djets_vec x, double p, double* out) {
         s = round_to(dt, s + round_to(dt, p == 2.0 ? zk * zk : pow(zk, pp)));
       }
       *out = round_to(dt, p == 2.0 ? sqrt(s) : pow(s, round_to(dt, 1.0 / pp)));
+    }
+  });
+}
+
+
+// ---- stream-ordered forms: nothing here waits for the device -------------------------------------------------
+int32_t djets_vec_scatter_async(djets_vec x, const void* host_src) {
+  return guard([&] { bulk_copy_async(x, const_cast<void*>(host_src), true); });
+}
+int32_t djets_vec_collect_async(djets_vec x, void* host_dst) {
+  return guard([&] { bulk_copy_async(x, host_dst, false); });
+}
+
+int32_t djets_vec_dot_s(djets_vec x, djets_vec y, djets_scalar out) {
+  return guard([&] {
+    REQUIRE(x && y && out, DJETS_ERR_INVALID, "dot: null argument");
+    REQUIRE(same_layout(x, y), DJETS_ERR_MISMATCH, "DimensionMismatch: dot of DBArrays with different block layouts");
+    REQUIRE(x->dtype == y->dtype, DJETS_ERR_MISMATCH, "dot: element types differ (reference: MethodError, src:214)");
+    reduce_to_scalar(x, y, RED_DOT, 0.0, FOLD_SUM, 0.0, out);
+  });
+}
+
+int32_t djets_vec_norm_s(djets_vec x, double p, djets_scalar out) {
+  return guard([&] {
+    REQUIRE(x && out, DJETS_ERR_INVALID, "norm: null argument");
+    if (p == INFINITY)
+      reduce_to_scalar(x, nullptr, DJETS_RED_ABSMAX, 0.0, FOLD_MAX, 0.0, out, true);
+    else if (p == -INFINITY)
+      reduce_to_scalar(x, nullptr, DJETS_RED_ABSMIN, 0.0, FOLD_MIN, 0.0, out, true);
+    else if (p == 0.0 || p == 1.0)
+      reduce_to_scalar(x, nullptr, p == 0.0 ? DJETS_RED_NNZ : DJETS_RED_ABSSUM, 0.0, FOLD_SUM, 0.0, out);
+    else if (p == 2.0)
+      reduce_to_scalar(x, nullptr, DJETS_RED_SUMSQ, 0.0, FOLD_NORM2, 2.0, out);
+    else
+      reduce_to_scalar(x, nullptr, DJETS_RED_SUMPOW, round_to(x->dtype, p), FOLD_NORMP, p, out);
+  });
+}
+
+int32_t djets_vec_reduce_s(djets_vec x, int32_t kind, double param, djets_scalar out) {
+  return guard([&] {
+    REQUIRE(x && out, DJETS_ERR_INVALID, "reduce: null argument");
+    REQUIRE(kind >= 0 && kind <= DJETS_RED_SUMSQ_SHIFT, DJETS_ERR_INVALID, "reduce: unknown kind");
+    reduce_to_scalar(x, nullptr, kind, param, kind_is_min(kind) ? FOLD_MIN : (kind_is_max(kind) ? FOLD_MAX : FOLD_SUM),
+                     0.0, out);
+  });
+}
+
+// ---- the closed elementwise program (src:363-375) --------------------------------------------------------------
+int32_t djets_vec_eval(djets_vec dest, const uint8_t* program, int32_t nops, const djets_vec* inputs, int32_t ninputs,
+                       const double* scalars, const djets_scalar* dscalars, int32_t nscalars, int32_t flags) {
+  return guard([&] {
+    REQUIRE(dest && program, DJETS_ERR_INVALID, "eval: null argument");
+    REQUIRE(nops >= 1 && nops <= kEvalMaxOps, DJETS_ERR_UNSUPPORTED, "eval: 1 to 48 operations per program");
+    REQUIRE(ninputs >= 0 && ninputs <= kEvalMaxIn, DJETS_ERR_UNSUPPORTED, "eval: at most 8 input vectors");
+    REQUIRE(nscalars >= 0 && nscalars <= kEvalMaxScalars, DJETS_ERR_UNSUPPORTED, "eval: at most 16 scalars");
+    REQUIRE(ninputs == 0 || inputs, DJETS_ERR_INVALID, "eval: null input list");
+    REQUIRE(nscalars == 0 || scalars || dscalars, DJETS_ERR_INVALID, "eval: null scalar list");
+    for (int k = 0; k < ninputs; ++k) {
+      REQUIRE(inputs[k], DJETS_ERR_INVALID, "eval: null operand");
+      REQUIRE(same_layout(dest, inputs[k]), DJETS_ERR_MISMATCH,
+              "DimensionMismatch: broadcast operands have different block layouts");
+    }
+    EvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nops = nops;
+    for (int k = 0; k < nops; ++k) {
+      a.op[k] = program[2 * k];
+      a.arg[k] = program[2 * k + 1];
+    }
+    a.nin = ninputs;
+    for (int k = 0; k < ninputs; ++k) a.in_dtype[k] = inputs[k]->dtype;
+    a.nsc = nscalars;
+    for (int k = 0; k < nscalars; ++k) {
+      a.sc[k] = scalars ? scalars[k] : 0.0;
+      REQUIRE(!(dscalars && dscalars[k]) || dscalars[k]->ctx == dest->ctx, DJETS_ERR_INVALID, "eval: scalar of another context");
+    }
+    const char* why = nullptr;
+    REQUIRE(eval_check(a, &why) >= 0, DJETS_ERR_UNSUPPORTED, why ? why : "eval: malformed program");
+    for (size_t p = 0; p < dest->parts.size(); ++p) {
+      VecPart& dp = dest->parts[p];
+      RankCtx* rc = dest->ctx->local(dp.rank);
+      if (!rc) continue;
+      use(*rc);
+      for (int k = 0; k < ninputs; ++k) a.in[k] = inputs[k]->parts[p].d;
+      for (int k = 0; k < nscalars; ++k) a.dsc[k] = (dscalars && dscalars[k]) ? rc->d_scalars + dscalars[k]->slot : nullptr;
+      launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE,
+                     [&] { return launch_eval(dest->dtype, dp.d, a, dp.elem_count, flags & 1, rc->stream); });
     }
   });
 }

@@ -35,6 +35,8 @@ extern "C" {
 typedef struct djets_ctx_s* djets_ctx;
 typedef struct djets_vec_s* djets_vec;
 typedef struct djets_op_s* djets_op;
+typedef struct djets_scalar_s* djets_scalar; /* a scalar resident on the devices (result of dot / norm, solver coefficients) */
+typedef struct djets_graph_s* djets_graph;   /* a captured sequence of calls, replayed with one launch */
 
 enum { DJETS_F32 = 0, DJETS_F64 = 1 };
 enum { DJETS_BLOCK_ZERO = 0, DJETS_BLOCK_DENSE = 1, DJETS_BLOCK_DIAG = 2 };
@@ -59,6 +61,23 @@ enum {
   DJETS_RED_NNZ = 7,        /* count(!iszero,x)       norm(x,0) */
   DJETS_RED_SUMPOW = 8,     /* sum(abs(x)^param)      norm(x,p) partial */
   DJETS_RED_SUMSQ_SHIFT = 9 /* sum((x-param)^2)       src:265 (var) */
+};
+/* Operation codes of the closed elementwise program of djets_vec_eval: a postfix program of (op, arg) byte pairs.
+ * IN / SC push input vector `arg` / scalar `arg`; binary operators pop b, pop a and push `a op b`; unary operators
+ * replace the top; the *S forms combine the top with scalar `arg` without a push (x .+ a, a .* x, max.(x, a) ...;
+ * the R* forms put the scalar on the left: a .- x, a ./ x). */
+enum {
+  DJETS_EV_IN = 1, DJETS_EV_SC = 2,
+  DJETS_EV_ADD = 3, DJETS_EV_SUB = 4, DJETS_EV_MUL = 5, DJETS_EV_DIV = 6, DJETS_EV_POW = 7, DJETS_EV_MIN = 8, DJETS_EV_MAX = 9,
+  DJETS_EV_NEG = 10, DJETS_EV_ABS = 11, DJETS_EV_SQRT = 12, DJETS_EV_SQUARE = 13, DJETS_EV_CUBE = 14, DJETS_EV_EXP = 15,
+  DJETS_EV_LOG = 16,
+  DJETS_EV_ADDS = 17, DJETS_EV_SUBS = 18, DJETS_EV_RSUBS = 19, DJETS_EV_MULS = 20, DJETS_EV_RMULS = 21, DJETS_EV_DIVS = 22,
+  DJETS_EV_RDIVS = 23, DJETS_EV_POWS = 24, DJETS_EV_MINS = 25, DJETS_EV_MAXS = 26
+};
+/* operations of djets_scalar_op */
+enum {
+  DJETS_SC_ADD = 0, DJETS_SC_SUB = 1, DJETS_SC_MUL = 2, DJETS_SC_DIV = 3, DJETS_SC_NEG = 4, DJETS_SC_SQRT = 5, DJETS_SC_COPY = 6,
+  DJETS_SC_ABS = 7, DJETS_SC_MAX = 8, DJETS_SC_MIN = 9
 };
 /* kernel kinds for djets_ctx_kernel_stats */
 enum {
@@ -124,9 +143,34 @@ int32_t djets_timer_stop(djets_ctx ctx, float* ms);
 int32_t djets_ctx_kernel_timing(djets_ctx ctx, int32_t enable);
 int32_t djets_ctx_kernel_stats(djets_ctx ctx, int32_t kind, int64_t* launches, double* total_ms);
 int32_t djets_ctx_reset_stats(djets_ctx ctx);
-/* Tuning knob (schedule shapes); name in {"fwd_tx","fwd_tc","adj_ru","adj_tc","ld_policy","graphs","p2p","auto_tile","pdl"}.
- * Affects operators finalised afterwards. */
+/* Tuning knob; name in {"fwd_tx","fwd_tc","adj_ru","adj_tc","ld_policy","auto_tile"} (schedule shapes: affect
+ * operators finalised or re-planned afterwards) or {"graphs","p2p","pdl","prefetch","persistent"} (launch mechanisms:
+ * take effect on the next apply; applies captured under older settings are dropped). */
 int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value);
+/* Stream marks: djets_ctx_mark records slot (0..7) on every local rank's stream; djets_ctx_wait_mark blocks the host
+ * until everything enqueued before that mark has finished, without draining what was enqueued after it (double
+ * buffering of host transfers: scatter_async / collect_async). */
+int32_t djets_ctx_mark(djets_ctx ctx, int32_t slot);
+int32_t djets_ctx_wait_mark(djets_ctx ctx, int32_t slot);
+/* Captured sequences: every stream-ordered call between begin and end (mul!, adjoint, *_s reductions, scalar_op,
+ * eval / lincomb / binary / fill) is recorded instead of executed; djets_graph_launch replays the whole sequence
+ * with one launch (a solver iteration without host round trips).  Calls that return host data or allocate are
+ * refused while a capture is open.  Needs every rank of the job in this process. */
+int32_t djets_ctx_capture_begin(djets_ctx ctx);
+int32_t djets_ctx_capture_end(djets_ctx ctx, djets_graph* out);
+int32_t djets_graph_launch(djets_graph g);
+int32_t djets_graph_destroy(djets_graph g);
+
+/* ---- device-resident scalars ---------------------------------------------------------------------- */
+/* The reference returns dot / norm to the master and the solver forms alpha = gamma / delta there (src:189-223);
+ * here the value can stay on the devices (a replica per rank), feed djets_vec_eval as a coefficient and be combined
+ * by djets_scalar_op, so a CG-type iteration never waits for the host. */
+int32_t djets_scalar_create(djets_ctx ctx, djets_scalar* out);
+int32_t djets_scalar_destroy(djets_scalar s);
+int32_t djets_scalar_set(djets_scalar s, double v);
+int32_t djets_scalar_get(djets_scalar s, double* out); /* synchronises */
+/* out = a op b (DJETS_SC_*; b may be NULL for unary operations), rounded to the element type `dtype`. */
+int32_t djets_scalar_op(djets_scalar out, int32_t op, djets_scalar a, djets_scalar b, int32_t dtype);
 
 /* ---- DBArray: distributed block vector (src:109-412) ------------------------------------------ */
 /* DBArray(f, blkidxs, pids) / zeros(R) (src:135-159, 378-381): `nparts` parts, part p owned by
@@ -156,6 +200,11 @@ int32_t djets_vec_collect(djets_vec x, void* host_dst);
 /* inverse of collect: every locally driven part is loaded from its slice of host_src (one H2D
  * per rank; the block-by-block form is setblock!, docs:211-227). */
 int32_t djets_vec_scatter(djets_vec x, const void* host_src);
+/* Stream-ordered forms of scatter / collect: they return at once; host_src must stay unmodified / host_dst is
+ * valid only after the next synchronising call (djets_ctx_sync, djets_ctx_wait_mark of a later mark, ...).  Meant for
+ * page-locked buffers (djets_host_alloc). */
+int32_t djets_vec_scatter_async(djets_vec x, const void* host_src);
+int32_t djets_vec_collect_async(djets_vec x, void* host_dst);
 /* fill!(x, a) (src:332-339; also `x .= a`, test:329). */
 int32_t djets_vec_fill(djets_vec x, double a);
 /* Broadcast `dest .= c0*x0 .+ c1*x1 .+ ...` (src:348-376 for the expression class the
@@ -166,6 +215,19 @@ int32_t djets_vec_fill(djets_vec x, double a);
 int32_t djets_vec_lincomb(djets_vec dest, int32_t nterms, const double* coef, const djets_vec* xs, int32_t flags);
 /* Broadcast `dest .= a .* b` (op 0) or `dest .= a ./ b` (op 1). */
 int32_t djets_vec_binary(djets_vec dest, int32_t op, djets_vec a, djets_vec b);
+/* General broadcast `dest .= f(x_1 .. x_k, scalars)` (src:363-375: the reference evaluates any Broadcasted tree per
+ * worker) for the closed operator set DJETS_EV_*: `program` holds nops (op, arg) byte pairs in postfix order,
+ * at most 48 operations, 8 inputs, 16 scalars, 8 operands deep.  Scalar k is scalars[k] unless dscalars != NULL and
+ * dscalars[k] != NULL (then the device-resident value is read by the kernel).  dest may alias any input; layouts
+ * must match; element types may differ (conversion).  flags bit 0: evaluate in Float64 although every vector is
+ * Float32 (Julia semantics with Float64 scalars).  One streaming kernel per part: every input read once. */
+int32_t djets_vec_eval(djets_vec dest, const uint8_t* program, int32_t nops, const djets_vec* inputs, int32_t ninputs,
+                       const double* scalars, const djets_scalar* dscalars, int32_t nscalars, int32_t flags);
+/* dot / norm / reductions whose result stays on the devices (no host synchronisation): the per-rank partials are
+ * folded by a one-thread kernel with the reference's rules (src:200-209, 222, 236) into `out`. */
+int32_t djets_vec_dot_s(djets_vec x, djets_vec y, djets_scalar out);
+int32_t djets_vec_norm_s(djets_vec x, double p, djets_scalar out);
+int32_t djets_vec_reduce_s(djets_vec x, int32_t kind, double param, djets_scalar out);
 /* dot(x, y) (src:212-223): per-rank partial, folded over ranks in rank order in the element type. */
 int32_t djets_vec_dot(djets_vec x, djets_vec y, double* out);
 /* norm(x, p) (src:189-210) with the reference's fold rules; p may be +-INFINITY, 0, 1, 2, other. */

@@ -14,6 +14,8 @@ C2JL = {
     "uint8_t*": {"Ptr{UInt8}"}, "void*": {"Ptr{Cvoid}"}, "void**": {"Ptr{Ptr{Cvoid}}"}, "char*": {"Cstring", "Ptr{UInt8}"},
     "djets_ctx": {"Ptr{Cvoid}"}, "djets_vec": {"Ptr{Cvoid}"}, "djets_op": {"Ptr{Cvoid}"},
     "djets_ctx*": {"Ptr{Ptr{Cvoid}}"}, "djets_vec*": {"Ptr{Ptr{Cvoid}}"}, "djets_op*": {"Ptr{Ptr{Cvoid}}"},
+    "djets_scalar": {"Ptr{Cvoid}"}, "djets_graph": {"Ptr{Cvoid}"}, "djets_scalar*": {"Ptr{Ptr{Cvoid}}"},
+    "djets_graph*": {"Ptr{Ptr{Cvoid}}"},
 }
 
 
@@ -102,7 +104,8 @@ def test_python_ctypes_signatures_match_the_header():
         "float*": C.POINTER(C.c_float), "uint8_t*": C.POINTER(C.c_uint8), "void*": C.c_void_p,
         "void**": C.POINTER(C.c_void_p), "char*": C.c_char_p, "djets_ctx": C.c_void_p, "djets_vec": C.c_void_p,
         "djets_op": C.c_void_p, "djets_ctx*": C.POINTER(C.c_void_p), "djets_vec*": C.POINTER(C.c_void_p),
-        "djets_op*": C.POINTER(C.c_void_p),
+        "djets_op*": C.POINTER(C.c_void_p), "djets_scalar": C.c_void_p, "djets_graph": C.c_void_p,
+        "djets_scalar*": C.POINTER(C.c_void_p), "djets_graph*": C.POINTER(C.c_void_p),
     }
     sigs = header_signatures()
     for name, argtypes in L.SIGNATURES.items():
