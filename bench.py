@@ -2,18 +2,23 @@
 """Benchmark of the hot path: JopDBlock mul! + adjoint on device-resident DBArrays.
 
     python bench.py --gpus N --steps K --warmup W            # this backend (CUDA, sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on the host cores
 
 A "step" is one forward apply ``mul!(d, A, m)`` plus one adjoint apply ``mul!(m, A', d)`` of the
 workload BASELINE.json's metric is quoted on: configs[1], the block-diagonal operator of 64 dense
 Float32 4096x4096 blocks (strong scaling: the 64 blocks are sharded over the N ranks, grid [N,1],
-isdiag, no data-path collective).  Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement".
+isdiag, no data-path collective).  Prints ONE JSON line on rank 0.  After the headline timing the same
+run also times and parity-checks BASELINE configs[2] (full 32x32 grid of dense Float64 2048x2048
+blocks: the cross-GPU exchange) and one dot / norm (the all-reduced scalars), reported under
+"secondary".  See DESIGN.md "Measurement".
 """
 from __future__ import annotations
 
 import argparse
 import json
+import multiprocessing as mp
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -28,6 +33,8 @@ METRIC = "JopDBlock mul!+adjoint effective HBM GB/s"
 NBLK, BM, BN = 64, 4096, 4096
 DTYPE = np.float32
 SEED = 20242
+# BASELINE configs[2]
+C3_NB, C3_BS, C3_SEED = 32, 2048, 20243
 
 
 def block_payload(i: int, m: int = BM, n: int = BN, dtype=DTYPE) -> np.ndarray:
@@ -74,6 +81,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         rows = self.rows
+
         def num(v):
             try:
                 return float(v)
@@ -92,66 +100,119 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-# reference arm: the restated reference (oracle port) on the host cores
+# reference arm: the reference's CPU algorithm for this path on the host cores
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_run(nblocks_sample: int, steps: int, warmup: int):
-    """Block-diagonal forward + adjoint as the reference runs it (src:656-661, 703-708): W workers, one
-    core each with single-threaded BLAS (what `addprocs` workers are), every worker applying its own
-    blocks with per-block gemv (`A*m`, `A'*d`: test/runtests.jl:30-36).  Uses the oracle's block
-    operator classes; this is the only place outside tests/ that executes oracle/ code."""
-    from concurrent.futures import ThreadPoolExecutor
-    from oracle import djets_oracle as O
+def _ref_worker(conn, first: int, count: int):
+    """One stand-in for a Distributed.jl worker: a process of its own with single-threaded BLAS (what
+    `addprocs` workers are), owning `count` consecutive diagonal blocks, applying them one after the
+    other with per-block gemv (`A*m`, `A'*d`: test/runtests.jl:30-36) through the oracle's restatement of
+    the worker-side loops (src/DistributedJets.jl:656-661, 703-708)."""
     try:
         from threadpoolctl import threadpool_limits
-    except ImportError:                                  # pragma: no cover
-        threadpool_limits = None
-    cores = max(1, min(os.cpu_count() or 1, nblocks_sample))
-    blocks = [O.ODense(block_payload(i)) for i in range(1, nblocks_sample + 1)]
-    rng = np.random.default_rng(SEED + 1)
-    xs = [rng.random(BN, dtype=DTYPE) for _ in blocks]
-    cuts = np.linspace(0, nblocks_sample, cores + 1).astype(int)
+        threadpool_limits(limits=1)
+    except ImportError:                                      # pragma: no cover
+        pass
+    from oracle import djets_oracle as O
+    blocks = [O.ODense(block_payload(i)) for i in range(first, first + count)]
+    rng = np.random.default_rng([SEED + 1, first])
+    ms = [rng.random(BN, dtype=DTYPE) for _ in blocks]
+    ds = [np.zeros(BM, dtype=DTYPE) for _ in blocks]
+    m2s = [np.zeros(BN, dtype=DTYPE) for _ in blocks]
+    conn.send("ready")
+    while True:
+        cmd = conn.recv()
+        if cmd == "stop":
+            break
+        O.worker_rows_diag_forward(blocks, ms, ds)           # mul!(d, A, m)  on this worker's block rows
+        O.worker_cols_diag_adjoint(blocks, m2s, ds)          # mul!(m2, A', d) on this worker's block columns
+        conn.send("done")
+    conn.close()
 
-    def worker(w):
-        for b in range(cuts[w], cuts[w + 1]):            # a worker's local block rows, sequentially
-            d = blocks[b].mul(xs[b])                     # mul!(getblock(d,i), A[i,i], getblock(m,i))
-            blocks[b].mul_adjoint(d)                     # mul!(getblock(m,i), A[i,i]', getblock(d,i))
 
-    def step(pool):
-        list(pool.map(worker, range(cores)))
+def cpu_reference_run(nblocks: int, steps: int, warmup: int, workers: int):
+    """Forward + adjoint of the block-diagonal operator over `nblocks` of its blocks on `workers` worker
+    processes.  Returns (GB/s, seconds per step, workers).  Together with --impl reference this is the only
+    place outside tests/ that executes oracle/ code."""
+    workers = max(1, min(workers, nblocks))
+    cuts = np.linspace(0, nblocks, workers + 1).astype(int)  # even split of the block rows (src:154)
+    ctxm = mp.get_context("fork")
+    pipes, procs = [], []
+    for w in range(workers):
+        a, b = ctxm.Pipe()
+        p = ctxm.Process(target=_ref_worker, args=(b, int(cuts[w]) + 1, int(cuts[w + 1] - cuts[w])), daemon=True)
+        p.start()
+        pipes.append(a)
+        procs.append(p)
+    for a in pipes:
+        assert a.recv() == "ready"
 
-    limiter = threadpool_limits(limits=1) if threadpool_limits else None
-    with ThreadPoolExecutor(cores) as pool:
-        for _ in range(warmup):
-            step(pool)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            step(pool)
-        dt = (time.perf_counter() - t0) / steps
-    if limiter:
-        limiter.restore_original_limits() if hasattr(limiter, "restore_original_limits") else None
-    nbytes = 2 * nblocks_sample * (BM * BN + BM + BN) * np.dtype(DTYPE).itemsize
-    return nbytes / dt / 1e9, dt, cores
+    def step():
+        for a in pipes:
+            a.send("go")
+        for a in pipes:
+            a.recv()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    for a in pipes:
+        a.send("stop")
+    for p in procs:
+        p.join(timeout=10)
+    nbytes = 2 * nblocks * (BM * BN + BM + BN) * np.dtype(DTYPE).itemsize
+    return nbytes / dt / 1e9, dt, workers
+
+
+def julia_reference_run(args):
+    """If a Julia toolchain with the reference's packages is ever present, time the UNMODIFIED reference
+    (baseline/ref_bench.jl: addprocs(W), same shapes, same metric).  Returns its JSON dict or None."""
+    exe = shutil.which("julia")
+    script = os.path.join(ROOT, "baseline", "ref_bench.jl")
+    if not exe or not os.path.exists(script):
+        return None
+    try:
+        out = subprocess.run([exe, script, "--config", "2", "--steps", str(args.steps), "--warmup", str(args.warmup),
+                              "--workers", str(args.ref_workers or (os.cpu_count() or 1))],
+                             capture_output=True, text=True, timeout=1800, check=True).stdout
+        for line in reversed(out.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+    except (OSError, subprocess.SubprocessError, ValueError):
+        return None
+    return None
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = max(16, min(NBLK, os.cpu_count() or 1))     # at least one block per host core
-    steps = max(1, min(args.steps, 10))
-    gbs, dt, cores = cpu_reference_run(sample, steps, max(1, min(args.warmup, 2)))
-    sample_txt = (f"{sample} of the {NBLK} dense Float32 {BM}x{BN} diagonal blocks, forward+adjoint, "
-                  f"{cores} worker threads x 1 BLAS thread, {steps} steps")
+    jl = julia_reference_run(args)
+    if jl is not None:
+        gbs, dt, cores, kind = float(jl["value"]), float(jl["ms_per_step"]) * 1e-3, int(jl["workers"]), "julia"
+        sample_txt = (f"the UNMODIFIED reference under Julia (baseline/ref_bench.jl): all {NBLK} blocks, {cores} "
+                      f"addprocs workers, {args.steps} steps after {args.warmup} warm-ups")
+        note = "ChevronETC/DistributedJets.jl itself, timed with addprocs on the host cores"
+    else:
+        workers = args.ref_workers or (os.cpu_count() or 1)
+        gbs, dt, cores = cpu_reference_run(NBLK, args.steps, args.warmup, workers)
+        kind = "port"
+        sample_txt = (f"all {NBLK} dense Float32 {BM}x{BN} diagonal blocks (no sampling), forward+adjoint, {cores} worker "
+                      f"processes x 1 BLAS thread, {args.steps} steps after {args.warmup} warm-ups")
+        note = ("restated reference (NumPy/OpenBLAS port of src/DistributedJets.jl:656-661,703-708), not Julia: Julia is "
+                "absent from the image; one worker process per host core (BASELINE.md section 3 proposed min(nproc, 8): "
+                "--ref-workers 8), no Distributed.jl RPC / serialisation cost, so it flatters the reference")
     line = {
-        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
         "host_cores": os.cpu_count(),
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample_txt},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample_txt},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "restated reference (NumPy/OpenBLAS port of src/DistributedJets.jl:656-661,703-708), not Julia: "
-                "Julia is absent from the image; omits Distributed.jl RPC cost, so it flatters the reference",
+        "note": note,
     }
     print(json.dumps(line), file=args.out, flush=True)
     return 0
@@ -162,6 +223,96 @@ def workload_config(ngpus: int, nblk: int = NBLK) -> dict:
                         f"isdiag, grid [{ngpus},1], forward mul! + adjoint mul! per step",
             "blocks": nblk, "block_shape": [BM, BN], "grid": [ngpus, 1],
             "l2": "inputs larger than L2 (operator payload per GPU >= 512 MiB vs 126 MB L2), no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# secondary: BASELINE configs[2] (the grid exchange) and the all-reduced scalars, timed and parity-checked
+# ------------------------------------------------------------------------------------------------------
+def c3_pool():
+    rng = np.random.default_rng(C3_SEED)
+    return [np.asfortranarray(rng.random((C3_BS, C3_BS))) for _ in range(4)]
+
+
+def c3_block_index(i: int, j: int) -> int:
+    return (i + 3 * j) % 4
+
+
+def secondary_config3(dj, ctx, grid, reps, max_over_ranks, sum_over_ranks, barrier, world_devices):
+    """Full 32x32 operator of dense Float64 2048x2048 blocks on an n1 x n2 grid of ranks: forward and adjoint
+    timed separately; block row 1, block column 1, one dot and one norm checked against Float64 / long-double
+    NumPy computed here (not the oracle)."""
+    n1, n2 = grid
+    pool = c3_pool()
+    nb, bs = C3_NB, C3_BS
+    shapes = ([(bs,)] * nb, [(bs,)] * nb)
+    t0 = time.perf_counter()
+    A = dj.JopDBlock(lambda i, j: dj.JopDense(pool[c3_block_index(i, j)]), dims=(nb, nb), pids=list(range(n1 * n2)),
+                     dist=[n1, n2], shapes=shapes, dtype=np.float64, ctx=ctx)
+    build_s = time.perf_counter() - t0
+    rng = np.random.default_rng(C3_SEED + 1)
+    hx, hy = rng.random(nb * bs), rng.random(nb * bs)
+    x, y = A.domain().zeros().scatter(hx), A.range().zeros().scatter(hy)
+    yo, xo = A.range().zeros(), A.domain().zeros()
+    nbytes = sum_over_ranks(float(A.algorithmic_bytes()))
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        barrier()
+        ctx.timer_start()
+        for _ in range(reps):
+            fn()
+        return max_over_ranks(ctx.timer_stop() / reps)
+
+    ms_f = timed(lambda: A.mul(yo, x))
+    ms_a = timed(lambda: A.mul_adjoint(xo, y))
+    # parity: block row 1 of A*x and block column 1 of A'*y, where their owner is driven by this process
+    relerr = {}
+
+    def blk(v, i):
+        return v[(i - 1) * bs:i * bs]
+    if ctx.is_local(A.range().pids[0]):
+        want = sum(pool[c3_block_index(1, j)] @ blk(hx, j) for j in range(1, nb + 1))
+        got = yo.getblock(1)
+        relerr["forward_block_row_1"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    if ctx.is_local(A.domain().pids[0]):
+        want = sum(pool[c3_block_index(i, 1)].T @ blk(hy, i) for i in range(1, nb + 1))
+        got = xo.getblock(1)
+        relerr["adjoint_block_column_1"] = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    # scalars: every process makes the calls (all-reduce), every process gets the value
+    xs = A.domain().zeros().scatter(hy)
+    dot, nrm = float(x.dot(xs)), float(x.norm())
+    wx, wy = hx.astype(np.longdouble), hy.astype(np.longdouble)
+    relerr["dot"] = float(abs(dot - float(np.sum(wx * wy))) / float(np.sum(wx * wy)))
+    relerr["norm"] = float(abs(nrm - float(np.sqrt(np.sum(wx * wx)))) / float(np.sqrt(np.sum(wx * wx))))
+    ms_dot = timed(lambda: x.dot(xs))
+    # bytes that cross between GPUs per apply: the messages of the exchange plan whose ends sit on different devices
+    es = 8
+    link = {}
+    for adjoint in (0, 1):
+        total = 0
+        for phase in (0, 1):
+            for (sr, sc, dr, dc, part, _slot) in dj.plan_exchange(n1, n2, False, bool(adjoint), phase):
+                src, dst = sr + sc * n1, dr + dc * n1
+                if world_devices[src] == world_devices[dst]:
+                    continue
+                if phase == 0:
+                    total += len((A.range() if adjoint else A.domain()).indices[part]) * es
+                else:
+                    total += len((A.domain() if adjoint else A.range()).indices[part]) * es
+        link["adjoint" if adjoint else "forward"] = total
+    ngpu = len(set(world_devices[:n1 * n2]))
+    peak, _ = peaks()
+    out = {"grid": [n1, n2], "ranks": n1 * n2, "gpus": ngpu, "algorithmic_bytes_per_apply": int(nbytes),
+           "ms_fwd": ms_f, "ms_adj": ms_a, "GBps_fwd": nbytes / ms_f / 1e6, "GBps_adj": nbytes / ms_a / 1e6,
+           "GBps_per_gpu_fwd": nbytes / ms_f / 1e6 / ngpu, "GBps_per_gpu_adj": nbytes / ms_a / 1e6 / ngpu,
+           "frac_of_hbm": min(nbytes / ms_f, nbytes / ms_a) / 1e6 / (peak * ngpu),
+           "relerr": relerr, "relerr_max": max(relerr.values()) if relerr else None,
+           "nvlink_bytes_per_apply": link, "dot_ms": ms_dot, "dot_GBps": 2 * nb * bs * es / ms_dot / 1e6,
+           "build_s": build_s}
+    A.close()
+    del A, x, y, yo, xo, xs
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -182,13 +333,16 @@ def run_cuda(args):
         box = [dj.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         ctx = dj.Context.spmd(rank, world, local_rank, box[0])
+        world_devices = list(range(world))
     elif args.single_process and args.gpus > 1:
         world = args.gpus
         ctx = dj.Context(world=world, devices=list(range(world)))
+        world_devices = list(range(world))
     else:
         ctx = dj.Context(world=1, devices=[0])
+        world_devices = [0]
     dj.set_default_context(ctx)
-    for name in ("fwd_tx", "fwd_tc", "adj_ru", "adj_tc", "ld_policy", "pdl", "graphs", "p2p", "auto_tile"):
+    for name in TUNABLES:
         v = getattr(args, name)
         if v is not None:
             ctx.set_param(name, v)
@@ -225,10 +379,11 @@ def run_cuda(args):
     t_build = time.perf_counter() - t_build
     m, d, m2 = A.domain().zeros(), A.range().zeros(), A.domain().zeros()
     rng = np.random.default_rng(SEED + 1)
-    hx = dj.PinnedBuffer(len(m), DTYPE)
-    hout = dj.PinnedBuffer(len(m), DTYPE)
-    hx.array[:] = rng.random(len(m), dtype=DTYPE)
-    m.scatter(hx.array)
+    hx = [dj.PinnedBuffer(len(m), DTYPE) for _ in range(2)]
+    hout = [dj.PinnedBuffer(len(m), DTYPE) for _ in range(2)]
+    hx[0].array[:] = rng.random(len(m), dtype=DTYPE)
+    hx[1].array[:] = hx[0].array
+    m.scatter(hx[0].array)
     bytes_local = 2 * A.algorithmic_bytes()              # forward + adjoint on the ranks this process drives
     bytes_total = sum_over_ranks(float(bytes_local))
 
@@ -263,23 +418,52 @@ def run_cuda(args):
     kstats = ctx.kernel_stats()
     barrier()
 
-    # end to end through the public API with pinned host buffers: setblock!/scatter of m (H2D),
-    # mul!, adjoint mul!, collect of the result (D2H), every step
-    def e2e_step():
-        m.scatter(hx.array)
+    # End to end through the public API with page-locked host buffers: H2D of m, mul!, adjoint mul!, D2H of the
+    # result, every step.  (a) one host synchronisation per step; (b) double-buffered: the host reads step k-2's
+    # result (wait_mark) while steps k-1 and k are in flight -- every step still moves its own input and output.
+    def e2e_sync_step(k):
+        b = k % 2
+        hx[b].array[0] = np.float32(k % 7) * np.float32(0.125)
+        m.scatter_async(hx[b].array)
         A.mul(d, m)
         A.mul_adjoint(m2, d)
-        m2.to_array(hout.array)
+        m2.to_array_async(hout[b].array)
+        ctx.sync()
+        return float(hout[b].array[0])
+
+    def e2e_pipelined(nsteps):
+        acc = 0.0
+        for k in range(nsteps):
+            b = k % 2
+            if k >= 2:
+                ctx.wait_mark(b)
+                acc += float(hout[b].array[0])              # the host consumes the result of step k-2
+            hx[b].array[0] = np.float32(k % 7) * np.float32(0.125)
+            m.scatter_async(hx[b].array)
+            A.mul(d, m)
+            A.mul_adjoint(m2, d)
+            m2.to_array_async(hout[b].array)
+            ctx.mark(b)
+        ctx.sync()
+        return acc + float(hout[0].array[0]) + float(hout[1].array[0])
 
     e2e_steps = 0 if args.profile else args.steps
-    for _ in range(0 if args.profile else max(3, args.warmup)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / max(e2e_steps, 1))
+    e2e_s = e2e_sync_s = 0.0
+    if e2e_steps:
+        for k in range(max(3, args.warmup)):
+            e2e_sync_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            e2e_sync_step(k)
+        barrier()
+        e2e_sync_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        e2e_pipelined(max(3, args.warmup))
+        barrier()
+        t0 = time.perf_counter()
+        e2e_pipelined(e2e_steps)
+        barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     local_elems = sum(len(r) for r, p in zip(m.indices, m.pids) if ctx.is_local(p))
     h2d = int(sum_over_ranks(float(local_elems * 4)))
     d2h = h2d
@@ -297,19 +481,49 @@ def run_cuda(args):
     # computed here with NumPy (the parity tests proper live in tests/)
     parity = None
     if rank == 0:
-        x1 = hx.array[:BN].astype(np.float64)
+        m.scatter(hx[0].array)
+        x1 = hx[0].array[:BN].astype(np.float64)
         want = block_payload(1).astype(np.float64) @ x1
         A.mul(d, m)
         got = d.getblock(1).astype(np.float64)
         parity = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    sched = {"fwd_tiles_items": A.schedule_info(False), "adj_tiles_items": A.schedule_info(True)}
+    barrier()
+
+    # secondary: configs[2] on a grid that exchanges between ranks, plus the all-reduced scalars
+    secondary = None
+    if not args.profile and not args.no_secondary:
+        A.close()
+        del A, m, d, m2
+        secondary = {"config3": []}
+        if world == 1:                                   # one GPU: four ranks share it, each on its own stream
+            ctx4 = dj.Context(world=4, devices=[0, 0, 0, 0])
+            for grid in ([2, 2], [1, 4]):
+                secondary["config3"].append(secondary_config3(dj, ctx4, grid, args.secondary_reps, lambda v: v, lambda v: v,
+                                                              ctx4.sync, [0, 0, 0, 0]))
+            ctx4.close()
+        else:
+            grids = [[2, world // 2]] if world % 2 == 0 else []
+            grids.append([1, world])
+            for grid in grids:
+                secondary["config3"].append(secondary_config3(dj, ctx, grid, args.secondary_reps, max_over_ranks,
+                                                              sum_over_ranks, barrier, world_devices))
+        if dist is not None:                             # relerr entries live on the owners' processes: merge on rank 0
+            gathered = [None] * world
+            dist.all_gather_object(gathered, [c["relerr"] for c in secondary["config3"]])
+            for k, c in enumerate(secondary["config3"]):
+                for g in gathered:
+                    c["relerr"].update(g[k])
+                c["relerr_max"] = max(c["relerr"].values())
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile:
-        sample = 8
-        gbs, dt, cores = cpu_reference_run(sample, 3, 1)
+        cores = os.cpu_count() or 1
+        sample = min(NBLK, max(16, cores))
+        gbs, dt, cores = cpu_reference_run(sample, 5, 2, args.ref_workers or cores)
         cpu = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
-               "sample": f"{sample} of the {NBLK} blocks, forward+adjoint, {cores} worker threads x 1 BLAS thread, "
-                         f"3 steps ({dt * 1e3:.1f} ms/step)"}
+               "sample": f"{sample} of the {NBLK} blocks, forward+adjoint, {cores} worker processes x 1 BLAS thread, "
+                         f"5 steps after 2 warm-ups ({dt * 1e3:.1f} ms/step)"}
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -348,12 +562,16 @@ def run_cuda(args):
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": per_launch, "kernels": kernels},
             "cpu_baseline": cpu,
-            "e2e": {"value": bytes_total / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
+            "e2e": {"value": bytes_total / e2e_s / 1e9 if e2e_s else None, "unit": "GB/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
+                    "mode": "double-buffered page-locked host buffers: scatter_async, mul!, adjoint mul!, collect_async, mark; "
+                            "the host reads step k-2's result after wait_mark while later steps are in flight",
+                    "sync_every_step": {"value": bytes_total / e2e_sync_s / 1e9 if e2e_sync_s else None,
+                                        "ms_per_step": e2e_sync_s * 1e3}},
             "gpu_launches": launches if (world == 1 or args.single_process) else int(launches * world),
             "mode": "one host process" if (args.single_process or world == 1) else "one process per GPU (NCCL)",
             "clocks": clocks, "host_cores": os.cpu_count(), "parity_relerr_block1": parity, "build_s": t_build,
-            "schedule": {"fwd_tiles_items": A.schedule_info(False), "adj_tiles_items": A.schedule_info(True)},
+            "schedule": sched, "secondary": secondary,
         }
         print(json.dumps(line), file=args.out, flush=True)
     if dist is not None:
@@ -371,6 +589,10 @@ def quiet_stdout():
     return os.fdopen(keep, "w")
 
 
+TUNABLES = ("fwd_tx", "fwd_tc", "adj_ru", "adj_tc", "ld_policy", "pdl", "graphs", "p2p", "auto_tile", "prefetch",
+            "persistent")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -385,9 +607,13 @@ def main():
                     help="drive all --gpus N ranks from this one process (the Julia-master model) instead of one "
                          "process per GPU under torchrun")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2] / scalar measurements")
+    ap.add_argument("--secondary-reps", type=int, default=10)
+    ap.add_argument("--ref-workers", type=int, default=None,
+                    help="worker processes of the CPU reference (default: one per host core)")
     ap.add_argument("--profile", action="store_true",
-                    help="short run for ncu: skips the e2e pass, the clock-sampling loop and the CPU baseline")
-    for name in ("fwd_tx", "fwd_tc", "adj_ru", "adj_tc", "ld_policy", "pdl", "graphs", "p2p", "auto_tile"):
+                    help="short run for ncu: skips the e2e pass, the clock-sampling loop, the secondary configs and the CPU baseline")
+    for name in TUNABLES:
         ap.add_argument(f"--{name}", type=int, default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -557,6 +557,20 @@ def tree_reduce(bufs: List[np.ndarray]) -> np.ndarray:
     return bufs[0]
 
 
+def worker_rows_diag_forward(blocks, m_blocks, d_blocks) -> None:
+    """One worker's share of a block-diagonal forward apply, ``JetDBlock_local_rows_diag_df!`` src:656-661:
+    ``for i in local rows: mul!(getblock(d,i), A[i,i], getblock(m,i))``.  On the owner ``getblock`` aliases
+    the stored block (docs/src/index.md:126-132), so the product lands in place."""
+    for A, m, d in zip(blocks, m_blocks, d_blocks):
+        d[...] = A.mul(m)
+
+
+def worker_cols_diag_adjoint(blocks, m_blocks, d_blocks) -> None:
+    """``JetDBlock_local_cols_diag_df′!`` src:703-708: ``mul!(getblock(m,j), A[j,j]', getblock(d,j))``."""
+    for A, m, d in zip(blocks, m_blocks, d_blocks):
+        m[...] = A.mul_adjoint(d)
+
+
 class OJopDBlock:
     """Distributed block operator, src:414-508 (build) and src:510-721 (apply).
 

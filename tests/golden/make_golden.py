@@ -5,6 +5,11 @@ the reference's own isapprox checks -- and freeze it: any later change of the or
 path that moves a result shows up against these files.
 
     python tests/golden/make_golden.py
+
+It also writes operator_cases_inputs.json: the same seeded INPUTS (blocks, x, y) in a form the Julia side can read
+without extra packages.  tests/golden/make_golden.jl feeds them to the unmodified reference and writes
+operator_cases_julia.json; once that file exists tests/test_golden_julia.py pins the oracle and the CUDA path to
+the reference's own outputs (and "parity unpinned" can be lifted).
 """
 import os
 import sys
@@ -72,10 +77,33 @@ def build(name):
     return payload
 
 
+def export_inputs(payload) -> dict:
+    """Inputs of every case as plain JSON (floats printed with repr round-trip exactly)."""
+    doc = {}
+    for name, (rs, cs, grid, isdiag, dtype, rule) in CASES.items():
+        blocks = {}
+        for key, val in payload.items():
+            case, _, item = key.partition("/")
+            if case != name or item.count("_") != 2 or item[0] not in "AD":
+                continue
+            kind, i, j = item.split("_")
+            blocks[f"{i}_{j}"] = {"kind": "dense" if kind == "A" else "diag", "shape": list(val.shape),
+                                  "data": [float(v) for v in np.asarray(val).reshape(-1, order="F")]}
+        doc[name] = {"dtype": dtype, "row_sizes": rs, "col_sizes": cs, "grid": grid, "isdiag": isdiag, "blocks": blocks,
+                     "x": [float(v) for v in payload[f"{name}/x"]], "y": [float(v) for v in payload[f"{name}/y"]]}
+    return doc
+
+
 if __name__ == "__main__":
+    import json
     out = {}
     for name in CASES:
         out.update(build(name))
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "operator_cases.npz")
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = os.path.join(here, "operator_cases.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes,", len(out), "arrays")
+    jpath = os.path.join(here, "operator_cases_inputs.json")
+    with open(jpath, "w") as f:
+        json.dump(export_inputs(out), f)
+    print(jpath, os.path.getsize(jpath), "bytes")
