@@ -195,7 +195,8 @@ int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ran
       CK(cudaMalloc(&rc.d_scalars, sizeof(double) * kMaxScalars));
       CK(cudaMemset(rc.d_scalars, 0, sizeof(double) * kMaxScalars));
       for (cudaEvent_t& e : rc.marks) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      CK(cudaHostAlloc(&rc.h_result, sizeof(double) * 2 * kMaxParts, cudaHostAllocPortable));
+      CK(cudaHostAlloc(&rc.h_result, sizeof(double) * 2 * kMaxParts, cudaHostAllocPortable | cudaHostAllocMapped));
+      CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&rc.h_result_dev), rc.h_result, 0));
     }
     // peer access between the GPUs this process drives: local->local exchange is in-place peer
     // loads / stores from the kernels (or a peer copy when p2p is off)

@@ -13,6 +13,10 @@
 #include "djets_kernels.h"
 
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
 
 namespace djets {
 
@@ -70,9 +74,9 @@ struct EvalDev {
 };
 
 // The interpreter proper over E elements held in registers.  XIN(k, e) yields input k's element e.
-template <typename ACC, int E, int D, int NIN, typename XIN>
+template <typename ACC, int E, int D, typename XIN>
 __device__ __forceinline__ void run_program(const EvalDev& a, const ACC* __restrict__ sc, XIN xin, ACC (&top)[E]) {
-  ACC st[D - 1][E];
+  ACC st[D > 1 ? D - 1 : 1][E];
 #pragma unroll
   for (int k = 0; k < D - 1; ++k)
 #pragma unroll
@@ -111,17 +115,29 @@ __device__ __forceinline__ void run_program(const EvalDev& a, const ACC* __restr
     }                                                     \
   } while (0)
 
+#define EV_OPD(expr)                                      \
+  do {                                                    \
+    _Pragma("unroll") for (int e = 0; e < E; ++e) {       \
+      const ACC x = top[e], v = xin(arg & 7, e);          \
+      top[e] = (expr);                                    \
+    }                                                     \
+  } while (0)
+#define EV_OPDS(expr)                                     \
+  do {                                                    \
+    const ACC s = sc[arg >> 3];                           \
+    _Pragma("unroll") for (int e = 0; e < E; ++e) {       \
+      const ACC x = top[e], v = xin(arg & 7, e);          \
+      top[e] = (expr);                                    \
+    }                                                     \
+  } while (0)
+
   for (int pc = 0; pc < a.nops; ++pc) {
     const int op = a.op[pc], arg = a.arg[pc];
     switch (op) {
       case EV_IN:
         EV_PUSH();
 #pragma unroll
-        for (int k = 0; k < NIN; ++k)
-          if (k == arg) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) top[e] = xin(k, e);
-          }
+        for (int e = 0; e < E; ++e) top[e] = xin(arg, e);
         break;
       case EV_SC: {
         EV_PUSH();
@@ -143,6 +159,17 @@ __device__ __forceinline__ void run_program(const EvalDev& a, const ACC* __restr
       case EV_CUBE: EV_UN(ev_mul(ev_mul(x, x), x)); break;
       case EV_EXP: EV_UN(ev_exp(x)); break;
       case EV_LOG: EV_UN(ev_log(x)); break;
+      // fused operand forms (made by the host-side peephole pass): arg = input | scalar << 3
+      case EV_ADD_IN: EV_OPD(ev_add(x, v)); break;
+      case EV_SUB_IN: EV_OPD(ev_sub(x, v)); break;
+      case EV_RSUB_IN: EV_OPD(ev_sub(v, x)); break;
+      case EV_MUL_IN: EV_OPD(ev_mul(x, v)); break;
+      case EV_DIV_IN: EV_OPD(ev_div(x, v)); break;
+      case EV_RDIV_IN: EV_OPD(ev_div(v, x)); break;
+      case EV_MIN_IN: EV_OPD(ev_min(x, v)); break;
+      case EV_MAX_IN: EV_OPD(ev_max(x, v)); break;
+      case EV_AXPY_IN: EV_OPDS(ev_add(x, ev_mul(v, s))); break;
+      case EV_AXMY_IN: EV_OPDS(ev_sub(x, ev_mul(v, s))); break;
       case EV_ADDS: EV_SCL(ev_add(x, s)); break;
       case EV_SUBS: EV_SCL(ev_sub(x, s)); break;
       case EV_RSUBS: EV_SCL(ev_sub(s, x)); break;
@@ -156,6 +183,8 @@ __device__ __forceinline__ void run_program(const EvalDev& a, const ACC* __restr
       default: break;
     }
   }
+#undef EV_OPD
+#undef EV_OPDS
 #undef EV_PUSH
 #undef EV_BIN
 #undef EV_UN
@@ -173,47 +202,98 @@ __device__ __forceinline__ void load_scalars(const EvalDev& a, ACC* sc) {
   __syncthreads();
 }
 
-// Vector path: destination and every input share the element type T.  Each thread iteration covers NV
-// 128-bit vectors per input (grid-strided, so a warp's loads stay fully coalesced), all loaded up front.
-template <typename T, typename ACC, int NV, int D, int NIN>
-__global__ void __launch_bounds__(kThreads) eval_vec_kernel(T* dest /* may alias an input */, EvalDev a, long long n) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Vector path: destination and every input share the element type T.  A CTA walks tiles of NV*256 vectors
+// (16 bytes each); thread t owns vectors t, t+256, ... of the tile (a warp's accesses stay fully coalesced).
+// ring[stage][input][v][thread] holds the operands; `stages` tiles are in flight per CTA.
+template <typename T, typename ACC, int NV, int D, bool kStreamStores>
+__global__ void __launch_bounds__(kThreads) eval_vec_kernel(T* dest /* may alias an input */, EvalDev a, long long n,
+                                                            int stages) {
   using V = typename Vec16<T>::type;
   constexpr int VEC = Vec16<T>::N;
   constexpr int E = NV * VEC;
+  extern __shared__ __align__(16) unsigned char ring_raw[];
+  V* ring = reinterpret_cast<V*>(ring_raw);
   __shared__ ACC sc[kEvalMaxScalars];
   load_scalars<ACC>(a, sc);
-  const long long nvec = (n + VEC - 1) / VEC;  // the last vector may be partial: parts carry >= 256 B of slack for the over-read
-  const long long gstride = (long long)gridDim.x * kThreads;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += NV * gstride) {
-    V x[NIN][NV];
-#pragma unroll
-    for (int k = 0; k < NIN; ++k)
-      if (k < a.nin) {
+  const int tid = threadIdx.x;
+  const int nin = a.nin;
+  const long long nvec = (n + VEC - 1) / VEC;
+  const long long tile = (long long)NV * kThreads;
+  const long long ntiles = (nvec + tile - 1) / tile;
+  const int stage_vecs = nin * NV * kThreads;
+
+  auto issue = [&](long long t, int stage) {  // this thread's slots of tile t
+    if (t < ntiles) {
+      V* dst = ring + (size_t)stage * stage_vecs + tid;
+      for (int k = 0; k < nin; ++k) {
+        const V* src = reinterpret_cast<const V*>(a.in[k]) + t * tile + tid;
 #pragma unroll
         for (int u = 0; u < NV; ++u) {
-          const long long idx = i + u * gstride;
-          if (idx < nvec) x[k][u] = reinterpret_cast<const V*>(a.in[k])[idx];
+          const long long idx = t * tile + (long long)u * kThreads + tid;
+          // parts carry >= 256 B of slack, so a partial last vector may be read whole; past the end nothing is read
+          const bool live = idx < nvec;
+          cp_async16(dst + (k * NV + u) * kThreads, live ? src + u * kThreads : reinterpret_cast<const V*>(a.in[k]), live ? 16 : 0);
         }
       }
+    }
+    cp_async_commit();
+  };
+
+  long long t = blockIdx.x;
+  for (int s = 0; s < stages - 1; ++s) issue(t + (long long)s * gridDim.x, s);
+  int stage = 0;
+  for (; t < ntiles; t += gridDim.x) {
+    {
+      const int ahead = stage == 0 ? stages - 1 : stage - 1;
+      issue(t + (long long)(stages - 1) * gridDim.x, ahead);
+    }
+    // all but the newest stages-1 groups are complete: tile t has landed
+    switch (stages) {
+      case 2: cp_async_wait<1>(); break;
+      case 3: cp_async_wait<2>(); break;
+      default: cp_async_wait<3>(); break;
+    }
+    const V* mine = ring + (size_t)stage * stage_vecs + tid;
     ACC top[E];
-    run_program<ACC, E, D, NIN>(
-        a, sc, [&](int k, int e) { return (ACC) reinterpret_cast<const T*>(&x[k][e / VEC])[e % VEC]; }, top);
+    run_program<ACC, E, D>(
+        a, sc,
+        [&](int k, int e) {
+          const T* v = reinterpret_cast<const T*>(mine + (k * NV + e / VEC) * kThreads);
+          return (ACC)v[e % VEC];
+        },
+        top);
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
-      const long long idx = i + u * gstride;
+      const long long idx = t * tile + (long long)u * kThreads + tid;
       if (idx >= nvec) continue;
       V o;
       T* oe = reinterpret_cast<T*>(&o);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) oe[e] = (T)top[u * VEC + e];
       if ((idx + 1) * VEC <= n) {
-        reinterpret_cast<V*>(dest)[idx] = o;
+        if (kStreamStores)
+          __stcs(reinterpret_cast<V*>(dest) + idx, o);
+        else
+          reinterpret_cast<V*>(dest)[idx] = o;
       } else {
         for (int e = 0; e < VEC; ++e)
           if (idx * VEC + e < n) dest[idx * VEC + e] = oe[e];
       }
     }
+    stage = stage + 1 == stages ? 0 : stage + 1;
   }
+  cp_async_wait<0>();
 }
 
 // Generic path: any mix of element types (conversions); one element per thread iteration, in double.
@@ -223,45 +303,60 @@ __global__ void __launch_bounds__(kThreads) eval_generic_kernel(TD* dest, EvalDe
   load_scalars<double>(a, sc);
   const long long gstride = (long long)gridDim.x * kThreads;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += gstride) {
-    double x[kEvalMaxIn];
-#pragma unroll
-    for (int k = 0; k < kEvalMaxIn; ++k)
-      if (k < a.nin)
-        x[k] = a.in_dtype[k] == 0 ? (double) reinterpret_cast<const float*>(a.in[k])[i]
-                                  : reinterpret_cast<const double*>(a.in[k])[i];
     double top[1];
-    run_program<double, 1, kEvalMaxDepth, kEvalMaxIn>(a, sc, [&](int k, int) { return x[k]; }, top);
+    run_program<double, 1, kEvalMaxDepth>(
+        a, sc,
+        [&](int k, int) {
+          return a.in_dtype[k] == 0 ? (double) reinterpret_cast<const float*>(a.in[k])[i]
+                                    : reinterpret_cast<const double*>(a.in[k])[i];
+        },
+        top);
     dest[i] = (TD)top[0];
   }
 }
 
-int eval_grid(long long work_items) {
-  long long want = (work_items + kThreads - 1) / kThreads;
-  const long long cap = 148LL * 8;
-  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+int eval_sm_count() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
 }
 
-template <typename T, typename ACC, int NV, int NIN>
-void launch_vec_d(T* dest, const EvalDev& d, long long n, int depth, cudaStream_t stream) {
+template <typename T, typename ACC, int NV, int D>
+cudaError_t launch_vec_k(T* dest, const EvalDev& d, long long n, cudaStream_t stream) {
+  // ring size: about 48 KB per CTA, 2 to 4 stages -> 4 CTAs per SM keep ~100-150 KB in flight per SM
+  const size_t stage_bytes = (size_t)std::max(d.nin, 1) * NV * kThreads * 16;
+  static const int ring_kb = getenv("DJETS_EVAL_RING_KB") ? atoi(getenv("DJETS_EVAL_RING_KB")) : 32;
+  int stages = (int)std::min<size_t>(4, std::max<size_t>(2, ((size_t)ring_kb * 1024) / stage_bytes));
+  const size_t smem = stage_bytes * stages;
+  static const bool cs = getenv("DJETS_EVAL_CS") && atoi(getenv("DJETS_EVAL_CS"));
+  auto kernel = cs ? eval_vec_kernel<T, ACC, NV, D, true> : eval_vec_kernel<T, ACC, NV, D, false>;
+  if (smem > 40 * 1024) {  // the kernel also holds a few hundred bytes of static shared memory
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const long long nvec = (n + Vec16<T>::N - 1) / Vec16<T>::N;
-  const int grid = eval_grid((nvec + NV - 1) / NV);
-  if (depth <= 3)
-    eval_vec_kernel<T, ACC, NV, 3, NIN><<<grid, kThreads, 0, stream>>>(dest, d, n);
-  else
-    eval_vec_kernel<T, ACC, NV, kEvalMaxDepth, NIN><<<grid, kThreads, 0, stream>>>(dest, d, n);
+  const long long ntiles = (nvec + (long long)NV * kThreads - 1) / ((long long)NV * kThreads);
+  const int grid = (int)std::min<long long>(ntiles, (long long)eval_sm_count() * per_sm);
+  kernel<<<grid, kThreads, smem, stream>>>(dest, d, n, stages);
+  return cudaGetLastError();
 }
 
-// in-flight bytes per thread are kept near 64: fewer inputs -> more vectors per input per iteration
 template <typename T, typename ACC>
-void launch_vec(T* dest, const EvalDev& d, long long n, int depth, cudaStream_t stream) {
-  if (d.nin <= 1)
-    launch_vec_d<T, ACC, 4, 1>(dest, d, n, depth, stream);
-  else if (d.nin == 2)
-    launch_vec_d<T, ACC, 2, 2>(dest, d, n, depth, stream);
-  else if (d.nin <= 4)
-    launch_vec_d<T, ACC, 1, 4>(dest, d, n, depth, stream);
-  else
-    launch_vec_d<T, ACC, 1, kEvalMaxIn>(dest, d, n, depth, stream);
+cudaError_t launch_vec(T* dest, const EvalDev& d, long long n, int depth, cudaStream_t stream) {
+  constexpr int NV = 4;  // 8 doubles / 16 floats per thread iteration (profiles/r02_eval_sweep.txt)
+  static const int nv_env = getenv("DJETS_EVAL_NV") ? atoi(getenv("DJETS_EVAL_NV")) : NV;
+  if (nv_env == 8 && depth <= 1) return launch_vec_k<T, ACC, 8, 1>(dest, d, n, stream);
+  if (nv_env == 8 && depth <= 2) return launch_vec_k<T, ACC, 8, 2>(dest, d, n, stream);
+  if (nv_env == 2 && depth <= 1) return launch_vec_k<T, ACC, 2, 1>(dest, d, n, stream);
+  if (nv_env == 2 && depth <= 2) return launch_vec_k<T, ACC, 2, 2>(dest, d, n, stream);
+  if (nv_env == 1 && depth <= 1) return launch_vec_k<T, ACC, 1, 1>(dest, d, n, stream);
+  if (nv_env == 1 && depth <= 2) return launch_vec_k<T, ACC, 1, 2>(dest, d, n, stream);
+  if (depth <= 1) return launch_vec_k<T, ACC, NV, 1>(dest, d, n, stream);
+  if (depth <= 2) return launch_vec_k<T, ACC, NV, 2>(dest, d, n, stream);
+  if (depth <= 4) return launch_vec_k<T, ACC, 2, 4>(dest, d, n, stream);
+  return launch_vec_k<T, ACC, 1, kEvalMaxDepth>(dest, d, n, stream);
 }
 
 }  // namespace
@@ -293,6 +388,10 @@ int eval_check(const EvalArgs& a, const char** why) {
     } else if (op >= EV_ADDS && op <= EV_MAXS) {
       if (sp < 1) return bad("eval: scalar-operand operator on an empty stack");
       if (arg >= a.nsc) return bad("eval: scalar index outside the scalar list");
+    } else if (op >= EV_ADD_IN && op <= EV_AXMY_IN) {  // internal forms (peephole pass)
+      if (sp < 1) return bad("eval: operand form on an empty stack");
+      if ((arg & 7) >= a.nin) return bad("eval: input index outside the input list");
+      if (op >= EV_AXPY_IN && (arg >> 3) >= a.nsc) return bad("eval: scalar index outside the scalar list");
     } else {
       return bad("eval: unknown operation code");
     }
@@ -303,16 +402,55 @@ int eval_check(const EvalArgs& a, const char** why) {
   return depth;
 }
 
+// Peephole pass over a valid program: an operand that is pushed only to be consumed by the next binary operator is
+// folded into that operator (`... IN k ADD` -> `ADD_IN k`, `... IN k MULS j ADD` -> `AXPY_IN k,j`), which saves the
+// stack shift and a dispatch per operand.  Same arithmetic, same rounding: x*s == s*x and the fused forms round the
+// product and the sum separately.
+static int peephole(const EvalArgs& a, unsigned char* op, unsigned char* arg) {
+  int n = 0;
+  for (int pc = 0; pc < a.nops;) {
+    const bool stacked = n > 0;  // something is already on the stack for the operand to combine with
+    if (stacked && a.op[pc] == EV_IN && a.arg[pc] < 8) {
+      const int k = a.arg[pc];
+      if (pc + 2 < a.nops && (a.op[pc + 1] == EV_MULS || a.op[pc + 1] == EV_RMULS) && a.arg[pc + 1] < 16 &&
+          (a.op[pc + 2] == EV_ADD || a.op[pc + 2] == EV_SUB)) {
+        op[n] = a.op[pc + 2] == EV_ADD ? EV_AXPY_IN : EV_AXMY_IN;
+        arg[n++] = (unsigned char)(k | (a.arg[pc + 1] << 3));
+        pc += 3;
+        continue;
+      }
+      if (pc + 1 < a.nops) {
+        int f = 0;
+        switch (a.op[pc + 1]) {
+          case EV_ADD: f = EV_ADD_IN; break;
+          case EV_SUB: f = EV_SUB_IN; break;
+          case EV_MUL: f = EV_MUL_IN; break;
+          case EV_DIV: f = EV_DIV_IN; break;
+          case EV_MIN: f = EV_MIN_IN; break;
+          case EV_MAX: f = EV_MAX_IN; break;
+        }
+        if (f) {
+          op[n] = (unsigned char)f;
+          arg[n++] = (unsigned char)k;
+          pc += 2;
+          continue;
+        }
+      }
+    }
+    op[n] = a.op[pc];
+    arg[n++] = a.arg[pc];
+    ++pc;
+  }
+  return n;
+}
+
 cudaError_t launch_eval(int ddtype, void* dest, const EvalArgs& a, long long n, int wide, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  const int depth = eval_check(a, nullptr);
-  if (depth < 0) return cudaErrorInvalidValue;
+  if (eval_check(a, nullptr) < 0) return cudaErrorInvalidValue;
   EvalDev d;
   bool same = true;
-  for (int k = 0; k < kEvalMaxOps; ++k) {
-    d.op[k] = k < a.nops ? a.op[k] : 0;
-    d.arg[k] = k < a.nops ? a.arg[k] : 0;
-  }
+  memset(&d, 0, sizeof(d));
+  d.nops = peephole(a, d.op, d.arg);
   for (int k = 0; k < kEvalMaxIn; ++k) {
     d.in[k] = k < a.nin ? a.in[k] : nullptr;
     d.in_dtype[k] = k < a.nin ? a.in_dtype[k] : ddtype;
@@ -322,26 +460,27 @@ cudaError_t launch_eval(int ddtype, void* dest, const EvalArgs& a, long long n, 
     d.sc[k] = k < a.nsc ? a.sc[k] : 0.0;
     d.dsc[k] = k < a.nsc ? a.dsc[k] : nullptr;
   }
-  d.nops = a.nops;
   d.nin = a.nin;
   d.nsc = a.nsc;
+  // stack depth of the rewritten program
+  EvalArgs b = a;
+  b.nops = d.nops;
+  memcpy(b.op, d.op, sizeof(b.op));
+  memcpy(b.arg, d.arg, sizeof(b.arg));
+  const int depth = eval_check(b, nullptr);
+  if (depth < 0) return cudaErrorInvalidValue;
   if (same) {
-    if (ddtype == 1)
-      launch_vec<double, double>(reinterpret_cast<double*>(dest), d, n, depth, stream);
-    else if (wide)
-      launch_vec<float, double>(reinterpret_cast<float*>(dest), d, n, depth, stream);
-    else
-      launch_vec<float, float>(reinterpret_cast<float*>(dest), d, n, depth, stream);
-  } else {
-    const int grid = eval_grid(n);
-    if (ddtype == 1)
-      eval_generic_kernel<double><<<grid, kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), d, n);
-    else
-      eval_generic_kernel<float><<<grid, kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), d, n);
+    if (ddtype == 1) return launch_vec<double, double>(reinterpret_cast<double*>(dest), d, n, depth, stream);
+    if (wide) return launch_vec<float, double>(reinterpret_cast<float*>(dest), d, n, depth, stream);
+    return launch_vec<float, float>(reinterpret_cast<float*>(dest), d, n, depth, stream);
   }
+  const int grid = (int)std::min<long long>((n + kThreads - 1) / kThreads, 148LL * 8);
+  if (ddtype == 1)
+    eval_generic_kernel<double><<<grid, kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), d, n);
+  else
+    eval_generic_kernel<float><<<grid, kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), d, n);
   return cudaGetLastError();
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // Device-resident scalars: the master-side folds of the reference's reductions and the scalar arithmetic

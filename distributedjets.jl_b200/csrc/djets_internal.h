@@ -94,7 +94,8 @@ struct RankCtx {
   double* d_partials = nullptr;  // per-CTA partials of the reduction in flight
   unsigned* d_ticket = nullptr;  // last-CTA ticket of the reduction kernel (zero between launches)
   double* d_result = nullptr;    // 2*kMaxParts doubles: per-part results, then the all-reduce buffer
-  double* h_result = nullptr;    // pinned mirror
+  double* h_result = nullptr;    // pinned mirror, also mapped into the device's address space ...
+  double* h_result_dev = nullptr;  // ... so a reduction kernel can store its result straight into host memory
   double* d_gather = nullptr;    // kMaxParts doubles: per-part partials gathered on the root rank of a device-side fold
   double* d_scalars = nullptr;   // kMaxScalars doubles: this rank's replica of every device-resident scalar
   cudaEvent_t marks[8] = {};     // djets_ctx_mark / djets_ctx_wait_mark

@@ -89,7 +89,10 @@ enum {
   EV_ADD = 3, EV_SUB = 4, EV_MUL = 5, EV_DIV = 6, EV_POW = 7, EV_MIN = 8, EV_MAX = 9,           // pop b, pop a, push a op b
   EV_NEG = 10, EV_ABS = 11, EV_SQRT = 12, EV_SQUARE = 13, EV_CUBE = 14, EV_EXP = 15, EV_LOG = 16,  // top = f(top)
   EV_ADDS = 17, EV_SUBS = 18, EV_RSUBS = 19, EV_MULS = 20, EV_RMULS = 21, EV_DIVS = 22, EV_RDIVS = 23,
-  EV_POWS = 24, EV_MINS = 25, EV_MAXS = 26                                                         // top = top op scalar[arg]
+  EV_POWS = 24, EV_MINS = 25, EV_MAXS = 26,                                                        // top = top op scalar[arg]
+  // internal (never cross the ABI): operand folded into the operator by the peephole pass; arg = input | scalar << 3
+  EV_ADD_IN = 32, EV_SUB_IN = 33, EV_RSUB_IN = 34, EV_MUL_IN = 35, EV_DIV_IN = 36, EV_RDIV_IN = 37, EV_MIN_IN = 38,
+  EV_MAX_IN = 39, EV_AXPY_IN = 40, EV_AXMY_IN = 41
 };
 constexpr int kEvalMaxOps = 48, kEvalMaxIn = 8, kEvalMaxScalars = 16, kEvalMaxDepth = 8;
 struct EvalArgs {

@@ -233,7 +233,12 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
         weighted_cols += (double)b * (double)op->col_len[j];
         max_rows = std::max(max_rows, op->row_len[i]);
       }
-    const int64_t tile_bytes = std::max<int64_t>(64 * 1024, dense_bytes / (148 * 6));
+    // ranks of this process that share the device run their cells side by side: size the tiles for the sum of them
+    int share = 0;
+    for (const Cell& other : op->cells)
+      if (RankCtx* orc = ctx->local(other.rank)) share += orc->device == rc->device ? 1 : 0;
+    const int64_t tile_bytes = share > 1 ? std::max<int64_t>(64 * 1024, dense_bytes * share / (148 * 4))
+                                         : std::max<int64_t>(64 * 1024, dense_bytes / (148 * 6));
     // forward: narrow blocks (few columns) give a tile its bytes through more rows -- the CTA goes wider
     // along the rows and needs fewer (or no) column groups to sum
     const int64_t typical_cols = dense_bytes > 0 ? (int64_t)(weighted_cols / (double)dense_bytes) : 1;

@@ -168,9 +168,11 @@ void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_
     }
     use(*rc);
     const void* yp = y ? y->parts[p].d : nullptr;
+    // without an exchange the kernel stores the part's result straight into mapped host memory: no copy to wait for
+    double* res = exchange ? rc->d_result + p : rc->h_result_dev + p;
     launch_counted(ctx, *rc, DJETS_K_REDUCE, [&] {
-      return launch_reduce(x->dtype, kind, part.d, yp, part.elem_count, param, rc->d_partials, rc->d_ticket,
-                           rc->d_result + p, rc->stream);
+      return launch_reduce(x->dtype, kind, part.d, yp, part.elem_count, param, rc->d_partials, rc->d_ticket, res,
+                           rc->stream);
     });
   }
   if (exchange) {
@@ -186,10 +188,11 @@ void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_
   } else {
     REQUIRE(!any_remote, DJETS_ERR_NCCL, "vector has parts in other processes but the context has no NCCL");
   }
-  for (RankCtx* rc : involved) {
-    use(*rc);
-    CK(cudaMemcpyAsync(rc->h_result, rc->d_result, sizeof(double) * np, cudaMemcpyDeviceToHost, rc->stream));
-  }
+  if (exchange)
+    for (RankCtx* rc : involved) {
+      use(*rc);
+      CK(cudaMemcpyAsync(rc->h_result, rc->d_result, sizeof(double) * np, cudaMemcpyDeviceToHost, rc->stream));
+    }
   for (RankCtx* rc : involved) {
     use(*rc);
     CK(cudaStreamSynchronize(rc->stream));
@@ -667,6 +670,55 @@ int32_t djets_vec_eval(djets_vec dest, const uint8_t* program, int32_t nops, con
     }
     const char* why = nullptr;
     REQUIRE(eval_check(a, &why) >= 0, DJETS_ERR_UNSUPPORTED, why ? why : "eval: malformed program");
+    // Linear combinations `c0*x0 + c1*x1 - c2*x2 ...` of up to four vectors with host scalars (the forms the reference's
+    // tests and benchmark use: test:322, bench:43) go to the specialised kernel: same products, same sums, same rounding.
+    {
+      double coef[4];
+      int which[4], nt = 0, pc = 0;
+      bool linear = true;
+      while (linear && pc < nops) {
+        if (a.op[pc] != EV_IN || nt == 4) {
+          linear = false;
+          break;
+        }
+        which[nt] = a.arg[pc++];
+        coef[nt] = 1.0;
+        if (pc < nops && (a.op[pc] == EV_MULS || a.op[pc] == EV_RMULS)) {
+          const int j = a.arg[pc++];
+          if (dscalars && dscalars[j]) linear = false;
+          coef[nt] = a.sc[j];
+        }
+        if (nt > 0) {
+          if (pc < nops && a.op[pc] == EV_ADD) {
+            ++pc;
+          } else if (pc < nops && a.op[pc] == EV_SUB) {
+            coef[nt] = -coef[nt];
+            ++pc;
+          } else {
+            linear = false;
+          }
+        }
+        ++nt;
+      }
+      if (linear && nt >= 1) {
+        for (size_t p = 0; p < dest->parts.size(); ++p) {
+          VecPart& dp = dest->parts[p];
+          RankCtx* rc = dest->ctx->local(dp.rank);
+          if (!rc) continue;
+          use(*rc);
+          LincombArgs la;
+          la.nterms = nt;
+          for (int k = 0; k < nt; ++k) {
+            la.x[k] = inputs[which[k]]->parts[p].d;
+            la.coef[k] = coef[k];
+            la.xdtype[k] = inputs[which[k]]->dtype;
+          }
+          launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE,
+                         [&] { return launch_lincomb(dest->dtype, dp.d, la, dp.elem_count, flags & 1, rc->stream); });
+        }
+        return;
+      }
+    }
     for (size_t p = 0; p < dest->parts.size(); ++p) {
       VecPart& dp = dest->parts[p];
       RankCtx* rc = dest->ctx->local(dp.rank);

@@ -29,6 +29,11 @@ const DJETS_F32, DJETS_F64 = Int32(0), Int32(1)
 const BLOCK_ZERO, BLOCK_DENSE, BLOCK_DIAG = Int32(0), Int32(1), Int32(2)
 const RED_SUM, RED_MIN, RED_MAX, RED_ABSSUM, RED_ABSMAX, RED_ABSMIN, RED_SUMSQ, RED_NNZ, RED_SUMPOW, RED_SUMSQ_SHIFT = Int32.(0:9)
 
+# operation codes of djets_vec_eval (DJETS_EV_*) and djets_scalar_op (DJETS_SC_*)
+const EV_IN, EV_SC, EV_ADD, EV_SUB, EV_MUL, EV_DIV, EV_POW, EV_MIN, EV_MAX, EV_NEG, EV_ABS, EV_SQRT, EV_SQUARE, EV_CUBE, EV_EXP, EV_LOG,
+      EV_ADDS, EV_SUBS, EV_RSUBS, EV_MULS, EV_RMULS, EV_DIVS, EV_RDIVS, EV_POWS, EV_MINS, EV_MAXS = UInt8.(1:26)
+const SC_ADD, SC_SUB, SC_MUL, SC_DIV, SC_NEG, SC_SQRT, SC_COPY, SC_ABS, SC_MAX, SC_MIN = Int32.(0:9)
+
 dtypecode(::Type{Float32}) = DJETS_F32
 dtypecode(::Type{Float64}) = DJETS_F64
 dtypecode(::Type{T}) where {T} = error("DistributedJetsB200: element type $T is not supported (Float32, Float64)")
@@ -76,6 +81,26 @@ function evencuts(n::Integer, nparts::Integer)
     cuts = Vector{Int64}(undef, nparts + 1)
     @dj djets_even_cuts (Int64, Int32, Ptr{Int64}) Int64(n) Int32(nparts) cuts
     cuts                                   # 0-based starts; block range k is cuts[k]+1:cuts[k+1]
+end
+
+# DistributedArrays.defaultdist(dims, pids): prime factors of the worker count, largest first, each handed to the
+# currently largest remaining dimension (ties go to the last dimension)
+function defaultgrid(dims, npids::Integer)
+    facs, n, p = Int[], Int(npids), 2
+    while p * p <= n
+        while n % p == 0; push!(facs, p); n ÷= p; end
+        p += 1
+    end
+    n > 1 && push!(facs, n)
+    sort!(facs, rev=true)
+    rem, chunks = collect(Int, dims), ones(Int, length(dims))
+    for fac in facs
+        k = findlast(==(maximum(rem)), rem)
+        if rem[k] >= fac
+            rem[k] ÷= fac; chunks[k] *= fac
+        end
+    end
+    chunks
 end
 
 # ---- JetDSpace (src:48-107) ------------------------------------------------------------------------
@@ -145,7 +170,7 @@ function DBArray(f::Function, blkidxs::Vector{UnitRange{Int}}, pids=workers())
     for (rng, part) in zip(blkidxs, blocks), (i, b) in zip(rng, part); setblock!(x, i, b); end
     x
 end
-function DBArray(f::Function, nblks::Tuple, pids::AbstractArray=workers()[1:min(length(workers()), nblks[1])], dist::AbstractArray=[min(length(pids), nblks[1])])
+function DBArray(f::Function, nblks::Tuple, pids::AbstractArray=workers()[1:min(length(workers()), nblks[1])], dist::AbstractArray=defaultgrid(nblks, length(pids)))   # src:153-159
     cuts = evencuts(nblks[1], dist[1])
     DBArray(f, [cuts[k]+1:cuts[k+1] for k in 1:dist[1]], pids)
 end
@@ -213,6 +238,57 @@ function Base.collect(x::DBArray{T}) where {T}
     Jets.BlockArray(arrays, idx)
 end
 Base.fill!(x::DBArray, a) = (@dj djets_vec_fill (Ptr{Cvoid}, Float64) x.h Float64(a); x)
+# stream-ordered forms for page-locked buffers: `a` must stay alive and untouched until `synchronize()` / `waitmark`
+scatter_async!(x::DBArray{T}, a::Vector{T}) where {T} = (@dj djets_vec_scatter_async (Ptr{Cvoid}, Ptr{Cvoid}) x.h pointer(a); x)
+collect_async!(a::Vector{T}, x::DBArray{T}) where {T} = (@dj djets_vec_collect_async (Ptr{Cvoid}, Ptr{Cvoid}) x.h pointer(a); a)
+mark(slot::Integer=0) = @dj djets_ctx_mark (Ptr{Cvoid}, Int32) context().h Int32(slot)
+waitmark(slot::Integer=0) = @dj djets_ctx_wait_mark (Ptr{Cvoid}, Int32) context().h Int32(slot)
+
+# ---- device-resident scalars: dot / norm results that never visit the host, and arithmetic on them -----------------
+mutable struct DScalar{T}
+    h::Ptr{Cvoid}
+    function DScalar{T}() where {T}
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        @dj djets_scalar_create (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}) context().h h
+        s = new{T}(h[])
+        finalizer(s -> (s.h == C_NULL || ccall((:djets_scalar_destroy, libdjets), Int32, (Ptr{Cvoid},), s.h); s.h = C_NULL), s)
+    end
+end
+DScalar{T}(v::Real) where {T} = (s = DScalar{T}(); @dj djets_scalar_set (Ptr{Cvoid}, Float64) s.h Float64(T(v)); s)
+function Base.getindex(s::DScalar{T}) where {T}                       # s[] synchronises
+    v = Ref{Float64}(0)
+    @dj djets_scalar_get (Ptr{Cvoid}, Ptr{Float64}) s.h v
+    T(v[])
+end
+function scalarop!(out::DScalar{T}, op::Int32, a::DScalar{T}, b::Union{Nothing,DScalar{T}}=nothing) where {T}
+    @dj djets_scalar_op (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Int32) out.h op a.h (b === nothing ? C_NULL : b.h) dtypecode(T)
+    out
+end
+Base.:+(a::DScalar{T}, b::DScalar{T}) where {T} = scalarop!(DScalar{T}(), SC_ADD, a, b)
+Base.:-(a::DScalar{T}, b::DScalar{T}) where {T} = scalarop!(DScalar{T}(), SC_SUB, a, b)
+Base.:*(a::DScalar{T}, b::DScalar{T}) where {T} = scalarop!(DScalar{T}(), SC_MUL, a, b)
+Base.:/(a::DScalar{T}, b::DScalar{T}) where {T} = scalarop!(DScalar{T}(), SC_DIV, a, b)
+Base.:-(a::DScalar{T}) where {T} = scalarop!(DScalar{T}(), SC_NEG, a)
+Base.sqrt(a::DScalar{T}) where {T} = scalarop!(DScalar{T}(), SC_SQRT, a)
+Base.broadcastable(s::DScalar) = Ref(s)                              # `x .+ alpha .* p` with a device scalar
+dot!(out::DScalar{T}, x::DBArray{T}, y::DBArray{T}) where {T} = (@dj djets_vec_dot_s (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}) x.h y.h out.h; out)
+norm!(out::DScalar, x::DBArray, p::Real=2) = (@dj djets_vec_norm_s (Ptr{Cvoid}, Float64, Ptr{Cvoid}) x.h Float64(p) out.h; out)
+
+# captured sequences: `g = capture() do ... end; launch(g)` replays the stream-ordered calls made in the block
+mutable struct Graph; h::Ptr{Cvoid}; end
+function capture(f::Function)
+    @dj djets_ctx_capture_begin (Ptr{Cvoid},) context().h
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    try
+        f()
+    finally
+        status = ccall((:djets_ctx_capture_end, libdjets), Int32, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), context().h, h)
+        check(status)
+    end
+    g = Graph(h[])
+    finalizer(g -> (g.h == C_NULL || ccall((:djets_graph_destroy, libdjets), Int32, (Ptr{Cvoid},), g.h); g.h = C_NULL), g)
+end
+launch(g::Graph) = @dj djets_graph_launch (Ptr{Cvoid},) g.h
 
 # reductions (src:189-283) ------------------------------------------------------------------------------------
 function reduce_kind(x::DBArray{T}, kind::Int32, param=0.0) where {T}
@@ -248,8 +324,10 @@ function Statistics.var(x::DBArray{T}; corrected=true, mean=nothing) where {T}
     corrected ? σ² / (length(x) - 1) : σ² / length(x)
 end
 
-# broadcasting (src:348-376): the closed expression class  dest .= Σ cₖ .* xₖ ,  dest .= x ,  dest .= a ,
-# dest .= x .* y ,  dest .= x ./ y ;  anything else is refused (a CUDA library cannot run a Julia closure).
+# broadcasting (src:348-376).  The reference ships the Broadcasted tree to the workers and evaluates it over the local
+# blocks (src:363-375); here the tree is lowered to the closed elementwise program of djets_vec_eval -- operators
+# + - * / ^ abs sqrt exp log min max, unary minus, scalars (host numbers or device DScalars) -- and ONE streaming kernel
+# per GPU evaluates it.  Anything else (an arbitrary Julia closure) is refused.
 struct DBArrayStyle <: Broadcast.AbstractArrayStyle{1} end
 Base.BroadcastStyle(::Type{<:DBArray}) = DBArrayStyle()
 DBArrayStyle(::Val{1}) = DBArrayStyle()
@@ -260,51 +338,87 @@ find_dbarray(a::DBArray, rest) = a
 find_dbarray(::Any, rest) = find_dbarray(rest)
 Base.similar(bc::Broadcast.Broadcasted{DBArrayStyle}, ::Type{T}) where {T} = similar(find_dbarray(bc))      # src:353-356 (ignores T)
 
-# linear form of a broadcast tree: Vector of (coefficient, DBArray), or nothing
-linterms(x::DBArray, c=1.0) = [(Float64(c), x)]
-function linterms(bc::Broadcast.Broadcasted, c=1.0)
-    f, a = bc.f, bc.args
-    if f === (+)
-        ts = Tuple{Float64,DBArray}[]
-        for arg in a
-            t = linterms(arg, c); t === nothing && return nothing; append!(ts, t)
-        end
-        return ts
-    elseif f === (-) && length(a) == 2
-        t1, t2 = linterms(a[1], c), linterms(a[2], -c)
-        return (t1 === nothing || t2 === nothing) ? nothing : vcat(t1, t2)
-    elseif f === (-) && length(a) == 1
-        return linterms(a[1], -c)
-    elseif f === (*) && length(a) == 2 && a[1] isa Number
-        return linterms(a[2], c * a[1])
-    elseif f === (*) && length(a) == 2 && a[2] isa Number
-        return linterms(a[1], c * a[2])
-    elseif f === (/) && length(a) == 2 && a[2] isa Number
-        return linterms(a[1], c / a[2])
-    elseif f === identity && length(a) == 1
-        return linterms(a[1], c)
-    end
-    nothing
+mutable struct Program
+    code::Vector{UInt8}                    # (op, arg) pairs, postfix
+    vecs::Vector{DBArray}
+    scal::Vector{Float64}
+    dscal::Vector{Ptr{Cvoid}}              # C_NULL: host scalar
+    wide::Bool                             # a Float64 scalar or array takes part: evaluate in Float64 (Julia's promotion)
 end
-linterms(::Any, c=1.0) = nothing
+Program() = Program(UInt8[], DBArray[], Float64[], Ptr{Cvoid}[], false)
+isscalar(x) = x isa Number || x isa DScalar || (x isa Base.RefValue && (x[] isa Number || x[] isa DScalar))
+unref(x) = x isa Base.RefValue ? x[] : x
+function vecindex!(p::Program, x::DBArray)
+    k = findfirst(v -> v === x, p.vecs)
+    k === nothing && (push!(p.vecs, x); k = length(p.vecs))
+    eltype(x) === Float64 && (p.wide = true)
+    UInt8(k - 1)
+end
+function scalarindex!(p::Program, a)
+    a = unref(a)
+    if a isa DScalar
+        push!(p.scal, 0.0); push!(p.dscal, a.h)
+        a isa DScalar{Float64} && (p.wide = true)
+    else
+        push!(p.scal, Float64(a)); push!(p.dscal, C_NULL)
+        a isa Float64 && (p.wide = true)                              # Int and Float32 scalars do not promote Float32 arrays
+    end
+    UInt8(length(p.scal) - 1)
+end
+emit!(p::Program, op::UInt8, arg::UInt8=0x00) = (push!(p.code, op); push!(p.code, arg); p)
+const BIN = Dict{Any,Tuple{UInt8,UInt8,Union{UInt8,Nothing}}}(     # f => (stack form, vector op scalar, scalar op vector)
+    (+) => (EV_ADD, EV_ADDS, EV_ADDS), (-) => (EV_SUB, EV_SUBS, EV_RSUBS), (*) => (EV_MUL, EV_MULS, EV_RMULS),
+    (/) => (EV_DIV, EV_DIVS, EV_RDIVS), (^) => (EV_POW, EV_POWS, nothing), min => (EV_MIN, EV_MINS, EV_MINS),
+    max => (EV_MAX, EV_MAXS, EV_MAXS))
+const UN = Dict{Any,UInt8}((-) => EV_NEG, abs => EV_ABS, sqrt => EV_SQRT, exp => EV_EXP, log => EV_LOG)
+refuse(f) = error("DistributedJetsB200: broadcast of $f over a DBArray is outside the closed operator set (+ - * / ^ abs sqrt exp log min max)")
 
-function lincomb!(dest::DBArray, ts)
-    length(ts) <= 4 || error("DistributedJetsB200: at most 4 terms per fused broadcast; split the expression")
-    coef = Float64[t[1] for t in ts]
-    hs = Ptr{Cvoid}[t[2].h for t in ts]
-    GC.@preserve ts @dj djets_vec_lincomb (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Ptr{Cvoid}}, Int32) dest.h Int32(length(ts)) coef hs Int32(1)
+lower!(p::Program, x::DBArray) = emit!(p, EV_IN, vecindex!(p, x))
+lower!(p::Program, x) = isscalar(x) ? emit!(p, EV_SC, scalarindex!(p, x)) : refuse(typeof(x))
+function lower!(p::Program, bc::Broadcast.Broadcasted)
+    f, a = bc.f, bc.args
+    if f === identity && length(a) == 1
+        return lower!(p, a[1])
+    elseif f === Base.literal_pow && length(a) == 3                   # x .^ 2 lowers to literal_pow(^, x, Val(2)): x*x, like Julia
+        pw = typeof(unref(a[3])).parameters[1]
+        lower!(p, a[2])
+        return pw == 2 ? emit!(p, EV_SQUARE) : pw == 3 ? emit!(p, EV_CUBE) : emit!(p, EV_POWS, scalarindex!(p, Float64(pw)))
+    elseif length(a) == 1 && haskey(UN, f)
+        lower!(p, a[1])
+        return emit!(p, UN[f])
+    elseif length(a) >= 2 && haskey(BIN, f)
+        (length(a) == 2 || f === (+) || f === (*)) || refuse(f)
+        stack, vs, sv = BIN[f]
+        # n-ary + and * fold from the left, as Base's +(a, b, c...) does
+        if isscalar(a[1]) && !isscalar(a[2]) && sv !== nothing
+            lower!(p, a[2]); emit!(p, sv, scalarindex!(p, a[1]))
+        elseif !isscalar(a[1]) && isscalar(a[2])
+            lower!(p, a[1]); emit!(p, vs, scalarindex!(p, a[2]))
+        else
+            lower!(p, a[1]); lower!(p, a[2]); emit!(p, stack)
+        end
+        for k in 3:length(a)
+            isscalar(a[k]) ? emit!(p, vs, scalarindex!(p, a[k])) : (lower!(p, a[k]); emit!(p, stack))
+        end
+        return p
+    end
+    refuse(f)
+end
+
+function Base.copyto!(dest::DBArray, bc::Broadcast.Broadcasted{DBArrayStyle})                 # src:370-375
+    if bc.f === identity && length(bc.args) == 1 && unref(bc.args[1]) isa Number               # dest .= a  (test:329)
+        return fill!(dest, unref(bc.args[1]))
+    end
+    p = lower!(Program(), bc)
+    length(p.code) <= 96 || error("DistributedJetsB200: broadcast expression longer than 48 operations; split it")
+    GC.@preserve p @dj djets_vec_eval (Ptr{Cvoid}, Ptr{UInt8}, Int32, Ptr{Ptr{Cvoid}}, Int32, Ptr{Float64}, Ptr{Ptr{Cvoid}}, Int32, Int32) dest.h p.code Int32(length(p.code) ÷ 2) Ptr{Cvoid}[v.h for v in p.vecs] Int32(length(p.vecs)) p.scal p.dscal Int32(length(p.scal)) Int32(p.wide && eltype(dest) === Float32 ? 1 : 0)
     dest
 end
-function Base.copyto!(dest::DBArray, bc::Broadcast.Broadcasted{DBArrayStyle})                 # src:370-375
-    ts = linterms(bc)
-    ts === nothing || return lincomb!(dest, ts)
-    if (bc.f === (*) || bc.f === (/)) && length(bc.args) == 2 && all(a -> a isa DBArray, bc.args)
-        @dj djets_vec_binary (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}) dest.h Int32(bc.f === (*) ? 0 : 1) bc.args[1].h bc.args[2].h
-        return dest
-    end
-    error("DistributedJetsB200: broadcast expression outside the closed set (linear combinations, .*, ./, fill, convert)")
+function Base.copyto!(dest::DBArray, src::DBArray)                                            # dest .= x, also converts (test:237-238)
+    coef, hs = Float64[1.0], Ptr{Cvoid}[src.h]
+    @dj djets_vec_lincomb (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Ptr{Cvoid}}, Int32) dest.h Int32(1) coef hs Int32(0)
+    dest
 end
-Base.copyto!(dest::DBArray, src::DBArray) = lincomb!(dest, [(1.0, src)])
 
 # ---- native block kinds (SURVEY F5: what replaces arbitrary JopLn closures) -------------------------------
 abstract type B200Block{T} end

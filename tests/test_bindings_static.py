@@ -81,10 +81,32 @@ def test_shim_covers_the_hot_path_entry_points():
     bound = {name for name, _ in shim_bindings()}
     for needed in ("djets_ctx_create", "djets_vec_create", "djets_vec_similar", "djets_vec_destroy", "djets_vec_getblock",
                    "djets_vec_setblock", "djets_vec_getindex", "djets_vec_collect", "djets_vec_scatter", "djets_vec_fill",
-                   "djets_vec_lincomb", "djets_vec_binary", "djets_vec_dot", "djets_vec_norm", "djets_vec_reduce",
+                   "djets_vec_lincomb", "djets_vec_eval", "djets_vec_dot", "djets_vec_norm", "djets_vec_reduce",
+                   "djets_vec_dot_s", "djets_vec_norm_s", "djets_scalar_create", "djets_scalar_op", "djets_scalar_get",
+                   "djets_vec_scatter_async", "djets_vec_collect_async", "djets_ctx_mark", "djets_ctx_wait_mark",
+                   "djets_ctx_capture_begin", "djets_ctx_capture_end", "djets_graph_launch",
                    "djets_op_create", "djets_op_set_dense", "djets_op_set_diag", "djets_op_finalize", "djets_op_destroy",
                    "djets_op_mul", "djets_op_mul_adjoint", "djets_op_getblock", "djets_op_perfstat"):
         assert needed in bound, needed
+
+
+def test_shim_lowers_broadcasts_like_the_python_mirror():
+    """The two hosts must agree on the byte-code: same operation numbering as include/djets.h, `dest .= scalar` is a
+    fill (test/runtests.jl:329), and the Float64 flag follows the scalar / array element types."""
+    src = open(SHIM).read()
+    hdr = open(HEADER).read()
+    import djets_loader
+    djets_loader.load()
+    import djets_b200._lib as L
+    names = ["IN", "SC", "ADD", "SUB", "MUL", "DIV", "POW", "MIN", "MAX", "NEG", "ABS", "SQRT", "SQUARE", "CUBE", "EXP", "LOG",
+             "ADDS", "SUBS", "RSUBS", "MULS", "RMULS", "DIVS", "RDIVS", "POWS", "MINS", "MAXS"]
+    for k, n in enumerate(names, start=1):
+        assert re.search(rf"DJETS_EV_{n} = {k}\b", hdr), n
+        assert getattr(L, "EV_" + n) == k
+    jl = re.search(r"const (EV_IN,.*?) = UInt8\.\(1:26\)", src, flags=re.S).group(1)
+    assert [t.strip() for t in jl.replace("\n", " ").split(",")] == ["EV_" + n for n in names]
+    assert "return fill!(dest, unref(bc.args[1]))" in src
+    assert "a isa Float64 && (p.wide = true)" in src and "defaultgrid(nblks, length(pids))" in src
 
 
 def test_shim_keeps_the_reference_exports():
