@@ -7,7 +7,7 @@ from ._lib import (DJetsError, DimensionMismatch, NotLocal, LIB_PATH, F32, F64, 
                    BLOCK_DIAG)
 from .partition import (urange, even_cuts, even_ranges, default_grid, cuts_from_ranges, ranges_from_cuts,
                         grid_of, plan_exchange)
-from .core import (Context, init, set_default_context, context, workers, nworkers, nccl_unique_id,
+from .core import (Context, init, set_default_context, context, workers, nworkers, nccl_unique_id, torch_allgather,
                    PinnedBuffer, Graph, Scalar, Expr, lazy, bc_abs, bc_sqrt, bc_exp, bc_log, bc_max, bc_min,
                    JetDSpace, DBArray, LinExpr, dotted, zeros, ones, rand, Array, getblock,
                    getblock_into, setblock, collect, dot, norm, blockmap, localblockindices, procs, nprocs,

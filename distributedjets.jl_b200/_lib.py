@@ -27,6 +27,10 @@ KERNEL_NAMES = {K_GEMV_N: "gemv_n", K_GEMV_T: "gemv_t", K_FINISH: "finish", K_RE
                 K_ELTWISE: "eltwise"}
 
 
+# int32 (*djets_allgather_fn)(void* user, const void* send, void* recv, int64 bytes)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+
+
 class DJetsError(RuntimeError):
     """Any failure reported by the library (status != 0)."""
 
@@ -67,6 +71,7 @@ SIGNATURES = {
     "djets_host_free": [vp],
     "djets_ctx_create": [i32, i32, p_i32, p_i32, C.POINTER(C.c_uint8), p_vp],
     "djets_ctx_destroy": [vp],
+    "djets_ctx_set_host_allgather": [vp, vp, vp],
     "djets_ctx_sync": [vp],
     "djets_ctx_info": [vp, p_i32, p_i32, p_i32],
     "djets_ctx_is_local": [vp, i32, p_i32],

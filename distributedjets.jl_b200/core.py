@@ -64,8 +64,30 @@ class Context:
         self.myrank = self.local_ranks[0] if len(self.local_ranks) == 1 and world > 1 else None
 
     @staticmethod
-    def spmd(rank: int, world: int, device: int, nccl_uid: Optional[bytes]) -> "Context":
-        return Context(world=world, devices=[device], local_ranks=[rank], nccl_uid=nccl_uid)
+    def spmd(rank: int, world: int, device: int, nccl_uid: Optional[bytes] = None,
+             allgather: Optional[Callable[[bytes], List[bytes]]] = None) -> "Context":
+        """One rank per process.  ``nccl_uid``: exchange over NCCL where needed; ``allgather``: a host-side collective
+        ``bytes -> [bytes of every process]`` (e.g. ``torch_allgather()``) that carries the control plane, so the job
+        needs no NCCL at all: block data moves through CUDA-IPC-mapped peer memory."""
+        ctx = Context(world=world, devices=[device], local_ranks=[rank], nccl_uid=nccl_uid)
+        if allgather is not None:
+            ctx.set_host_allgather(allgather)
+        return ctx
+
+    def set_host_allgather(self, fn: Callable[[bytes], List[bytes]]) -> None:
+        def thunk(_user, send, recv, nbytes):
+            try:
+                records = fn(C.string_at(send, nbytes))
+                for k, rec in enumerate(records):
+                    assert len(rec) == nbytes
+                    C.memmove(recv + k * nbytes, rec, nbytes)
+                return 0
+            except Exception:                                # never let an exception cross the C ABI
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._allgather_cb = _lib.ALLGATHER_FN(thunk)        # kept alive as long as the context
+        _lib.call("djets_ctx_set_host_allgather", self.h, C.cast(self._allgather_cb, C.c_void_p), None)
 
     def workers(self) -> List[int]:
         return list(range(self.world))
@@ -243,6 +265,17 @@ def workers() -> List[int]:
 
 def nworkers() -> int:
     return context().world
+
+
+def torch_allgather(group=None) -> Callable[[bytes], List[bytes]]:
+    """Host all-gather over an initialised ``torch.distributed`` process group (gloo or nccl)."""
+    import torch.distributed as dist
+
+    def gather(send: bytes) -> List[bytes]:
+        out = [None] * dist.get_world_size(group)
+        dist.all_gather_object(out, send, group=group)
+        return out
+    return gather
 
 
 def nccl_unique_id() -> bytes:

@@ -60,6 +60,64 @@ cudaError_t device_alloc(djets_ctx ctx, void** p, size_t bytes) {
   return cudaMalloc(p, bytes);
 }
 
+void control_allgather(djets_ctx ctx, const void* send, void* recv, size_t bytes) {
+  RankCtx& rc = ctx->ranks.front();
+  if (ctx->host_allgather) {
+    // the callback orders records by process; a process stands for its first local rank
+    std::vector<char> tmp(bytes * (size_t)ctx->world, 0), mine(bytes + sizeof(int32_t));
+    const int32_t myrank = rc.rank;
+    memcpy(mine.data(), &myrank, sizeof(int32_t));
+    memcpy(mine.data() + sizeof(int32_t), send, bytes);
+    std::vector<char> all((bytes + sizeof(int32_t)) * (size_t)ctx->world, 0);
+    // the number of processes is not known to the library: the callback fills one record per process and leaves the
+    // rest of `all` untouched (rank field -1 marks unused slots)
+    for (size_t k = 0; k < (size_t)ctx->world; ++k) {
+      const int32_t none = -1;
+      memcpy(all.data() + k * (bytes + sizeof(int32_t)), &none, sizeof(int32_t));
+    }
+    const int32_t st = ctx->host_allgather(ctx->host_allgather_user, mine.data(), all.data(), (int64_t)(bytes + sizeof(int32_t)));
+    REQUIRE(st == 0, DJETS_ERR_NCCL, "the host all-gather callback failed");
+    memset(recv, 0, bytes * (size_t)ctx->world);
+    for (size_t k = 0; k < (size_t)ctx->world; ++k) {
+      int32_t r;
+      memcpy(&r, all.data() + k * (bytes + sizeof(int32_t)), sizeof(int32_t));
+      if (r >= 0 && r < ctx->world)
+        memcpy(reinterpret_cast<char*>(recv) + (size_t)r * bytes, all.data() + k * (bytes + sizeof(int32_t)) + sizeof(int32_t), bytes);
+    }
+    return;
+  }
+  REQUIRE(ctx->has_nccl, DJETS_ERR_NCCL, "a multi-process job needs a host all-gather callback or an NCCL unique id");
+  const char* why = nullptr;
+  const NcclApi* api = nccl_api(&why);
+  REQUIRE(api, DJETS_ERR_NCCL, why ? why : "NCCL unavailable");
+  use(rc);
+  char *d_send = nullptr, *d_recv = nullptr;
+  CK(cudaMalloc(&d_send, bytes));
+  CK(cudaMalloc(&d_recv, bytes * (size_t)ctx->world));
+  CK(cudaMemcpyAsync(d_send, send, bytes, cudaMemcpyHostToDevice, rc.stream));
+  NCK(api, api->GroupStart());
+  for (RankCtx& each : ctx->ranks) {  // every local rank takes part in the collective; only the first carries data
+    use(each);
+    if (&each == &rc) {
+      NCK(api, api->AllGather(d_send, d_recv, bytes, ncclChar, each.comm, each.stream));
+    } else {
+      char *s2 = nullptr, *r2 = nullptr;
+      CK(cudaMalloc(&s2, bytes));
+      CK(cudaMalloc(&r2, bytes * (size_t)ctx->world));
+      CK(cudaMemsetAsync(s2, 0, bytes, each.stream));
+      NCK(api, api->AllGather(s2, r2, bytes, ncclChar, each.comm, each.stream));
+      ctx->graveyard.push_back(s2);
+      ctx->graveyard.push_back(r2);
+    }
+  }
+  NCK(api, api->GroupEnd());
+  use(rc);
+  CK(cudaMemcpyAsync(recv, d_recv, bytes * (size_t)ctx->world, cudaMemcpyDeviceToHost, rc.stream));
+  CK(cudaStreamSynchronize(rc.stream));
+  cudaFree(d_send);
+  cudaFree(d_recv);
+}
+
 unsigned long long* trace_slot(RankCtx& rc, int kind, int ctas) {
   static const char* prefix = getenv("DJETS_TRACE");
   if (!prefix || rc.trace_launches >= kTraceLaunches || ctas > kTraceCtas) return nullptr;
@@ -192,6 +250,8 @@ int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ran
       CK(cudaMemset(rc.d_ticket, 0, sizeof(unsigned)));
       CK(cudaMalloc(&rc.d_result, sizeof(double) * 2 * kMaxParts));
       CK(cudaMalloc(&rc.d_gather, sizeof(double) * kMaxParts));
+      CK(cudaMalloc(&rc.d_xp_err, sizeof(unsigned)));
+      CK(cudaMemset(rc.d_xp_err, 0, sizeof(unsigned)));
       CK(cudaMalloc(&rc.d_scalars, sizeof(double) * kMaxScalars));
       CK(cudaMemset(rc.d_scalars, 0, sizeof(double) * kMaxScalars));
       for (cudaEvent_t& e : rc.marks) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -252,6 +312,7 @@ int32_t djets_ctx_destroy(djets_ctx ctx) {
       cudaFree(rc.d_partials);
       cudaFree(rc.d_ticket);
       cudaFree(rc.d_gather);
+      cudaFree(rc.d_xp_err);
       cudaFree(rc.d_scalars);
       for (cudaEvent_t e : rc.marks)
         if (e) cudaEventDestroy(e);
@@ -263,7 +324,16 @@ int32_t djets_ctx_destroy(djets_ctx ctx) {
       cudaEventDestroy(rc.t1);
       cudaStreamDestroy(rc.stream);
     }
+    for (void* p : ctx->graveyard) cudaFree(p);
     delete ctx;
+  });
+}
+
+int32_t djets_ctx_set_host_allgather(djets_ctx ctx, djets_allgather_fn fn, void* user) {
+  return guard([&] {
+    REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
+    ctx->host_allgather = fn;
+    ctx->host_allgather_user = user;
   });
 }
 
@@ -275,6 +345,15 @@ int32_t djets_ctx_sync(djets_ctx ctx) {
       use(rc);
       CK(cudaStreamSynchronize(rc.stream));
     }
+    if ((int)ctx->ranks.size() < ctx->world)
+      for (RankCtx& rc : ctx->ranks) {
+        unsigned err = 0;
+        use(rc);
+        CK(cudaMemcpy(&err, rc.d_xp_err, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        REQUIRE(err == 0, DJETS_ERR_NCCL,
+                "cross-process exchange: a peer did not raise its flag within 20 s (a process died or the call "
+                "sequences of the processes differ)");
+      }
   });
 }
 
@@ -562,6 +641,9 @@ int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
     } else if (n == "persistent") {
       REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "persistent in {0,1}");
       ctx->persistent = value;
+    } else if (n == "ipc") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "ipc in {0,1}");
+      ctx->ipc = value;
     } else if (n == "prefetch") {
       REQUIRE(value >= 0 && value <= (1 << 20), DJETS_ERR_INVALID, "prefetch in 0..1048576 bytes");
       ctx->prefetch = value;

@@ -98,6 +98,7 @@ struct RankCtx {
   double* h_result_dev = nullptr;  // ... so a reduction kernel can store its result straight into host memory
   double* d_gather = nullptr;    // kMaxParts doubles: per-part partials gathered on the root rank of a device-side fold
   double* d_scalars = nullptr;   // kMaxScalars doubles: this rank's replica of every device-resident scalar
+  unsigned* d_xp_err = nullptr;  // raised by a flag wait that timed out (cross-process peer exchange)
   cudaEvent_t marks[8] = {};     // djets_ctx_mark / djets_ctx_wait_mark
   ncclComm_t comm = nullptr;
   int64_t launches[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
@@ -134,6 +135,10 @@ struct djets_ctx_s {
   int64_t persistent = 0;
   int64_t prefetch = 32768;  // bytes each first-wave CTA prefetches to L2 ahead of the dependency wait
   uint64_t epoch = 0;  // bumped by every set_param: captured graphs of an older epoch are dropped
+  int64_t ipc = 1;     // one rank per process: exchange through CUDA-IPC-mapped peer buffers and epoch flags instead of NCCL
+  std::vector<void*> graveyard;  // exchange buffers other processes may still have mapped: freed with the context
+  djets_allgather_fn host_allgather = nullptr;  // caller-provided control-plane collective (no NCCL needed)
+  void* host_allgather_user = nullptr;
   bool capturing = false;  // between djets_ctx_capture_begin and _end: every call is recorded, nothing may synchronise
   std::vector<int> free_scalars;  // slots of d_scalars not in use
   int next_scalar = 0;
@@ -160,6 +165,11 @@ unsigned long long* trace_slot(RankCtx& rc, int kind, int ctas);  // nullptr unl
 // cudaMalloc that gives the per-rank caches of freed vector parts back to the driver and retries once on OOM
 cudaError_t device_alloc(djets_ctx ctx, void** p, size_t bytes);
 void flush_vec_caches(djets_ctx ctx);
+// All-gather of one fixed-size record per process among the processes of the job: the host callback when the caller
+// provided one, else NCCL on rank-local device buffers.  `recv` holds world records, indexed by rank (records of
+// ranks that are not a process' first local rank are zero).
+void control_allgather(djets_ctx ctx, const void* send, void* recv, size_t bytes);
+inline bool has_control_plane(djets_ctx ctx) { return ctx->host_allgather != nullptr || ctx->has_nccl; }
 inline void no_sync_in_capture(djets_ctx ctx, const char* what) {
   if (ctx->capturing) fail(DJETS_ERR_INVALID, std::string(what) + " synchronises with the host: not allowed between djets_ctx_capture_begin and _end");
 }

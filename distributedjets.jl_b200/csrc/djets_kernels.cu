@@ -1078,6 +1078,46 @@ cudaError_t launch_gemv_t(int dtype, int adj_ru, int adj_cw, int ld_policy, cons
                    : launch_gemv_t_t<double, 0>(adj_ru, adj_cw, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream);
 }
 
+// ------------------------------------------------------------------------------------------------
+// epoch flags of the cross-process peer-memory exchange
+// ------------------------------------------------------------------------------------------------
+__global__ void flags_wait_kernel(FlagList f, unsigned* err) {
+  const int k = threadIdx.x;
+  if (k >= f.n) return;
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned cur;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(f.p[k]) : "memory");
+    if ((int)(cur - f.v[k]) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 20000000000ull) {  // 20 s: a peer died or the call sequences of the processes diverged
+      atomicExch(err, 1u);
+      break;
+    }
+    __nanosleep(64);
+  }
+}
+
+__global__ void flags_signal_kernel(FlagList f) {
+  const int k = threadIdx.x;
+  if (k >= f.n) return;
+  __threadfence_system();  // everything this stream stored before (peer stores included) is visible first
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[k]), "r"(f.v[k]) : "memory");
+}
+
+cudaError_t launch_flags_wait(const FlagList& f, unsigned* err, cudaStream_t stream) {
+  if (f.n <= 0) return cudaSuccess;
+  flags_wait_kernel<<<1, 32, 0, stream>>>(f, err);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_flags_signal(const FlagList& f, cudaStream_t stream) {
+  if (f.n <= 0) return cudaSuccess;
+  flags_signal_kernel<<<1, 32, 0, stream>>>(f);
+  return cudaGetLastError();
+}
+
 template <typename K>
 static int resident_ctas(K kernel, size_t smem = 0) {
   int dev = 0, sms = 0, per_sm = 0;

@@ -83,6 +83,18 @@ cudaError_t launch_fill(int dtype, void* dest, double a, long long n, cudaStream
 cudaError_t launch_binary(int dtype, int op, void* dest, const void* a, const void* b, long long n,
                           cudaStream_t stream);
 
+// Epoch flags of the cross-process exchange over peer memory (CUDA IPC): a producer stores its data into the
+// consumer's buffer (NVLink peer stores / copies) and then raises the consumer's flag to the apply's epoch; the
+// consumer's stream spins on its own (local) flag before the kernel that reads the data.  Comparisons are
+// wrap-safe; a wait that is not satisfied within ~20 s raises *err instead of hanging the GPU.
+struct FlagList {
+  unsigned* p[16];
+  unsigned v[16];
+  int n;
+};
+cudaError_t launch_flags_wait(const FlagList& f, unsigned* err, cudaStream_t stream);
+cudaError_t launch_flags_signal(const FlagList& f, cudaStream_t stream);
+
 // Closed elementwise program (djets_vec_eval): postfix byte-code, see DJETS_EV_* in include/djets.h.
 enum {
   EV_IN = 1, EV_SC = 2,

@@ -43,6 +43,7 @@ static void bind_all() {
   DJ_BIND(Send, "ncclSend");
   DJ_BIND(Recv, "ncclRecv");
   DJ_BIND(AllReduce, "ncclAllReduce");
+  DJ_BIND(AllGather, "ncclAllGather");
   DJ_BIND(GetErrorString, "ncclGetErrorString");
   DJ_BIND(GetVersion, "ncclGetVersion");
 #undef DJ_BIND

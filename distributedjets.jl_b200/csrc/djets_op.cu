@@ -18,6 +18,9 @@ struct DirPlan {
   int nitems = 0, nloose = 0;
   unsigned* d_tickets = nullptr;  // one per item
   unsigned* d_counter = nullptr;  // tile queue of the persistent kernels (zero between launches)
+  unsigned* flags = nullptr;      // epoch flags of the cross-process exchange (see XP_* below)
+  int64_t in_len = 0, part_len = 0;  // elements of the input part this cell reads / of the output part it contributes to
+  int nremote = 0;
   DiagTerm* d_diags = nullptr;
   char* W = nullptr;
   char* stage_in = nullptr;   // input slice received from its owner
@@ -62,6 +65,17 @@ struct djets_op_s {
   uint64_t graph_clock = 0;
   uint64_t graph_epoch = 0;  // context parameter epoch the cached graphs were captured under
   bool graphs_broken = false;
+  // Cross-process exchange over peer memory (one rank per process, CUDA IPC): what this process can address of
+  // every cell's exchange buffers, per direction; the epoch of the last apply per direction.
+  struct PeerBuf {
+    char* stage_in = nullptr;
+    char* R = nullptr;
+    unsigned* flags = nullptr;
+  };
+  bool xp = false, xp_tried = false;
+  std::vector<PeerBuf> xpeer[2];
+  std::vector<void*> xp_opened;
+  unsigned xp_epoch[2] = {0u, 0u};
   bool perfstat = false;  // time every cell's share of each apply (replaces Jets.perfstat, src:723-745)
   int enqueue_ops[2] = {0, 0};  // launches + copies of one apply, counted on the first direct run
 
@@ -130,16 +144,23 @@ void run_transfers(djets_ctx ctx, const std::vector<Transfer>& ts) {
 }
 
 
-void free_plan(DirPlan& p) {
+// `keep`: exchange buffers that were published to other processes (CUDA IPC) outlive the operator: a slower
+// peer may still hold them mapped; they are freed with the context.
+void free_plan(DirPlan& p, std::vector<void*>* keep = nullptr) {
   cudaFree(p.d_tiles);
   cudaFree(p.d_items);
   cudaFree(p.d_tickets);
   cudaFree(p.d_counter);
   cudaFree(p.d_diags);
   cudaFree(p.W);
-  cudaFree(p.stage_in);
   cudaFree(p.stage_out);
-  cudaFree(p.R);
+  for (void* q : {(void*)p.flags, (void*)p.stage_in, (void*)p.R}) {
+    if (!q) continue;
+    if (keep)
+      keep->push_back(q);
+    else
+      cudaFree(q);
+  }
   p = DirPlan();
 }
 
@@ -199,7 +220,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   use(*rc);
   g_alloc_ctx = ctx;
   DirPlan& plan = adjoint ? cell.adj : cell.fwd;
-  free_plan(plan);
+  free_plan(plan, op->xp_tried ? &ctx->graveyard : nullptr);
   const int es = elem_size(op->dtype);
   const int64_t r0 = op->row_cuts[cell.r], r1 = op->row_cuts[cell.r + 1];
   const int64_t c0 = op->isdiag ? r0 : op->col_cuts[cell.c], c1 = op->isdiag ? r1 : op->col_cuts[cell.c + 1];
@@ -411,9 +432,117 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   const int64_t in_len = adjoint ? op->rowpart_len[cell.r]
                                  : (op->isdiag ? op->colpart_len[cell.r] : op->colpart_len[cell.c]);
   const bool in_owner = adjoint ? (cell.c == 0) : (op->isdiag || cell.r == 0);
-  if (!in_owner) plan.stage_in = dalloc((size_t)in_len * es);
+  // with ranks in other processes the receive buffers are double-buffered by the parity of the apply's epoch
+  const int nbuf = (int)ctx->ranks.size() < ctx->world ? 2 : 1;
+  if (!in_owner) plan.stage_in = dalloc((size_t)nbuf * in_len * es);
   if (!owner) plan.stage_out = dalloc((size_t)part_len * es);
-  if (nremote > 0) plan.R = dalloc((size_t)nremote * part_len * es);
+  if (nremote > 0) plan.R = dalloc((size_t)nbuf * nremote * part_len * es);
+  plan.in_len = in_len;
+  plan.part_len = part_len;
+  plan.nremote = nremote;
+  if (nbuf == 2 && !op->isdiag)
+    plan.flags = reinterpret_cast<unsigned*>(dalloc(sizeof(unsigned) * (size_t)(2 + 2 * std::max(op->n1, op->n2))));
+}
+
+// Layout of a cell's flag array (per direction), nmax = max(n1, n2):
+//   [0]              in_ready        raised by the owner of my input part once stage_in holds the apply's input
+//   [1]              part_consumed   raised by the owner of my output part once it has summed my partial
+//   [2 + slot]       part_ready      raised by the sender of receive slot `slot` (owners only)
+//   [2 + nmax + idx] in_consumed     raised by consumer `idx` of my input part (input owners only)
+inline int XP_IN_READY() { return 0; }
+inline int XP_PART_CONSUMED() { return 1; }
+inline int XP_PART_READY(int slot) { return 2 + slot; }
+inline int XP_IN_CONSUMED(djets_op op, int idx) { return 2 + std::max(op->n1, op->n2) + idx; }
+
+// Collective over the processes of the job (called from finalize, which every process reaches in the same
+// order): all-gather the CUDA IPC handles of every cell's exchange buffers, map the remote ones, and agree
+// (all-reduce) on whether every process succeeded; otherwise the exchange stays on ncclSend / ncclRecv.
+void xp_setup(djets_op op) {
+  djets_ctx ctx = op->ctx;
+  if (op->xp_tried) return;
+  op->xp_tried = true;
+  const bool multi_process = (int)ctx->ranks.size() < ctx->world;
+  if (!multi_process || !has_control_plane(ctx) || ctx->ranks.size() != 1 || op->isdiag || op->n1 * op->n2 < 2) return;
+  RankCtx& rc = ctx->ranks.front();
+  use(rc);
+  struct Record {  // what one rank publishes
+    cudaIpcMemHandle_t h[2][3];
+    int present[2][3];
+    int cell;  // index of the rank's cell in the grid, -1 when it is not part of this operator
+    int ok;
+  };
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  Record mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.cell = -1;
+  const int ncell = op->n1 * op->n2;
+  for (int k = 0; k < ncell; ++k)
+    if (op->grid[k] == rc.rank) mine.cell = k;
+  int ok = ctx->ipc ? 1 : 0;
+  if (mine.cell >= 0 && ok) {
+    Cell& cell = op->cells[mine.cell];
+    for (int d = 0; d < 2; ++d) {
+      DirPlan& plan = d ? cell.adj : cell.fwd;
+      void* bufs[3] = {plan.stage_in, plan.R, plan.flags};
+      for (int b = 0; b < 3; ++b) {
+        if (!bufs[b]) continue;
+        if (cudaIpcGetMemHandle(&mine.h[d][b], bufs[b]) != cudaSuccess) {
+          (void)cudaGetLastError();
+          ok = 0;
+        } else {
+          mine.present[d][b] = 1;
+        }
+      }
+    }
+  }
+  mine.ok = ok;
+  std::vector<Record> all((size_t)ctx->world);
+  control_allgather(ctx, &mine, all.data(), sizeof(Record));
+  for (int r = 0; r < ctx->world; ++r)
+    if (all[(size_t)r].cell >= 0 && !all[(size_t)r].ok) ok = 0;
+  for (int d = 0; d < 2; ++d) op->xpeer[d].assign((size_t)ncell, djets_op_s::PeerBuf());
+  for (int r = 0; r < ctx->world && ok; ++r) {
+    const Record& rec = all[(size_t)r];
+    if (rec.cell < 0 || rec.cell >= ncell) continue;
+    for (int d = 0; d < 2 && ok; ++d) {
+      djets_op_s::PeerBuf& pb = op->xpeer[d][(size_t)rec.cell];
+      void* ptr[3] = {nullptr, nullptr, nullptr};
+      if (r == rc.rank) {
+        DirPlan& plan = d ? op->cells[(size_t)rec.cell].adj : op->cells[(size_t)rec.cell].fwd;
+        ptr[0] = plan.stage_in;
+        ptr[1] = plan.R;
+        ptr[2] = plan.flags;
+      } else {
+        for (int b = 0; b < 3 && ok; ++b) {
+          if (!rec.present[d][b]) continue;
+          if (cudaIpcOpenMemHandle(&ptr[b], rec.h[d][b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            (void)cudaGetLastError();
+            ok = 0;
+          } else {
+            op->xp_opened.push_back(ptr[b]);
+          }
+        }
+      }
+      pb.stage_in = reinterpret_cast<char*>(ptr[0]);
+      pb.R = reinterpret_cast<char*>(ptr[1]);
+      pb.flags = reinterpret_cast<unsigned*>(ptr[2]);
+    }
+  }
+  // agree: the peer-memory path is used only if every process could map what it needs
+  std::vector<int> oks((size_t)ctx->world, 0);
+  control_allgather(ctx, &ok, oks.data(), sizeof(int));
+  bool everyone = true;
+  for (int r = 0; r < ctx->world; ++r)
+    if (all[(size_t)r].cell >= 0 && !oks[(size_t)r]) everyone = false;
+  op->xp = everyone;
+  REQUIRE(op->xp || ctx->has_nccl, DJETS_ERR_NCCL,
+          "the exchange buffers could not be mapped between the processes (CUDA IPC) and the context has no NCCL to fall back on");
+}
+
+void xp_release(djets_op op) {
+  for (void* p : op->xp_opened) cudaIpcCloseMemHandle(p);
+  op->xp_opened.clear();
+  op->xp = false;
 }
 
 // The cross-rank traffic of one apply as a list of point-to-point messages between grid cells.
@@ -474,6 +603,7 @@ void finalize_op(djets_op op) {
     build_plan(op, c, false);
     build_plan(op, c, true);
   }
+  xp_setup(op);
   op->finalized = true;
 }
 
@@ -509,10 +639,143 @@ int apply_enqueue_timed(djets_op op, djets_vec out, djets_vec in, bool adjoint) 
   return n;
 }
 
+// One apply when every rank lives in its own process and the exchange buffers are mapped into each other's address
+// space (CUDA IPC): nothing goes through NCCL.  The owner of an input part copies it into its consumers' stage_in
+// (peer copies over NVLink) and raises their in_ready flags; a cell that does not own its output part lets its
+// kernels store the reduced partial straight into the owner's receive plane (peer stores) and raises the owner's
+// part_ready flag; each stream spins on its own local flags right before the kernel that needs the data.
+// Buffers alternate with the parity of the apply's epoch, the *_consumed flags keep a producer at most two applies
+// ahead of its consumer.  Replaces ArrayFutures + reduce! (src:600-604, 647-651, 694-698) and the remote getblock
+// (src:588, 635, 682) like the NCCL path, with one-sided traffic and ~2 us flag kernels instead of two collectives.
+int apply_enqueue_xp(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
+  djets_ctx ctx = op->ctx;
+  RankCtx& rc = ctx->ranks.front();
+  const int n1 = op->n1, n2 = op->n2, dir = adjoint ? 1 : 0;
+  int mine = -1;
+  for (int k = 0; k < n1 * n2; ++k)
+    if (op->grid[k] == rc.rank) mine = k;
+  const unsigned e = ++op->xp_epoch[dir];
+  if (mine < 0) return 0;  // this rank holds no cell of the operator
+  use(rc);
+  const int r = mine % n1, c = mine / n1;
+  Cell& cell = op->cells[mine];
+  DirPlan& plan = adjoint ? cell.adj : cell.fwd;
+  const int es = elem_size(op->dtype);
+  const int par = (int)(e & 1u);
+  const bool in_owner = adjoint ? (c == 0) : (r == 0);
+  const bool owner = adjoint ? (r == 0) : (c == 0);
+  const int ip = adjoint ? r : c, opart = adjoint ? c : r;
+  std::vector<djets_op_s::PeerBuf>& peer = op->xpeer[dir];
+  int nops = 0;
+  auto wait = [&](const FlagList& f) {
+    if (f.n == 0) return;
+    ++nops;
+    CK(launch_flags_wait(f, rc.d_xp_err, rc.stream));
+  };
+  auto signal = [&](const FlagList& f) {
+    if (f.n == 0) return;
+    ++nops;
+    CK(launch_flags_signal(f, rc.stream));
+  };
+  auto push = [&](FlagList& f, unsigned* p, unsigned v) {
+    REQUIRE(f.n < 16, DJETS_ERR_UNSUPPORTED, "peer-memory exchange: more than 16 peers along one grid dimension");
+    f.p[f.n] = p;
+    f.v[f.n++] = v;
+  };
+  // cells that consume my input part / that send partials to me
+  const int nbcast = adjoint ? n2 : n1;   // cells along the dimension the input is broadcast over
+  const int nred = adjoint ? n1 : n2;     // cells along the dimension the output is reduced over
+  auto bcast_cell = [&](int idx) { return adjoint ? (r + idx * n1) : (idx + c * n1); };
+  auto red_cell = [&](int idx) { return adjoint ? (idx + c * n1) : (r + idx * n1); };
+
+  const char* inp = nullptr;
+  if (in_owner) {
+    inp = in->parts[ip].d;
+    if (nbcast > 1) {
+      FlagList w{}, s{};
+      for (int idx = 1; idx < nbcast; ++idx) push(w, plan.flags + XP_IN_CONSUMED(op, idx), e - 2u);
+      wait(w);
+      const size_t bytes = (size_t)in->parts[ip].elem_count * es;
+      for (int idx = 1; idx < nbcast; ++idx) {
+        const djets_op_s::PeerBuf& pb = peer[(size_t)bcast_cell(idx)];
+        if (bytes) CK(cudaMemcpyAsync(pb.stage_in + (size_t)par * bytes, inp, bytes, cudaMemcpyDeviceToDevice, rc.stream));
+        ++nops;
+        push(s, pb.flags + XP_IN_READY(), e);
+      }
+      signal(s);
+    }
+  } else {
+    FlagList w{};
+    push(w, plan.flags + XP_IN_READY(), e);
+    if (!owner) push(w, plan.flags + XP_PART_CONSUMED(), e - 2u);
+    wait(w);
+    inp = plan.stage_in + (size_t)par * plan.in_len * es;
+  }
+  char* outp = nullptr;
+  if (owner) {
+    outp = out->parts[opart].d;
+  } else {
+    if (in_owner) {  // not waited for above
+      FlagList w{};
+      push(w, plan.flags + XP_PART_CONSUMED(), e - 2u);
+      wait(w);
+    }
+    const int own = red_cell(0);
+    const DirPlan& oplan_shape = plan;  // same part length along the reduced dimension
+    const int slot = (adjoint ? r : c) - 1;
+    outp = peer[(size_t)own].R + ((size_t)par * (nred - 1) + slot) * (size_t)oplan_shape.part_len * es;
+  }
+  if (plan.ntiles > 0) {
+    ++nops;
+    const Prefetch pf{plan.wave, (int)ctx->prefetch, (int)ctx->pdl, trace_slot(rc, adjoint ? DJETS_K_GEMV_T : DJETS_K_GEMV_N, plan.ntiles)};
+    const FusedFinish ff{plan.d_items, plan.d_diags, plan.d_tickets};
+    if (!adjoint)
+      launch_counted(ctx, rc, DJETS_K_GEMV_N, [&] {
+        return launch_gemv_n(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles, tile_grid(ctx, plan),
+                             plan.d_counter, inp, plan.W, outp, ff, pf, rc.stream);
+      });
+    else
+      launch_counted(ctx, rc, DJETS_K_GEMV_T, [&] {
+        return launch_gemv_t(op->dtype, plan.adj_ru, plan.adj_cw, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles,
+                             tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, ff, pf, rc.stream);
+      });
+  }
+  if (!owner) {
+    if (plan.nloose > 0) {
+      ++nops;
+      launch_counted(ctx, rc, DJETS_K_FINISH, [&] {
+        return launch_finish(op->dtype, plan.d_items, plan.nloose, plan.d_diags, inp, plan.W, nullptr, outp, rc.stream);
+      });
+    }
+    FlagList s{};
+    const int slot = (adjoint ? r : c) - 1;
+    push(s, peer[(size_t)red_cell(0)].flags + XP_PART_READY(slot), e);
+    if (!in_owner) push(s, peer[(size_t)bcast_cell(0)].flags + XP_IN_CONSUMED(op, adjoint ? c : r), e);
+    signal(s);
+  } else {
+    if (plan.nloose > 0) {
+      FlagList w{};
+      for (int idx = 1; idx < nred; ++idx) push(w, plan.flags + XP_PART_READY(idx - 1), e);
+      wait(w);
+      ++nops;
+      const char* Rp = plan.R ? plan.R + (size_t)par * plan.nremote * plan.part_len * es : nullptr;
+      launch_counted(ctx, rc, DJETS_K_FINISH, [&] {
+        return launch_finish(op->dtype, plan.d_items, plan.nloose, plan.d_diags, inp, plan.W, Rp, outp, rc.stream);
+      });
+    }
+    FlagList s{};
+    for (int idx = 1; idx < nred; ++idx) push(s, peer[(size_t)red_cell(idx)].flags + XP_PART_CONSUMED(), e);
+    if (!in_owner) push(s, peer[(size_t)bcast_cell(0)].flags + XP_IN_CONSUMED(op, adjoint ? c : r), e);
+    signal(s);
+  }
+  return nops;
+}
+
 // Enqueues one apply on the ranks' streams: exchange phase 0, tile kernels (+ fused sums), exchange
 // phase 1, owners' segmented sums.  Returns the number of enqueued operations.
 int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   djets_ctx ctx = op->ctx;
+  if (op->xp) return apply_enqueue_xp(op, out, in, adjoint);
   int nops = 0;
   const int es = elem_size(op->dtype);
   const int n1 = op->n1, n2 = op->isdiag ? 1 : op->n2;
@@ -994,7 +1257,13 @@ int32_t djets_op_replan(djets_op op) {
     clear_graphs(op);
     op->enqueue_ops[0] = op->enqueue_ops[1] = 0;
     op->finalized = false;
-    finalize_op(op);
+    finalize_op(op);  // build_plan retires published exchange buffers to the context's graveyard
+    if (op->xp_tried && (int)op->ctx->ranks.size() < op->ctx->world) {
+      xp_release(op);  // collective, like finalize: every process re-publishes its new buffers
+      op->xp_tried = false;
+      op->xp_epoch[0] = op->xp_epoch[1] = 0;
+      xp_setup(op);
+    }
   });
 }
 
@@ -1008,14 +1277,15 @@ int32_t djets_op_destroy(djets_op op) {
       cudaStreamSynchronize(rc->stream);
     }
     clear_graphs(op);
+    xp_release(op);
     for (Cell& c : op->cells) {
       RankCtx* rc = op->ctx->local(c.rank);
       if (!rc) continue;
       cudaSetDevice(rc->device);
       if (c.pt0) cudaEventDestroy(c.pt0);
       if (c.pt1) cudaEventDestroy(c.pt1);
-      free_plan(c.fwd);
-      free_plan(c.adj);
+      free_plan(c.fwd, op->xp_tried ? &op->ctx->graveyard : nullptr);
+      free_plan(c.adj, op->xp_tried ? &op->ctx->graveyard : nullptr);
     }
     for (int64_t i = 0; i < op->nbrow; ++i)
       for (int64_t j = 0; j < op->nbcol; ++j) {

@@ -144,6 +144,7 @@ void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_
   // depend on which parts happen to be local: with NCCL up, always all-reduce.
   const bool multi_process = (int)ctx->ranks.size() < ctx->world;
   const bool exchange = multi_process && ctx->has_nccl;
+  const bool host_exchange = multi_process && !ctx->has_nccl && ctx->host_allgather != nullptr;
   // ranks that take part: the owners of x's parts; with an exchange every rank this process drives
   std::vector<RankCtx*> involved;
   if (exchange) {
@@ -186,7 +187,8 @@ void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_
     }
     NCK(api, api->GroupEnd());
   } else {
-    REQUIRE(!any_remote, DJETS_ERR_NCCL, "vector has parts in other processes but the context has no NCCL");
+    REQUIRE(!any_remote || host_exchange, DJETS_ERR_NCCL,
+            "vector has parts in other processes but the context has neither NCCL nor a host all-gather");
   }
   if (exchange)
     for (RankCtx* rc : involved) {
@@ -196,6 +198,19 @@ void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_
   for (RankCtx* rc : involved) {
     use(*rc);
     CK(cudaStreamSynchronize(rc->stream));
+  }
+  if (host_exchange) {  // the P partials travel through the caller's control plane: one contributor per slot
+    std::vector<double> mine((size_t)np, 0.0), all((size_t)np * (size_t)ctx->world, 0.0);
+    for (int p = 0; p < np; ++p)
+      if (RankCtx* rc = ctx->local(x->parts[p].rank)) mine[(size_t)p] = rc->h_result[p];
+    control_allgather(ctx, mine.data(), all.data(), sizeof(double) * (size_t)np);
+    for (int p = 0; p < np; ++p) {
+      double v = 0.0;
+      for (int r = 0; r < ctx->world; ++r) v += all[(size_t)r * np + p];
+      out_parts[p] = v;
+      if (as_norm && x->parts[p].elem_count == 0) out_parts[p] = 0.0;
+    }
+    return;
   }
   for (int p = 0; p < np; ++p) {
     RankCtx* rc = ctx->local(x->parts[p].rank);
@@ -248,8 +263,26 @@ void reduce_to_scalar(djets_vec x, djets_vec y, int kind, double param, int fold
   };
   const int np = (int)x->parts.size();
   const bool multi_process = (int)ctx->ranks.size() < ctx->world;
+  if (multi_process && !ctx->has_nccl) {
+    // no NCCL: the partials go through the caller's control plane (this synchronises), the fold still runs on the device
+    REQUIRE(ctx->host_allgather != nullptr, DJETS_ERR_NCCL,
+            "vector has parts in other processes but the context has neither NCCL nor a host all-gather");
+    no_sync_in_capture(ctx, "a reduction over parts in other processes without NCCL");
+    std::vector<double> z((size_t)np, 0.0);
+    reduce_parts(x, y, kind, param, z.data(), as_norm);
+    for (RankCtx& rc : ctx->ranks) {
+      use(rc);
+      memcpy(rc.h_result + kMaxParts, z.data(), sizeof(double) * (size_t)np);
+      CK(cudaMemcpyAsync(rc.d_result, rc.h_result + kMaxParts, sizeof(double) * (size_t)np, cudaMemcpyHostToDevice, rc.stream));
+      launch_counted(ctx, rc, DJETS_K_REDUCE, [&] {
+        return launch_fold(x->dtype, fold_mode, fold_p, rc.d_result, np, rc.d_scalars + out->slot, ScalarPeers{{}, 0},
+                           rc.stream);
+      });
+      CK(cudaStreamSynchronize(rc.stream));  // h_result is reused by the next reduction
+    }
+    return;
+  }
   if (multi_process) {
-    REQUIRE(ctx->has_nccl, DJETS_ERR_NCCL, "vector has parts in other processes but the context has no NCCL");
     for (RankCtx& rc : ctx->ranks) {
       use(rc);
       CK(cudaMemsetAsync(rc.d_result, 0, sizeof(double) * np, rc.stream));

@@ -125,6 +125,14 @@ int32_t djets_nccl_unique_id(uint8_t* out128);
 int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ranks, const int32_t* device_ids,
                          const uint8_t* nccl_uid, djets_ctx* out);
 int32_t djets_ctx_destroy(djets_ctx ctx);
+/* Host-side all-gather among the processes of the job, provided by the caller (Julia: Distributed; Python:
+ * torch.distributed / MPI): every process passes one record of `bytes` bytes; `recv` has room for `world` records and
+ * the callback stores the record of every process of the job there, contiguously from the start, in any order (each
+ * record names its sender).  Returns 0 on success.  With it a multi-process job needs no NCCL at all: it carries the
+ * control plane (exchange of CUDA IPC handles when an operator is finalised, the P scalar partials of dot / norm),
+ * while block data moves between GPUs through peer memory.  Every process must make the same sequence of calls. */
+typedef int32_t (*djets_allgather_fn)(void* user, const void* send, void* recv, int64_t bytes);
+int32_t djets_ctx_set_host_allgather(djets_ctx ctx, djets_allgather_fn fn, void* user);
 int32_t djets_ctx_sync(djets_ctx ctx);
 /* nprocs() of the job, how many ranks this process drives, whether cross-process exchange is up. */
 int32_t djets_ctx_info(djets_ctx ctx, int32_t* world, int32_t* nlocal, int32_t* has_nccl);

@@ -15,7 +15,7 @@ C2JL = {
     "djets_ctx": {"Ptr{Cvoid}"}, "djets_vec": {"Ptr{Cvoid}"}, "djets_op": {"Ptr{Cvoid}"},
     "djets_ctx*": {"Ptr{Ptr{Cvoid}}"}, "djets_vec*": {"Ptr{Ptr{Cvoid}}"}, "djets_op*": {"Ptr{Ptr{Cvoid}}"},
     "djets_scalar": {"Ptr{Cvoid}"}, "djets_graph": {"Ptr{Cvoid}"}, "djets_scalar*": {"Ptr{Ptr{Cvoid}}"},
-    "djets_graph*": {"Ptr{Ptr{Cvoid}}"},
+    "djets_graph*": {"Ptr{Ptr{Cvoid}}"}, "djets_allgather_fn": {"Ptr{Cvoid}"},
 }
 
 
@@ -127,7 +127,7 @@ def test_python_ctypes_signatures_match_the_header():
         "void**": C.POINTER(C.c_void_p), "char*": C.c_char_p, "djets_ctx": C.c_void_p, "djets_vec": C.c_void_p,
         "djets_op": C.c_void_p, "djets_ctx*": C.POINTER(C.c_void_p), "djets_vec*": C.POINTER(C.c_void_p),
         "djets_op*": C.POINTER(C.c_void_p), "djets_scalar": C.c_void_p, "djets_graph": C.c_void_p,
-        "djets_scalar*": C.POINTER(C.c_void_p), "djets_graph*": C.POINTER(C.c_void_p),
+        "djets_scalar*": C.POINTER(C.c_void_p), "djets_graph*": C.POINTER(C.c_void_p), "djets_allgather_fn": C.c_void_p,
     }
     sigs = header_signatures()
     for name, argtypes in L.SIGNATURES.items():
