@@ -243,6 +243,9 @@ int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ran
       CK(cudaStreamCreateWithFlags(&rc.stream, cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&rc.ev, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&rc.ev_fork, cudaEventDisableTiming));
+      CK(cudaStreamCreateWithFlags(&rc.xstream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&rc.ev_x0, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&rc.ev_x1, cudaEventDisableTiming));
       CK(cudaEventCreate(&rc.t0));
       CK(cudaEventCreate(&rc.t1));
       CK(cudaMalloc(&rc.d_partials, sizeof(double) * reduce_max_ctas()));
@@ -320,6 +323,10 @@ int32_t djets_ctx_destroy(djets_ctx ctx) {
       cudaFreeHost(rc.h_result);
       cudaEventDestroy(rc.ev);
       cudaEventDestroy(rc.ev_fork);
+      cudaStreamSynchronize(rc.xstream);
+      cudaStreamDestroy(rc.xstream);
+      cudaEventDestroy(rc.ev_x0);
+      cudaEventDestroy(rc.ev_x1);
       cudaEventDestroy(rc.t0);
       cudaEventDestroy(rc.t1);
       cudaStreamDestroy(rc.stream);

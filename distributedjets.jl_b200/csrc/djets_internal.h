@@ -90,6 +90,8 @@ struct RankCtx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev = nullptr;  // scratch event for cross-stream ordering
   cudaEvent_t ev_fork = nullptr;  // fork / join of a captured apply
+  cudaStream_t xstream = nullptr;  // side stream: pushes of an input part to its consumers in other processes
+  cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   double* d_partials = nullptr;  // per-CTA partials of the reduction in flight
   unsigned* d_ticket = nullptr;  // last-CTA ticket of the reduction kernel (zero between launches)

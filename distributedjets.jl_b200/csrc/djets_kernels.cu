@@ -105,6 +105,28 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Spin of a whole CTA on the epoch flags of the cross-process exchange (see Prefetch::wait_flag): wrap-safe compare,
+// 20 s timeout that raises *err instead of hanging the GPU.
+__device__ __forceinline__ void wait_epoch_flags(const Prefetch& pf) {
+  if (pf.nwait <= 0) return;
+  if ((int)threadIdx.x < pf.nwait) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned cur;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(pf.wait_flag[threadIdx.x]) : "memory");
+      if ((int)(cur - pf.wait_value[threadIdx.x]) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > 20000000000ull) {
+        atomicExch(pf.wait_err, 1u);
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+}
+
 // DJETS_TRACE: per-CTA time stamps (start, dependency released, input staged, done) of one launch
 __device__ __forceinline__ void trace_stamp(unsigned long long* trace, int tile, int slot) {
   if (trace && threadIdx.x == 0) {
@@ -348,6 +370,7 @@ __global__ void __launch_bounds__(kThreads, 4) gemv_n_kernel(const DenseTile* __
     mbar_fence_init();
   }
   griddep_wait();
+  wait_epoch_flags(pf);
   trace_stamp(pf.trace, cur, 1);
   __syncthreads();  // barriers initialised
   // bit 0: staging buffer in use; bits 1,2: phase parity of bar[0], bar[1]; bit 3: current tile staged by bulk copy
@@ -480,6 +503,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __
     mbar_fence_init();
   }
   griddep_wait();
+  wait_epoch_flags(pf);
   trace_stamp(pf.trace, cur, 1);
   __syncthreads();  // barriers initialised
 

@@ -57,6 +57,13 @@ struct Prefetch {
   int bytes;
   int pdl;  // launch attribute: programmatic dependent launch on / off (a context parameter)
   unsigned long long* trace;  // debugging (DJETS_TRACE): 4 globaltimer stamps per CTA of this launch, or nullptr
+  // Cross-process exchange: epoch flags (in this GPU's memory, raised by peers) every CTA waits for before it
+  // touches the input slice or stores a partial -- the kernel is resident and its L2 prefetch under way while
+  // the input is still arriving over NVLink.  nwait == 0: nothing to wait for.
+  unsigned* wait_flag[2];
+  unsigned wait_value[2];
+  int nwait;
+  unsigned* wait_err;
 };
 // `grid` CTAs (<= ntiles) walk the tile table: CTA b takes tile b, further tiles are drawn from `counter`
 // (one unsigned, zero between launches; rearmed by the launch itself).  grid == ntiles: one tile per CTA.

@@ -689,45 +689,55 @@ int apply_enqueue_xp(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   auto red_cell = [&](int idx) { return adjoint ? (idx + c * n1) : (r + idx * n1); };
 
   const char* inp = nullptr;
+  bool pushed = false;
+  Prefetch pf{plan.wave, (int)ctx->prefetch, (int)ctx->pdl, nullptr, {nullptr, nullptr}, {0u, 0u}, 0, rc.d_xp_err};
+  auto kernel_wait = [&](unsigned* flag, unsigned v) {  // folded into the tile kernel's prologue when there is one
+    pf.wait_flag[pf.nwait] = flag;
+    pf.wait_value[pf.nwait++] = v;
+  };
   if (in_owner) {
     inp = in->parts[ip].d;
     if (nbcast > 1) {
+      // the pushes run on a side stream, so this cell's own tiles start at once
+      CK(cudaEventRecord(rc.ev_x0, rc.stream));
+      CK(cudaStreamWaitEvent(rc.xstream, rc.ev_x0, 0));
       FlagList w{}, s{};
       for (int idx = 1; idx < nbcast; ++idx) push(w, plan.flags + XP_IN_CONSUMED(op, idx), e - 2u);
-      wait(w);
+      ++nops;
+      CK(launch_flags_wait(w, rc.d_xp_err, rc.xstream));
       const size_t bytes = (size_t)in->parts[ip].elem_count * es;
       for (int idx = 1; idx < nbcast; ++idx) {
         const djets_op_s::PeerBuf& pb = peer[(size_t)bcast_cell(idx)];
-        if (bytes) CK(cudaMemcpyAsync(pb.stage_in + (size_t)par * bytes, inp, bytes, cudaMemcpyDeviceToDevice, rc.stream));
+        if (bytes) CK(cudaMemcpyAsync(pb.stage_in + (size_t)par * bytes, inp, bytes, cudaMemcpyDeviceToDevice, rc.xstream));
         ++nops;
         push(s, pb.flags + XP_IN_READY(), e);
       }
-      signal(s);
+      ++nops;
+      CK(launch_flags_signal(s, rc.xstream));
+      CK(cudaEventRecord(rc.ev_x1, rc.xstream));
+      pushed = true;
     }
   } else {
-    FlagList w{};
-    push(w, plan.flags + XP_IN_READY(), e);
-    if (!owner) push(w, plan.flags + XP_PART_CONSUMED(), e - 2u);
-    wait(w);
+    kernel_wait(plan.flags + XP_IN_READY(), e);
     inp = plan.stage_in + (size_t)par * plan.in_len * es;
   }
   char* outp = nullptr;
   if (owner) {
     outp = out->parts[opart].d;
   } else {
-    if (in_owner) {  // not waited for above
-      FlagList w{};
-      push(w, plan.flags + XP_PART_CONSUMED(), e - 2u);
-      wait(w);
-    }
-    const int own = red_cell(0);
-    const DirPlan& oplan_shape = plan;  // same part length along the reduced dimension
+    kernel_wait(plan.flags + XP_PART_CONSUMED(), e - 2u);
     const int slot = (adjoint ? r : c) - 1;
-    outp = peer[(size_t)own].R + ((size_t)par * (nred - 1) + slot) * (size_t)oplan_shape.part_len * es;
+    outp = peer[(size_t)red_cell(0)].R + ((size_t)par * (nred - 1) + slot) * (size_t)plan.part_len * es;
+  }
+  if (plan.ntiles == 0 && pf.nwait > 0) {  // no tile kernel to carry the waits
+    FlagList w{};
+    for (int k = 0; k < pf.nwait; ++k) push(w, pf.wait_flag[k], pf.wait_value[k]);
+    wait(w);
+    pf.nwait = 0;
   }
   if (plan.ntiles > 0) {
     ++nops;
-    const Prefetch pf{plan.wave, (int)ctx->prefetch, (int)ctx->pdl, trace_slot(rc, adjoint ? DJETS_K_GEMV_T : DJETS_K_GEMV_N, plan.ntiles)};
+    pf.trace = trace_slot(rc, adjoint ? DJETS_K_GEMV_T : DJETS_K_GEMV_N, plan.ntiles);
     const FusedFinish ff{plan.d_items, plan.d_diags, plan.d_tickets};
     if (!adjoint)
       launch_counted(ctx, rc, DJETS_K_GEMV_N, [&] {
@@ -768,6 +778,7 @@ int apply_enqueue_xp(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
     if (!in_owner) push(s, peer[(size_t)bcast_cell(0)].flags + XP_IN_CONSUMED(op, adjoint ? c : r), e);
     signal(s);
   }
+  if (pushed) CK(cudaStreamWaitEvent(rc.stream, rc.ev_x1, 0));  // later writers of the input part wait for the pushes
   return nops;
 }
 
@@ -848,7 +859,7 @@ int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
             return launch_gemv_n(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles,
                                  tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets},
                                  Prefetch{plan.wave, (int)ctx->prefetch, (int)ctx->pdl,
-                                          trace_slot(*rc, DJETS_K_GEMV_N, plan.ntiles)},
+                                          trace_slot(*rc, DJETS_K_GEMV_N, plan.ntiles), {nullptr, nullptr}, {0u, 0u}, 0, nullptr},
                                  rc->stream);
           });
         else
@@ -856,7 +867,7 @@ int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
             return launch_gemv_t(op->dtype, plan.adj_ru, plan.adj_cw, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles,
                                  tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets},
                                  Prefetch{plan.wave, (int)ctx->prefetch, (int)ctx->pdl,
-                                          trace_slot(*rc, DJETS_K_GEMV_T, plan.ntiles)},
+                                          trace_slot(*rc, DJETS_K_GEMV_T, plan.ntiles), {nullptr, nullptr}, {0u, 0u}, 0, nullptr},
                                  rc->stream);
           });
       }
