@@ -255,6 +255,8 @@ int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ran
       CK(cudaMalloc(&rc.d_gather, sizeof(double) * kMaxParts));
       CK(cudaMalloc(&rc.d_xp_err, sizeof(unsigned)));
       CK(cudaMemset(rc.d_xp_err, 0, sizeof(unsigned)));
+      CK(cudaMalloc(&rc.d_xp_ticket, sizeof(unsigned)));
+      CK(cudaMemset(rc.d_xp_ticket, 0, sizeof(unsigned)));
       CK(cudaMalloc(&rc.d_scalars, sizeof(double) * kMaxScalars));
       CK(cudaMemset(rc.d_scalars, 0, sizeof(double) * kMaxScalars));
       for (cudaEvent_t& e : rc.marks) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -316,6 +318,7 @@ int32_t djets_ctx_destroy(djets_ctx ctx) {
       cudaFree(rc.d_ticket);
       cudaFree(rc.d_gather);
       cudaFree(rc.d_xp_err);
+      cudaFree(rc.d_xp_ticket);
       cudaFree(rc.d_scalars);
       for (cudaEvent_t e : rc.marks)
         if (e) cudaEventDestroy(e);
@@ -651,6 +654,9 @@ int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
     } else if (n == "ipc") {
       REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "ipc in {0,1}");
       ctx->ipc = value;
+    } else if (n == "xp_kwait" || n == "xp_side" || n == "xp_push") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "xp_kwait / xp_side / xp_push in {0,1}");
+      (n == "xp_kwait" ? ctx->xp_kwait : (n == "xp_side" ? ctx->xp_side : ctx->xp_push)) = value;
     } else if (n == "prefetch") {
       REQUIRE(value >= 0 && value <= (1 << 20), DJETS_ERR_INVALID, "prefetch in 0..1048576 bytes");
       ctx->prefetch = value;

@@ -101,6 +101,7 @@ struct RankCtx {
   double* d_gather = nullptr;    // kMaxParts doubles: per-part partials gathered on the root rank of a device-side fold
   double* d_scalars = nullptr;   // kMaxScalars doubles: this rank's replica of every device-resident scalar
   unsigned* d_xp_err = nullptr;  // raised by a flag wait that timed out (cross-process peer exchange)
+  unsigned* d_xp_ticket = nullptr;  // completion ticket of the push kernel
   cudaEvent_t marks[8] = {};     // djets_ctx_mark / djets_ctx_wait_mark
   ncclComm_t comm = nullptr;
   int64_t launches[DJETS_K_COUNT] = {0, 0, 0, 0, 0};
@@ -138,6 +139,9 @@ struct djets_ctx_s {
   int64_t prefetch = 32768;  // bytes each first-wave CTA prefetches to L2 ahead of the dependency wait
   uint64_t epoch = 0;  // bumped by every set_param: captured graphs of an older epoch are dropped
   int64_t ipc = 1;     // one rank per process: exchange through CUDA-IPC-mapped peer buffers and epoch flags instead of NCCL
+  int64_t xp_kwait = 1;  // peer-memory exchange: epoch-flag waits inside the tile kernels' prologue (0: separate wait kernels)
+  int64_t xp_side = 0;   // peer-memory exchange: input pushes on a side stream (0: on the rank's main stream)
+  int64_t xp_push = 1;   // peer-memory exchange: one push kernel (wait + copy to all consumers + signal); 0: wait kernel, one peer copy per consumer, signal kernel
   std::vector<void*> graveyard;  // exchange buffers other processes may still have mapped: freed with the context
   djets_allgather_fn host_allgather = nullptr;  // caller-provided control-plane collective (no NCCL needed)
   void* host_allgather_user = nullptr;

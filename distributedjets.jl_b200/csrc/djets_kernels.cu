@@ -1130,6 +1130,59 @@ __global__ void flags_signal_kernel(FlagList f) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[k]), "r"(f.v[k]) : "memory");
 }
 
+__global__ void __launch_bounds__(kThreads) xp_push_kernel(const char* __restrict__ src, size_t bytes, PushList dst,
+                                                           FlagList waits, FlagList signals, unsigned* ticket,
+                                                           unsigned* err) {
+  const int tid = threadIdx.x;
+  if (tid < waits.n) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned cur;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(waits.p[tid]) : "memory");
+      if ((int)(cur - waits.v[tid]) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > 20000000000ull) {
+        atomicExch(err, 1u);
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+  const size_t nvec = bytes / 16;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i = (size_t)blockIdx.x * kThreads + tid; i < nvec; i += stride) {
+    const int4 v = reinterpret_cast<const int4*>(src)[i];
+    for (int k = 0; k < dst.n; ++k) reinterpret_cast<int4*>(dst.dst[k])[i] = v;
+  }
+  if (blockIdx.x == 0)  // tail of a part whose size is not a multiple of 16 bytes (element sizes are 4 or 8)
+    for (size_t b = nvec * 16 + (size_t)tid * 4; b < bytes; b += (size_t)kThreads * 4) {
+      const int v = *reinterpret_cast<const int*>(src + b);
+      for (int k = 0; k < dst.n; ++k) *reinterpret_cast<int*>(dst.dst[k] + b) = v;
+    }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    if (t + 1u == gridDim.x) {
+      *ticket = 0u;
+      __threadfence_system();
+      for (int k = 0; k < signals.n; ++k)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(signals.p[k]), "r"(signals.v[k]) : "memory");
+    }
+  }
+}
+
+cudaError_t launch_xp_push(const char* src, size_t bytes, const PushList& dst, const FlagList& waits, const FlagList& signals,
+                           unsigned* ticket, unsigned* err, cudaStream_t stream) {
+  const size_t nvec = bytes / 16;
+  int grid = (int)((nvec + kThreads - 1) / kThreads);
+  grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
+  xp_push_kernel<<<grid, kThreads, 0, stream>>>(src, bytes, dst, waits, signals, ticket, err);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_flags_wait(const FlagList& f, unsigned* err, cudaStream_t stream) {
   if (f.n <= 0) return cudaSuccess;
   flags_wait_kernel<<<1, 32, 0, stream>>>(f, err);

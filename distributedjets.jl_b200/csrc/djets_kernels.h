@@ -99,6 +99,15 @@ struct FlagList {
   unsigned v[16];
   int n;
 };
+// One kernel for the whole input push of the peer-memory exchange: wait for the consumers' *_consumed flags, copy
+// `bytes` from src into every destination (peer stores: all NVLink destinations are written in parallel), then the
+// last CTA raises the consumers' in_ready flags.  `ticket`: one unsigned, zero between launches.
+struct PushList {
+  char* dst[16];
+  int n;
+};
+cudaError_t launch_xp_push(const char* src, size_t bytes, const PushList& dst, const FlagList& waits, const FlagList& signals,
+                           unsigned* ticket, unsigned* err, cudaStream_t stream);
 cudaError_t launch_flags_wait(const FlagList& f, unsigned* err, cudaStream_t stream);
 cudaError_t launch_flags_signal(const FlagList& f, cudaStream_t stream);
 

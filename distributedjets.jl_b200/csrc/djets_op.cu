@@ -434,7 +434,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   const bool in_owner = adjoint ? (cell.c == 0) : (op->isdiag || cell.r == 0);
   // with ranks in other processes the receive buffers are double-buffered by the parity of the apply's epoch
   const int nbuf = (int)ctx->ranks.size() < ctx->world ? 2 : 1;
-  if (!in_owner) plan.stage_in = dalloc((size_t)nbuf * in_len * es);
+  if (!in_owner) plan.stage_in = dalloc((size_t)nbuf * round_up(in_len * es, 256));  // each buffer 256-byte aligned
   if (!owner) plan.stage_out = dalloc((size_t)part_len * es);
   if (nremote > 0) plan.R = dalloc((size_t)nbuf * nremote * part_len * es);
   plan.in_len = in_len;
@@ -699,27 +699,41 @@ int apply_enqueue_xp(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
     inp = in->parts[ip].d;
     if (nbcast > 1) {
       // the pushes run on a side stream, so this cell's own tiles start at once
-      CK(cudaEventRecord(rc.ev_x0, rc.stream));
-      CK(cudaStreamWaitEvent(rc.xstream, rc.ev_x0, 0));
+      cudaStream_t ps = ctx->xp_side ? rc.xstream : rc.stream;
+      if (ctx->xp_side) {
+        CK(cudaEventRecord(rc.ev_x0, rc.stream));
+        CK(cudaStreamWaitEvent(rc.xstream, rc.ev_x0, 0));
+      }
       FlagList w{}, s{};
+      PushList pl{};
       for (int idx = 1; idx < nbcast; ++idx) push(w, plan.flags + XP_IN_CONSUMED(op, idx), e - 2u);
-      ++nops;
-      CK(launch_flags_wait(w, rc.d_xp_err, rc.xstream));
       const size_t bytes = (size_t)in->parts[ip].elem_count * es;
       for (int idx = 1; idx < nbcast; ++idx) {
         const djets_op_s::PeerBuf& pb = peer[(size_t)bcast_cell(idx)];
-        if (bytes) CK(cudaMemcpyAsync(pb.stage_in + (size_t)par * bytes, inp, bytes, cudaMemcpyDeviceToDevice, rc.xstream));
-        ++nops;
+        pl.dst[pl.n++] = pb.stage_in + (size_t)par * round_up((int64_t)bytes, 256);
         push(s, pb.flags + XP_IN_READY(), e);
       }
-      ++nops;
-      CK(launch_flags_signal(s, rc.xstream));
-      CK(cudaEventRecord(rc.ev_x1, rc.xstream));
-      pushed = true;
+      if (ctx->xp_push) {
+        ++nops;
+        CK(launch_xp_push(inp, bytes, pl, w, s, rc.d_xp_ticket, rc.d_xp_err, ps));
+      } else {
+        ++nops;
+        CK(launch_flags_wait(w, rc.d_xp_err, ps));
+        for (int k = 0; k < pl.n; ++k) {
+          if (bytes) CK(cudaMemcpyAsync(pl.dst[k], inp, bytes, cudaMemcpyDeviceToDevice, ps));
+          ++nops;
+        }
+        ++nops;
+        CK(launch_flags_signal(s, ps));
+      }
+      if (ctx->xp_side) {
+        CK(cudaEventRecord(rc.ev_x1, rc.xstream));
+        pushed = true;
+      }
     }
   } else {
     kernel_wait(plan.flags + XP_IN_READY(), e);
-    inp = plan.stage_in + (size_t)par * plan.in_len * es;
+    inp = plan.stage_in + (size_t)par * round_up(plan.in_len * es, 256);
   }
   char* outp = nullptr;
   if (owner) {
@@ -729,7 +743,7 @@ int apply_enqueue_xp(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
     const int slot = (adjoint ? r : c) - 1;
     outp = peer[(size_t)red_cell(0)].R + ((size_t)par * (nred - 1) + slot) * (size_t)plan.part_len * es;
   }
-  if (plan.ntiles == 0 && pf.nwait > 0) {  // no tile kernel to carry the waits
+  if ((plan.ntiles == 0 || !ctx->xp_kwait) && pf.nwait > 0) {  // no tile kernel to carry the waits
     FlagList w{};
     for (int k = 0; k < pf.nwait; ++k) push(w, pf.wait_flag[k], pf.wait_value[k]);
     wait(w);

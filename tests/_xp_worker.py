@@ -45,6 +45,9 @@ def main():
     dist.init_process_group("gloo")
     ctx = dj.Context.spmd(rank, world, rank % ngpu, nccl_uid=None, allgather=dj.torch_allgather())
     dj.set_default_context(ctx)
+    for name in ("xp_push", "xp_side", "xp_kwait"):                # A/B of the exchange mechanisms (scripts, debugging)
+        if os.environ.get("DJETS_" + name.upper()):
+            ctx.set_param(name, int(os.environ["DJETS_" + name.upper()]))
     grids = [(world, 1), (1, world)] + ([(2, world // 2)] if world >= 4 else [])
     for dtype, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
         for n1, n2 in grids:
