@@ -107,23 +107,25 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 // Spin of a whole CTA on the epoch flags of the cross-process exchange (see Prefetch::wait_flag): wrap-safe compare,
 // 20 s timeout that raises *err instead of hanging the GPU.
+__device__ __forceinline__ void spin_epoch_flag(const unsigned* flag, unsigned value, unsigned* err) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned cur;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(flag) : "memory");
+    if ((int)(cur - value) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 20000000000ull) {
+      atomicExch(err, 1u);
+      break;
+    }
+    __nanosleep(32);
+  }
+}
 __device__ __forceinline__ void wait_epoch_flags(const Prefetch& pf) {
   if (pf.nwait <= 0) return;
-  if ((int)threadIdx.x < pf.nwait) {
-    unsigned long long t0, t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-      unsigned cur;
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(pf.wait_flag[threadIdx.x]) : "memory");
-      if ((int)(cur - pf.wait_value[threadIdx.x]) >= 0) break;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (t - t0 > 20000000000ull) {
-        atomicExch(pf.wait_err, 1u);
-        break;
-      }
-      __nanosleep(32);
-    }
-  }
+  if (threadIdx.x == 0) spin_epoch_flag(pf.wait_flag[0], pf.wait_value[0], pf.wait_err);
+  if (threadIdx.x == 32 && pf.nwait > 1) spin_epoch_flag(pf.wait_flag[1], pf.wait_value[1], pf.wait_err);
   __syncthreads();
 }
 
@@ -198,6 +200,47 @@ __device__ __forceinline__ void stage_wait(bool bulk, T* __restrict__ dst, const
     for (int i = threadIdx.x; i < pad_to; i += blockDim.x) dst[i] = (i < n) ? src[i] : T(0);
   }
   __syncthreads();
+}
+
+// Synchronous form used by the one-tile-per-CTA kernels.
+template <typename T>
+__device__ __forceinline__ void stage_vector(T* __restrict__ dst, const T* __restrict__ src, int n, int pad_to,
+                                             uint64_t* bar) {
+  const int tid = threadIdx.x;
+  const uint32_t bytes = (uint32_t)n * (uint32_t)sizeof(T);
+  const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0) && bytes >= 512;
+  if (bulk) {
+    const uint32_t b = smem_u32(bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(dst)),
+          "l"(src), "r"(bytes), "r"(b)
+          : "memory");
+    }
+    for (int i = n + tid; i < pad_to; i += blockDim.x) dst[i] = T(0);
+    // all threads wait for the bytes to land (phase 0)
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(b)
+          : "memory");
+    }
+    __syncthreads();
+  } else {
+    for (int i = tid; i < pad_to; i += blockDim.x) dst[i] = (i < n) ? src[i] : T(0);
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -308,6 +351,261 @@ __device__ __forceinline__ void fused_finish(int fin, const FusedFinish& ff, con
     finish_item<T, true>(ff.items[fin], ff.diags, in, W, nullptr, out);
     if (threadIdx.x == 0) ff.tickets[fin] = 0u;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One tile per CTA (the default): the hardware scheduler hands the tiles out.
+// Forward dense tiles: partial[r] = sum_c A[r,c] x[c].  A is column-major, so a thread owns VEC
+// consecutive rows (one 128-bit load per column) and walks the columns; the CTA is TX threads wide
+// along the rows and TY = 256/TX column groups deep; the TY partial strips are summed in shared
+// memory in a fixed order.  U independent 128-bit loads are in flight per thread.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int TX, int POLICY>
+__global__ void __launch_bounds__(kThreads, 4) gemv_n_tile_kernel(const DenseTile* __restrict__ tiles,
+                                                          const T* __restrict__ in, T* W, T* __restrict__ out,
+                                                          FusedFinish ff, Prefetch pf) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  constexpr int TY = kThreads / TX;
+  constexpr int TR = TX * VEC;
+  constexpr int U = 8;
+  __shared__ __align__(128) T xs[kFwdMaxTC];
+  __shared__ __align__(16) T red[(TY > 1) ? TY * TR : 1];
+  __shared__ __align__(8) uint64_t bar;
+
+  griddep_launch_dependents();
+  trace_stamp(pf.trace, blockIdx.x, 0);
+  const DenseTile t = tiles[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int rows = t.rows, cols = t.cols;
+
+  uint64_t pol = 0;
+  if (POLICY == 1) pol = make_evict_first_policy();
+
+  const int tx = tid % TX, ty = tid / TX;
+  const int r0 = tx * VEC;
+  T acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = T(0);
+
+  const long long ld = t.ld;
+  const T* a = reinterpret_cast<const T*>(t.A) + r0 + (long long)ty * ld;
+  const long long cstep = (long long)TY * ld;
+  int c = ty;
+  // first batch of matrix loads goes out before the input vector is even looked at
+  const bool pre = (r0 < rows) && (c + (U - 1) * TY < cols);
+  V v0[U];
+  if (pre) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) v0[u] = ld_stream<POLICY>(reinterpret_cast<const V*>(a + u * cstep), pol);
+  }
+  if ((int)blockIdx.x < pf.ctas) {
+    // columns after the pre-loaded batch, one run of `rows` elements per column
+    const uint32_t run = ((uint32_t)rows * (uint32_t)sizeof(T)) & ~15u;
+    const int ncol = run ? min(cols - U * TY, (int)(pf.bytes / run)) : 0;
+    const T* base = reinterpret_cast<const T*>(t.A) + (long long)(U * TY) * ld;
+    for (int cc = tid; cc < ncol; cc += kThreads) prefetch_l2_bulk(base + (long long)cc * ld, run);
+  }
+  griddep_wait();
+  wait_epoch_flags(pf);
+  trace_stamp(pf.trace, blockIdx.x, 1);
+  stage_vector<T>(xs, in + t.vin, cols, cols, &bar);
+  trace_stamp(pf.trace, blockIdx.x, 2);
+
+  if (r0 < rows) {
+    if (pre) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) fma_vec(acc, v0[u], xs[c + u * TY]);
+      a += U * cstep;
+      c += U * TY;
+    }
+    for (; c + (U - 1) * TY < cols; c += U * TY) {
+      V v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = ld_stream<POLICY>(reinterpret_cast<const V*>(a + u * cstep), pol);
+#pragma unroll
+      for (int u = 0; u < U; ++u) fma_vec(acc, v[u], xs[c + u * TY]);
+      a += U * cstep;
+    }
+    for (; c < cols; c += TY) {
+      V v = ld_stream<POLICY>(reinterpret_cast<const V*>(a), pol);
+      fma_vec(acc, v, xs[c]);
+      a += cstep;
+    }
+  }
+
+  T* dst = (t.direct ? out : W) + t.wout;
+  if (TY > 1) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) red[ty * TR + r0 + k] = acc[k];
+    __syncthreads();
+    for (int r = tid; r < rows; r += kThreads) {  // rows <= TR
+      T s = red[r];
+#pragma unroll
+      for (int y = 1; y < TY; ++y) s += red[y * TR + r];
+      dst[r] = s;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if (r0 + k < rows) dst[r0 + k] = acc[k];
+  }
+  if (t.fin >= 0) fused_finish<T>(t.fin, ff, in, W, out);
+  trace_stamp(pf.trace, blockIdx.x, 3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adjoint dense tiles: partial[c] = sum_r A[r,c] y[r].  A warp owns CW columns at a time and
+// streams down them with 128-bit loads (each lane VEC rows, 32 lanes = 512 contiguous bytes per
+// column), RU row chunks unrolled -> CW*RU = 16 independent loads in flight per lane whatever the
+// column height: (RU,CW) = (4,4) for tall columns, (2,8) and (1,16) for short ones; the y slice is
+// staged once per CTA in shared memory and each 128-bit LDS of y is reused for the CW columns; the
+// per-lane sums are combined with a column-halving shuffle butterfly.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int RU, int CW, int POLICY>
+__global__ void __launch_bounds__(kThreads, 2) gemv_t_tile_kernel(const DenseTile* __restrict__ tiles,
+                                                             const T* __restrict__ in, T* W, T* __restrict__ out,
+                                                             FusedFinish ff, Prefetch pf) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  constexpr int S = 32 * VEC;  // rows one warp covers with one load per lane
+  __shared__ __align__(128) T ys[kAdjMaxTRBytes / sizeof(T)];
+  __shared__ __align__(8) uint64_t bar;
+
+  griddep_launch_dependents();
+  trace_stamp(pf.trace, blockIdx.x, 0);
+  const DenseTile t = tiles[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rows = t.rows, cols = t.cols;
+  const int rowsv = (rows + VEC - 1) / VEC * VEC;  // pad rows of A are zero; pad y with zeros too
+  if ((int)blockIdx.x < pf.ctas) {
+    // the columns of the first pass over the warps, below the first batch of loads: one run per column
+    const int ncol = min(cols, (kThreads / 32) * CW);
+    const int below = rowsv - RU * S;
+    const uint32_t want = ncol ? (uint32_t)(pf.bytes / ncol) & ~15u : 0u;
+    const uint32_t run = below > 0 ? min(want, ((uint32_t)below * (uint32_t)sizeof(T)) & ~15u) : 0u;
+    const T* base = reinterpret_cast<const T*>(t.A) + RU * S;
+    if (run)
+      for (int cc = tid; cc < ncol; cc += kThreads) prefetch_l2_bulk(base + (long long)cc * t.ld, run);
+  }
+  griddep_wait();
+  wait_epoch_flags(pf);
+  trace_stamp(pf.trace, blockIdx.x, 1);
+  stage_vector<T>(ys, in + t.vin, rows, rowsv, &bar);
+  trace_stamp(pf.trace, blockIdx.x, 2);
+
+  uint64_t pol = 0;
+  if (POLICY == 1) pol = make_evict_first_policy();
+
+  const long long ld = t.ld;
+  const T* A = reinterpret_cast<const T*>(t.A);
+  T* dst = (t.direct ? out : W) + t.wout;
+  const int ngroups = (cols + CW - 1) / CW;
+
+  for (int g = warp; g < ngroups; g += kThreads / 32) {
+    const int c0 = g * CW;
+    const int last = cols - 1 - c0;  // columns past the tile edge re-read the last one and are not stored
+    const T* base = A + (long long)c0 * ld + lane * VEC;
+    T acc[CW];
+#pragma unroll
+    for (int k = 0; k < CW; ++k) acc[k] = T(0);
+
+    int rb = 0;
+    for (; rb + RU * S <= rowsv; rb += RU * S) {
+      V a[RU][CW];
+#pragma unroll
+      for (int u = 0; u < RU; ++u)
+#pragma unroll
+        for (int k = 0; k < CW; ++k)
+          a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
+#pragma unroll
+        for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[u][k], y);
+      }
+    }
+    if (CW == 4) {
+      // tall columns: the remainder is at most RU-1 chunks: pairs of chunks first, then a guarded last one
+      if (RU > 2) {
+        for (; rb + 2 * S <= rowsv; rb += 2 * S) {
+          V a[2][CW];
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int k = 0; k < CW; ++k)
+              a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
+#pragma unroll
+            for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[u][k], y);
+          }
+        }
+      }
+      for (; rb < rowsv; rb += S) {
+        if (rb + lane * VEC < rowsv) {
+          V a[CW];
+#pragma unroll
+          for (int k = 0; k < CW; ++k)
+            a[k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb), pol);
+          const V y = *reinterpret_cast<const V*>(ys + rb + lane * VEC);
+#pragma unroll
+          for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[k], y);
+        }
+      }
+    } else if (rb < rowsv) {
+      // short columns: the remainder IS most of the column -- one guarded batch, CW*RU loads in flight
+      V a[RU][CW];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const bool ok = rb + u * S + lane * VEC < rowsv;
+#pragma unroll
+        for (int k = 0; k < CW; ++k) {
+          if (ok)
+            a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        if (rb + u * S + lane * VEC < rowsv) {
+          const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
+#pragma unroll
+          for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[u][k], y);
+        }
+      }
+    }
+    // Warp reduction of CW columns at once: while more than one column is live, each butterfly step
+    // also halves the columns a lane keeps (the lanes with the offset bit set keep the upper half), so
+    // CW columns cost CW-1 + (5 - log2 CW) shuffles instead of 5*CW.  The pattern is fixed: deterministic.
+    int width = CW;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      if (width > 1) {
+        width >>= 1;
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < CW / 2; ++k) {
+          if (k < width) {
+            const T send = upper ? acc[k] : acc[k + width];
+            const T keep = upper ? acc[k + width] : acc[k];
+            acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+      } else {
+        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+      }
+    }
+    // lane bits 16, 8, ... (one per halving step) spell the column a lane ended up with
+    constexpr int kHalvings = (CW == 16) ? 4 : (CW == 8) ? 3 : (CW == 4) ? 2 : (CW == 2) ? 1 : 0;
+    int mycol = 0;
+#pragma unroll
+    for (int h = 0; h < kHalvings; ++h) mycol |= ((lane >> (4 - h)) & 1) << (kHalvings - 1 - h);
+    const bool writer = (lane & ((32 >> kHalvings) - 1)) == 0;
+    if (writer && c0 + mycol < cols) dst[c0 + mycol] = acc[0];
+  }
+  if (t.fin >= 0) fused_finish<T>(t.fin, ff, in, W, out);
+  trace_stamp(pf.trace, blockIdx.x, 3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1054,10 +1352,18 @@ static cudaError_t launch_gemv_n_t(int fwd_tx, const DenseTile* tiles, int ntile
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
   switch (fwd_tx) {
-    case 32: return launch_tiles(gemv_n_kernel<T, 32, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
-    case 64: return launch_tiles(gemv_n_kernel<T, 64, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
-    case 128: return launch_tiles(gemv_n_kernel<T, 128, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
-    case 256: return launch_tiles(gemv_n_kernel<T, 256, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    case 32:
+      if (grid >= ntiles) return launch_tiles(gemv_n_tile_kernel<T, 32, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+      return launch_tiles(gemv_n_kernel<T, 32, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    case 64:
+      if (grid >= ntiles) return launch_tiles(gemv_n_tile_kernel<T, 64, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+      return launch_tiles(gemv_n_kernel<T, 64, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    case 128:
+      if (grid >= ntiles) return launch_tiles(gemv_n_tile_kernel<T, 128, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+      return launch_tiles(gemv_n_kernel<T, 128, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    case 256:
+      if (grid >= ntiles) return launch_tiles(gemv_n_tile_kernel<T, 256, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+      return launch_tiles(gemv_n_kernel<T, 256, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -1083,11 +1389,26 @@ static cudaError_t launch_gemv_t_t(int adj_ru, int adj_cw, const DenseTile* tile
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
   // (rows unrolled, columns per warp): tall columns stream down 4 columns, short ones fan out over 16
-  if (adj_cw == 16 && adj_ru == 1) return launch_tiles(gemv_t_kernel<T, 1, 16, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
-  if (adj_cw == 8 && adj_ru == 2) return launch_tiles(gemv_t_kernel<T, 2, 8, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
-  if (adj_cw == 4 && adj_ru == 4) return launch_tiles(gemv_t_kernel<T, 4, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
-  if (adj_cw == 4 && adj_ru == 2) return launch_tiles(gemv_t_kernel<T, 2, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
-  if (adj_cw == 4 && adj_ru == 1) return launch_tiles(gemv_t_kernel<T, 1, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+  if (adj_cw == 16 && adj_ru == 1) {
+    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 1, 16, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(gemv_t_kernel<T, 1, 16, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+  }
+  if (adj_cw == 8 && adj_ru == 2) {
+    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 2, 8, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(gemv_t_kernel<T, 2, 8, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+  }
+  if (adj_cw == 4 && adj_ru == 4) {
+    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 4, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(gemv_t_kernel<T, 4, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+  }
+  if (adj_cw == 4 && adj_ru == 2) {
+    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 2, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(gemv_t_kernel<T, 2, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+  }
+  if (adj_cw == 4 && adj_ru == 1) {
+    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 1, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(gemv_t_kernel<T, 1, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+  }
   return cudaErrorInvalidValue;
 }
 

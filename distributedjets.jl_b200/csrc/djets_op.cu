@@ -301,6 +301,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   plan.wave = gemv_resident_ctas(op->dtype, adjoint ? 1 : 0, adjoint ? adj_ru : (int)fwd_tx, adj_cw, (int)op->p_ld_policy);
   std::vector<DenseTile> tiles;
   std::vector<FinishItem> loose, fused;
+  std::vector<int64_t> loose_key;  // offset of the item's chunk inside its block: the launch order of the loose items
   std::vector<DiagTerm> diags;
   int64_t wtotal = 0;
   // A cell that sums planes received from peers finishes in a separate kernel after the receive;
@@ -357,6 +358,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
         it.len = (int)std::min<int64_t>(chunk, olen - e0);
         it.pad_ = 0;
         dst.push_back(it);
+        if (&dst == &loose) loose_key.push_back(e0);
       }
       return first;
     };
@@ -412,6 +414,22 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
       }
       plane += sh.nplanes;
     }
+  }
+  // Loose items whose block rows share input blocks are launched chunk-major (same offset inside every block, block
+  // after block): the diagonal terms of neighbouring CTAs then read the same slices of the input blocks, which stay in
+  // L2 -- a full grid of diagonal blocks reads every input block once from HBM instead of once per block row
+  // (24x24 diagonal blocks of 2^20 F64: 5.04 -> 5.67 TB/s).  Block-diagonal operators keep the block-major order
+  // (contiguous streams: 6.86 TB/s against 6.58 chunk-major).
+  bool shared_inputs = false;  // some item sums several diagonal terms: input slices are shared between block rows
+  for (const FinishItem& it : loose) shared_inputs = shared_inputs || (it.diag_end - it.diag_begin >= 2);
+  if (shared_inputs) {
+    std::vector<size_t> order(loose.size());
+    for (size_t k = 0; k < order.size(); ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return loose_key[a] < loose_key[b]; });
+    std::vector<FinishItem> sorted;
+    sorted.reserve(loose.size());
+    for (size_t k : order) sorted.push_back(loose[k]);
+    loose.swap(sorted);
   }
   // loose items first, fused items after them; tiles index the concatenated table
   const int nloose = (int)loose.size();

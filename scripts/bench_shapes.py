@@ -12,6 +12,9 @@ import djets_loader  # noqa: E402
 
 dj = djets_loader.load()
 ctx = dj.init(world=1, devices=[0])
+for kv in sys.argv[1:]:                                   # context parameters, e.g. persistent=1
+    k, v = kv.split("=")
+    ctx.set_param(k, int(v))
 CASES = [  # dtype, m, n, nb (nb x nb blocks)
     ("f64", 1000, 1000, 32), ("f32", 1023, 1025, 45), ("f32", 256, 256, 128), ("f64", 100, 100, 300),
     ("f32", 4096, 512, 20), ("f32", 512, 4096, 20), ("f64", 5000, 64, 40), ("f64", 64, 5000, 40),
