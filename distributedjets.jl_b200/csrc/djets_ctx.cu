@@ -660,6 +660,9 @@ int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
     } else if (n == "prefetch") {
       REQUIRE(value >= 0 && value <= (1 << 20), DJETS_ERR_INVALID, "prefetch in 0..1048576 bytes");
       ctx->prefetch = value;
+    } else if (n == "adj_light") {
+      REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "adj_light in {0,1}");
+      ctx->adj_light = value;
     } else if (n == "auto_tile") {
       REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "auto_tile in {0,1}");
       ctx->auto_tile = value;

@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 4) gemv_n_tile_kernel(const DenseTil
 // per-lane sums are combined with a column-halving shuffle butterfly.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int RU, int CW, int POLICY>
-__global__ void __launch_bounds__(kThreads, 2) gemv_t_tile_kernel(const DenseTile* __restrict__ tiles,
+__global__ void __launch_bounds__(kThreads, (RU * CW <= 8) ? 3 : 2) gemv_t_tile_kernel(const DenseTile* __restrict__ tiles,
                                                              const T* __restrict__ in, T* W, T* __restrict__ out,
                                                              FusedFinish ff, Prefetch pf) {
   using V = typename VecT<T>::type;
@@ -1389,6 +1389,10 @@ static cudaError_t launch_gemv_t_t(int adj_ru, int adj_cw, const DenseTile* tile
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
   // (rows unrolled, columns per warp): tall columns stream down 4 columns, short ones fan out over 16
+  if (adj_cw == 8 && adj_ru == 1) {
+    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 1, 8, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(gemv_t_kernel<T, 1, 8, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+  }
   if (adj_cw == 16 && adj_ru == 1) {
     if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 1, 16, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
     return launch_tiles(gemv_t_kernel<T, 1, 16, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
@@ -1537,6 +1541,7 @@ static int resident_t(int adjoint, int shape, int adj_cw) {
     }
     return 0;
   }
+  if (adj_cw == 8 && shape == 1) return resident_ctas(gemv_t_kernel<T, 1, 8, POLICY>, kAdjSmemBytes);
   if (adj_cw == 16 && shape == 1) return resident_ctas(gemv_t_kernel<T, 1, 16, POLICY>, kAdjSmemBytes);
   if (adj_cw == 8 && shape == 2) return resident_ctas(gemv_t_kernel<T, 2, 8, POLICY>, kAdjSmemBytes);
   if (adj_cw == 4 && shape == 4) return resident_ctas(gemv_t_kernel<T, 4, 4, POLICY>, kAdjSmemBytes);

@@ -242,7 +242,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   int adj_ru = (int)op->p_adj_ru, adj_cw = kAdjCW;
   int64_t fwd_tx = op->p_fwd_tx;
   if (ctx->auto_tile) {
-    int64_t dense_bytes = 0, max_rows = 1;
+    int64_t dense_bytes = 0, max_rows = 1, max_cols = 1;
     double weighted_rows = 0.0, weighted_cols = 0.0;
     for (int64_t i = r0; i < r1; ++i)
       for (int64_t j = c0; j < c1; ++j) {
@@ -253,6 +253,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
         weighted_rows += (double)b * (double)op->row_len[i];
         weighted_cols += (double)b * (double)op->col_len[j];
         max_rows = std::max(max_rows, op->row_len[i]);
+        max_cols = std::max(max_cols, op->col_len[j]);
       }
     // ranks of this process that share the device run their cells side by side: size the tiles for the sum of them
     int share = 0;
@@ -273,7 +274,12 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     // tiles so that a tile is still >= 256 KB
     const int64_t typical_rows = dense_bytes > 0 ? (int64_t)(weighted_rows / (double)dense_bytes) : 1;
     const int64_t chunks = ceil_div(std::min<int64_t>(typical_rows, adj_max_rows(op->dtype)), 32 * vec_elems(op->dtype));
-    if (chunks <= 2) {
+    // blocks too small to make a 128 KB tile (100x100 Float64 ...): fewer loads per lane, three CTAs per SM instead of
+    // two (4.62 -> 4.99 TB/s on 90,000 blocks of 100x100 F64; no gain once tiles can be widened)
+    if (chunks <= 2 && ctx->adj_light && max_rows * max_cols * es < 128 * 1024) {
+      adj_ru = 1;
+      adj_cw = 8;
+    } else if (chunks <= 2) {
       adj_ru = 1;
       adj_cw = 16;
     } else if (chunks == 3) {
@@ -488,6 +494,7 @@ void xp_setup(djets_op op) {
     int present[2][3];
     int cell;  // index of the rank's cell in the grid, -1 when it is not part of this operator
     int ok;
+    char gpu[16];  // UUID of the rank's GPU: ranks that share a GPU must not wait on each other's flags
   };
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   Record mine;
@@ -514,10 +521,21 @@ void xp_setup(djets_op op) {
     }
   }
   mine.ok = ok;
+  {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, rc.device));
+    memcpy(mine.gpu, prop.uuid.bytes, 16);
+  }
   std::vector<Record> all((size_t)ctx->world);
   control_allgather(ctx, &mine, all.data(), sizeof(Record));
   for (int r = 0; r < ctx->world; ++r)
     if (all[(size_t)r].cell >= 0 && !all[(size_t)r].ok) ok = 0;
+  // Kernels of different ranks wait on one another's flags: that needs every rank on a GPU of its own (nothing
+  // guarantees that kernels of several processes on ONE GPU run at the same time; the time-sliced spin can trip
+  // the driver's context-switch watchdog).  Ranks sharing a GPU keep the stream-ordered paths.
+  for (int a = 0; a < ctx->world && ok; ++a)
+    for (int b = a + 1; b < ctx->world && ok; ++b)
+      if (all[(size_t)a].cell >= 0 && all[(size_t)b].cell >= 0 && memcmp(all[(size_t)a].gpu, all[(size_t)b].gpu, 16) == 0) ok = 0;
   for (int d = 0; d < 2; ++d) op->xpeer[d].assign((size_t)ncell, djets_op_s::PeerBuf());
   for (int r = 0; r < ctx->world && ok; ++r) {
     const Record& rec = all[(size_t)r];
@@ -554,7 +572,8 @@ void xp_setup(djets_op op) {
     if (all[(size_t)r].cell >= 0 && !oks[(size_t)r]) everyone = false;
   op->xp = everyone;
   REQUIRE(op->xp || ctx->has_nccl, DJETS_ERR_NCCL,
-          "the exchange buffers could not be mapped between the processes (CUDA IPC) and the context has no NCCL to fall back on");
+          "the peer-memory exchange is unavailable (ranks of different processes share a GPU, or CUDA IPC could not map the "
+          "buffers) and the context has no NCCL to fall back on");
 }
 
 void xp_release(djets_op op) {

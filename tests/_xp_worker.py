@@ -1,6 +1,5 @@
 """One process per rank WITHOUT NCCL: the control plane is a host all-gather (gloo), block data moves through
-CUDA-IPC-mapped peer buffers guarded by epoch flags (csrc/djets_op.cu: apply_enqueue_xp).  The processes may share
-one GPU, so this runs on a 1-GPU box.  Launched by tests/test_gpu_xp.py:
+CUDA-IPC-mapped peer buffers guarded by epoch flags (csrc/djets_op.cu: apply_enqueue_xp).  One GPU per rank.  Launched by tests/test_gpu_xp.py:
     RANK=r WORLD_SIZE=4 MASTER_ADDR=127.0.0.1 MASTER_PORT=p python tests/_xp_worker.py [ipc]
 """
 import os
@@ -43,7 +42,8 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     ngpu = torch.cuda.device_count()
     dist.init_process_group("gloo")
-    ctx = dj.Context.spmd(rank, world, rank % ngpu, nccl_uid=None, allgather=dj.torch_allgather())
+    assert ngpu >= world, "one GPU per rank"
+    ctx = dj.Context.spmd(rank, world, rank, nccl_uid=None, allgather=dj.torch_allgather())
     dj.set_default_context(ctx)
     for name in ("xp_push", "xp_side", "xp_kwait"):                # A/B of the exchange mechanisms (scripts, debugging)
         if os.environ.get("DJETS_" + name.upper()):

@@ -1,6 +1,7 @@
-"""One process per rank without NCCL: host all-gather for the control plane, CUDA-IPC peer memory and epoch flags for
-the data plane.  Four processes share GPU 0 when the box has one GPU, so the cross-process exchange of a grid operator
-(src/DistributedJets.jl:600-604, 647-651, 694-698 in the reference) is exercised on every GPU box."""
+"""One process per rank without NCCL: host all-gather (gloo) for the control plane, CUDA-IPC peer memory and epoch
+flags for the data plane -- the cross-process exchange of a grid operator (src/DistributedJets.jl:600-604, 647-651,
+694-698 in the reference).  Kernels of different ranks wait on one another's flags, so every rank needs a GPU of its
+own: the test needs >= 2 GPUs (the library itself refuses the peer-memory path when ranks share a GPU)."""
 import os
 import signal
 import socket
@@ -20,7 +21,11 @@ def free_port():
 
 @pytest.mark.gpu
 def test_multiprocess_exchange_over_peer_memory():
-    world, port = 4, free_port()
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs one GPU per rank (>= 2 GPUs): kernels of different ranks wait on each other's flags")
+    world, port = (4 if ngpu >= 4 else 2), free_port()
     procs = []
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
@@ -40,4 +45,4 @@ def test_multiprocess_exchange_over_peer_memory():
         raise AssertionError("xp worker hung")
     for rank, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {rank}:\n{out[-4000:]}"
-    assert "xp ok 4" in outs[0]
+    assert f"xp ok {world}" in outs[0]
