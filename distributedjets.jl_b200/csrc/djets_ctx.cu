@@ -243,6 +243,9 @@ int32_t djets_ctx_create(int32_t world, int32_t nlocal, const int32_t* local_ran
       CK(cudaStreamCreateWithFlags(&rc.stream, cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&rc.ev, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&rc.ev_fork, cudaEventDisableTiming));
+      CK(cudaStreamCreateWithFlags(&rc.cstream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&rc.ev_c0, cudaEventDisableTiming));
+      for (cudaEvent_t& e : rc.cmarks) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       CK(cudaStreamCreateWithFlags(&rc.xstream, cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&rc.ev_x0, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&rc.ev_x1, cudaEventDisableTiming));
@@ -328,6 +331,11 @@ int32_t djets_ctx_destroy(djets_ctx ctx) {
       cudaEventDestroy(rc.ev_fork);
       cudaStreamSynchronize(rc.xstream);
       cudaStreamDestroy(rc.xstream);
+      cudaStreamSynchronize(rc.cstream);
+      cudaStreamDestroy(rc.cstream);
+      cudaEventDestroy(rc.ev_c0);
+      for (cudaEvent_t e : rc.cmarks)
+        if (e) cudaEventDestroy(e);
       cudaEventDestroy(rc.ev_x0);
       cudaEventDestroy(rc.ev_x1);
       cudaEventDestroy(rc.t0);
@@ -354,6 +362,7 @@ int32_t djets_ctx_sync(djets_ctx ctx) {
     for (RankCtx& rc : ctx->ranks) {
       use(rc);
       CK(cudaStreamSynchronize(rc.stream));
+      CK(cudaStreamSynchronize(rc.cstream));
     }
     if ((int)ctx->ranks.size() < ctx->world)
       for (RankCtx& rc : ctx->ranks) {
@@ -457,7 +466,10 @@ int32_t djets_ctx_mark(djets_ctx ctx, int32_t slot) {
   return guard([&] {
     REQUIRE(ctx && slot >= 0 && slot < 8, DJETS_ERR_INVALID, "mark: slot in 0..7");
     REQUIRE(!ctx->capturing, DJETS_ERR_INVALID, "mark inside a captured sequence");
-    for (RankCtx& rc : ctx->ranks) CK(cudaEventRecord(rc.marks[slot], rc.stream));
+    for (RankCtx& rc : ctx->ranks) {
+      CK(cudaEventRecord(rc.marks[slot], rc.stream));
+      CK(cudaEventRecord(rc.cmarks[slot], rc.cstream));
+    }
   });
 }
 
@@ -465,7 +477,10 @@ int32_t djets_ctx_wait_mark(djets_ctx ctx, int32_t slot) {
   return guard([&] {
     REQUIRE(ctx && slot >= 0 && slot < 8, DJETS_ERR_INVALID, "wait_mark: slot in 0..7");
     no_sync_in_capture(ctx, "djets_ctx_wait_mark");
-    for (RankCtx& rc : ctx->ranks) CK(cudaEventSynchronize(rc.marks[slot]));
+    for (RankCtx& rc : ctx->ranks) {
+      CK(cudaEventSynchronize(rc.marks[slot]));
+      CK(cudaEventSynchronize(rc.cmarks[slot]));
+    }
   });
 }
 

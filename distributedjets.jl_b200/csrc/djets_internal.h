@@ -90,6 +90,9 @@ struct RankCtx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev = nullptr;  // scratch event for cross-stream ordering
   cudaEvent_t ev_fork = nullptr;  // fork / join of a captured apply
+  cudaStream_t cstream = nullptr;  // copy stream: scatter_async / collect_async overlap the kernels of the main stream
+  cudaEvent_t cmarks[8] = {};      // djets_ctx_mark on the copy stream
+  cudaEvent_t ev_c0 = nullptr;     // main -> copy stream ordering
   cudaStream_t xstream = nullptr;  // side stream: pushes of an input part to its consumers in other processes
   cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -217,6 +220,10 @@ struct VecPart {
   int64_t blk_first = 0, blk_count = 0, elem_first = 0, elem_count = 0;
   char* d = nullptr;  // device storage on the owner (nullptr when the owner is another process)
   size_t cap = 0;     // allocated bytes
+  // an asynchronous host copy of this part is (or may still be) running on the owner's copy stream: the next call that
+  // touches the vector makes the main stream wait for `pending` first
+  cudaEvent_t pending = nullptr;
+  bool has_pending = false;
 };
 
 struct djets_vec_s {
@@ -232,5 +239,15 @@ namespace djets {
 
 djets_vec make_vec(djets_ctx ctx, int dtype, int nparts, const int32_t* part_rank, const int64_t* part_nblocks,
                    const int64_t* block_len);
+// Orders the main streams after any asynchronous host copy still running on this vector's parts.  Called by every
+// entry point for each vector it touches (a host-side flag test unless a copy is pending).
+inline void settle(djets_vec v) {
+  if (!v) return;
+  for (VecPart& p : v->parts)
+    if (p.has_pending) {
+      if (RankCtx* rc = v->ctx->local(p.rank)) CK(cudaStreamWaitEvent(rc->stream, p.pending, 0));
+      p.has_pending = false;
+    }
+}
 
 }  // namespace djets

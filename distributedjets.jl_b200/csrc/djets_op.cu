@@ -1000,6 +1000,8 @@ void apply(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
   check_vec(op, out, !adjoint, adjoint ? "mul!(m, A', d): m" : "mul!(d, A, m): d");
   check_vec(op, in, adjoint, adjoint ? "mul!(m, A', d): d" : "mul!(d, A, m): m");
   REQUIRE(out != in, DJETS_ERR_INVALID, "mul!: output aliases input");
+  settle(out);
+  settle(in);
   REQUIRE(!(ctx->capturing && (!op->finalized || op->perfstat)), DJETS_ERR_INVALID,
           "mul! inside a captured sequence needs a finalised operator without perfstat");
   finalize_op(op);

@@ -101,11 +101,12 @@ namespace {
 void free_vec(djets_vec v) {
   if (!v) return;
   for (VecPart& p : v->parts) {
-    if (!p.d) continue;
-    if (RankCtx* rc = v->ctx->local(p.rank)) {
-      cudaSetDevice(rc->device);
-      part_free(*rc, p.d, p.cap);
-    }
+    RankCtx* rc = v->ctx->local(p.rank);
+    if (rc && p.has_pending) cudaStreamWaitEvent(rc->stream, p.pending, 0);  // the part is reused in main-stream order
+    if (p.pending) cudaEventDestroy(p.pending);
+    if (!p.d || !rc) continue;
+    cudaSetDevice(rc->device);
+    part_free(*rc, p.d, p.cap);
   }
   delete v;
 }
@@ -138,6 +139,8 @@ void check_extrema_parts(djets_vec x, int kind) {
 void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_parts, bool as_norm = false) {
   djets_ctx ctx = x->ctx;
   no_sync_in_capture(ctx, "a reduction returning its value to the host");
+  settle(x);
+  settle(y);
   if (!as_norm) check_extrema_parts(x, kind);
   const int np = (int)x->parts.size();
   // Every process of a multi-process job makes the same calls, so the decision to exchange must not
@@ -251,6 +254,8 @@ void reduce_to_scalar(djets_vec x, djets_vec y, int kind, double param, int fold
                       bool as_norm = false) {
   djets_ctx ctx = x->ctx;
   REQUIRE(out && out->ctx == ctx, DJETS_ERR_INVALID, "reduction into a scalar of another context");
+  settle(x);
+  settle(y);
   if (!as_norm) check_extrema_parts(x, kind);
   // partial of one part into `res` on its owner's stream: the reduction kernel, or norm(empty) = 0
   auto partial = [&](RankCtx& rc, int p, double* res) {
@@ -348,19 +353,29 @@ void reduce_to_scalar(djets_vec x, djets_vec y, int kind, double param, int fold
     if (&rc != root) stream_after(*root, rc);
 }
 
+// scatter_async / collect_async run on the owner's copy stream: they start once everything enqueued so far on the
+// main stream has finished (the vector's earlier readers and writers) and overlap whatever is enqueued afterwards
+// that does not touch this vector; the next call that does touch it waits for the copy (VecPart::pending).
 void bulk_copy_async(djets_vec x, void* host, bool to_device) {
   REQUIRE(x, DJETS_ERR_INVALID, "null vector");
   REQUIRE(host || x->length == 0, DJETS_ERR_INVALID, "null host pointer");
+  REQUIRE(!x->ctx->capturing, DJETS_ERR_INVALID, "host transfers cannot be part of a captured sequence");
+  settle(x);
   const int es = elem_size(x->dtype);
   for (VecPart& p : x->parts) {
     RankCtx* rc = x->ctx->local(p.rank);
     if (!rc || p.elem_count == 0) continue;
     use(*rc);
+    CK(cudaEventRecord(rc->ev_c0, rc->stream));
+    CK(cudaStreamWaitEvent(rc->cstream, rc->ev_c0, 0));
     char* h = reinterpret_cast<char*>(host) + (size_t)p.elem_first * es;
     if (to_device)
-      CK(cudaMemcpyAsync(p.d, h, (size_t)p.elem_count * es, cudaMemcpyHostToDevice, rc->stream));
+      CK(cudaMemcpyAsync(p.d, h, (size_t)p.elem_count * es, cudaMemcpyHostToDevice, rc->cstream));
     else
-      CK(cudaMemcpyAsync(h, p.d, (size_t)p.elem_count * es, cudaMemcpyDeviceToHost, rc->stream));
+      CK(cudaMemcpyAsync(h, p.d, (size_t)p.elem_count * es, cudaMemcpyDeviceToHost, rc->cstream));
+    if (!p.pending) CK(cudaEventCreateWithFlags(&p.pending, cudaEventDisableTiming));
+    CK(cudaEventRecord(p.pending, rc->cstream));
+    p.has_pending = true;
   }
 }
 
@@ -431,6 +446,7 @@ int32_t djets_vec_block_info(djets_vec x, int64_t iblock, int32_t* part, int64_t
 static void block_copy(djets_vec x, int64_t iblock, void* host, bool to_device) {
   REQUIRE(x && iblock >= 0 && iblock < (int64_t)x->block_len.size(), DJETS_ERR_INVALID, "block index out of range");
   no_sync_in_capture(x->ctx, "getblock / setblock!");
+  settle(x);
   VecPart& p = x->parts[x->block_part[iblock]];
   RankCtx* rc = x->ctx->local(p.rank);
   if (!rc) {
@@ -461,6 +477,7 @@ int32_t djets_vec_getindex(djets_vec x, int64_t i, double* out) {
   return guard([&] {
     REQUIRE(x && out, DJETS_ERR_INVALID, "null argument");
     REQUIRE(i >= 0 && i < x->length, DJETS_ERR_INVALID, "BoundsError: index outside the DBArray");
+    settle(x);
     for (VecPart& p : x->parts) {
       if (i < p.elem_first || i >= p.elem_first + p.elem_count) continue;  // findfirst(rng->i in rng) src:175
       RankCtx* rc = x->ctx->local(p.rank);
@@ -486,6 +503,7 @@ int32_t djets_vec_getindex(djets_vec x, int64_t i, double* out) {
 static void bulk_copy(djets_vec x, void* host, bool to_device) {
   REQUIRE(x, DJETS_ERR_INVALID, "null vector");
   no_sync_in_capture(x->ctx, "collect / scatter");
+  settle(x);
   REQUIRE(host || x->length == 0, DJETS_ERR_INVALID, "null host pointer");
   const int es = elem_size(x->dtype);
   for (VecPart& p : x->parts) {
@@ -515,6 +533,7 @@ int32_t djets_vec_scatter(djets_vec x, const void* host_src) {
 int32_t djets_vec_fill(djets_vec x, double a) {
   return guard([&] {
     REQUIRE(x, DJETS_ERR_INVALID, "null vector");
+    settle(x);
     for (VecPart& p : x->parts) {
       RankCtx* rc = x->ctx->local(p.rank);
       if (!rc) continue;
@@ -533,7 +552,9 @@ int32_t djets_vec_lincomb(djets_vec dest, int32_t nterms, const double* coef, co
       REQUIRE(xs[k], DJETS_ERR_INVALID, "lincomb: null operand");
       REQUIRE(same_layout(dest, xs[k]), DJETS_ERR_MISMATCH,
               "DimensionMismatch: broadcast operands have different block layouts");
+      settle(xs[k]);
     }
+    settle(dest);
     for (size_t p = 0; p < dest->parts.size(); ++p) {
       VecPart& dp = dest->parts[p];
       RankCtx* rc = dest->ctx->local(dp.rank);
@@ -560,6 +581,9 @@ int32_t djets_vec_binary(djets_vec dest, int32_t op, djets_vec a, djets_vec b) {
             "DimensionMismatch: broadcast operands have different block layouts");
     REQUIRE(dest->dtype == a->dtype && dest->dtype == b->dtype, DJETS_ERR_UNSUPPORTED,
             "binary: operands must share the element type");
+    settle(dest);
+    settle(a);
+    settle(b);
     for (size_t p = 0; p < dest->parts.size(); ++p) {
       VecPart& dp = dest->parts[p];
       RankCtx* rc = dest->ctx->local(dp.rank);
@@ -686,7 +710,9 @@ int32_t djets_vec_eval(djets_vec dest, const uint8_t* program, int32_t nops, con
       REQUIRE(inputs[k], DJETS_ERR_INVALID, "eval: null operand");
       REQUIRE(same_layout(dest, inputs[k]), DJETS_ERR_MISMATCH,
               "DimensionMismatch: broadcast operands have different block layouts");
+      settle(inputs[k]);
     }
+    settle(dest);
     EvalArgs a;
     memset(&a, 0, sizeof(a));
     a.nops = nops;

@@ -208,9 +208,10 @@ int32_t djets_vec_collect(djets_vec x, void* host_dst);
 /* inverse of collect: every locally driven part is loaded from its slice of host_src (one H2D
  * per rank; the block-by-block form is setblock!, docs:211-227). */
 int32_t djets_vec_scatter(djets_vec x, const void* host_src);
-/* Stream-ordered forms of scatter / collect: they return at once; host_src must stay unmodified / host_dst is
- * valid only after the next synchronising call (djets_ctx_sync, djets_ctx_wait_mark of a later mark, ...).  Meant for
- * page-locked buffers (djets_host_alloc). */
+/* Asynchronous forms of scatter / collect for page-locked buffers (djets_host_alloc): they return at once and run
+ * on the owner's copy stream -- after everything enqueued so far, overlapping whatever is enqueued afterwards that
+ * does not touch x; the next call that touches x waits for the copy.  host_src must stay unmodified / host_dst is
+ * valid only after a later synchronising call (djets_ctx_sync, djets_ctx_wait_mark of a mark made after the copy). */
 int32_t djets_vec_scatter_async(djets_vec x, const void* host_src);
 int32_t djets_vec_collect_async(djets_vec x, void* host_dst);
 /* fill!(x, a) (src:332-339; also `x .= a`, test:329). */
