@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdjets_b200.so")
 
-F32, F64 = 0, 1
+F32, F64, C64, C128 = 0, 1, 2, 3
 BLOCK_ZERO, BLOCK_DENSE, BLOCK_DIAG = 0, 1, 2
 OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_MISMATCH, ERR_UNSUPPORTED, ERR_NOT_LOCAL = range(7)
 (RED_SUM, RED_MIN, RED_MAX, RED_ABSSUM, RED_ABSMAX, RED_ABSMIN, RED_SUMSQ, RED_NNZ, RED_SUMPOW,
@@ -90,6 +90,9 @@ SIGNATURES = {
     "djets_vec_setblock": [vp, i64, vp],
     "djets_vec_getblock": [vp, i64, vp],
     "djets_vec_getindex": [vp, i64, p_f64],
+    "djets_vec_getindex_c": [vp, i64, p_f64],
+    "djets_vec_fill_c": [vp, f64, f64],
+    "djets_vec_dot_c": [vp, vp, p_f64],
     "djets_vec_collect": [vp, vp],
     "djets_vec_scatter": [vp, vp],
     "djets_vec_fill": [vp, f64],

@@ -22,14 +22,15 @@ from . import _lib
 from ._lib import DimensionMismatch, DJetsError
 from .partition import cuts_from_ranges, default_grid, even_cuts, even_ranges, grid_of, urange
 
-_DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64}
+_DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64, np.dtype(np.complex64): _lib.C64,
+       np.dtype(np.complex128): _lib.C128}
 
 
 def _dt(dtype) -> int:
     try:
         return _DT[np.dtype(dtype)]
     except KeyError:
-        raise DJetsError(_lib.ERR_UNSUPPORTED, f"element type {dtype} (Float32 and Float64 only)") from None
+        raise DJetsError(_lib.ERR_UNSUPPORTED, f"element type {dtype} (Float32, Float64 and their Complex types only)") from None
 
 
 # ======================================================================================================
@@ -388,7 +389,12 @@ class JetDSpace:
         o = 0
         for shape in self.block_shapes():                # block by block: drawn on every process, identical streams
             n = _size(shape)
-            flat[o:o + n] = rng.random(shape, dtype=self.dtype).reshape(-1, order="F")
+            if self.dtype.kind == "c":                   # Julia's rand(Complex{T}): both parts U[0,1)
+                rt = np.zeros(0, self.dtype).real.dtype
+                blk = rng.random(shape, dtype=rt) + 1j * rng.random(shape, dtype=rt)
+            else:
+                blk = rng.random(shape, dtype=self.dtype)
+            flat[o:o + n] = blk.reshape(-1, order="F")
             o += n
         return x.scatter(flat)                           # one DMA per rank
 
@@ -498,6 +504,10 @@ class DBArray:
             return np.array([self[k] for k in i], dtype=self.dtype)
         if not 1 <= int(i) <= len(self):
             raise IndexError(f"BoundsError: attempt to access {len(self)}-element DBArray at index [{i}]")
+        if self.dtype.kind == "c":
+            z = (C.c_double * 2)()
+            _lib.call("djets_vec_getindex_c", self.h, int(i) - 1, z)
+            return self.dtype.type(complex(z[0], z[1]))
         out = C.c_double()
         _lib.call("djets_vec_getindex", self.h, int(i) - 1, C.byref(out))
         return self.dtype.type(out.value)
@@ -617,7 +627,10 @@ class DBArray:
 
     # fill! and broadcasting (src:332-376) ---------------------------------------------------------------------
     def fill(self, a) -> "DBArray":
-        _lib.call("djets_vec_fill", self.h, float(a))
+        if isinstance(a, (complex, np.complexfloating)):
+            _lib.call("djets_vec_fill_c", self.h, float(a.real), float(a.imag))
+        else:
+            _lib.call("djets_vec_fill", self.h, float(a))
         return self
 
     def lincomb_(self, coefs: Sequence[float], xs: Sequence["DBArray"], wide: Optional[bool] = None) -> "DBArray":
@@ -625,7 +638,10 @@ class DBArray:
         semantics when the scalars are Float64 and the arrays Float32); default: only if any operand is
         Float64."""
         if wide is None:
-            wide = any(x.dtype == np.float64 for x in xs)
+            wide = any(x.dtype in (np.float64, np.complex128) for x in xs)
+        if any(isinstance(c, (complex, np.complexfloating)) and c.imag != 0 for c in coefs):
+            raise DJetsError(_lib.ERR_UNSUPPORTED, "complex coefficients in a broadcast are outside the closed set")
+        coefs = [c.real if isinstance(c, (complex, np.complexfloating)) else c for c in coefs]
         arr = (C.c_void_p * len(xs))(*[x.h for x in xs])
         _lib.call("djets_vec_lincomb", self.h, len(xs), (C.c_double * len(xs))(*[float(c) for c in coefs]), arr,
                   1 if wide else 0)
@@ -725,9 +741,14 @@ class DBArray:
     def norm(self, p: float = 2):
         out = C.c_double()
         _lib.call("djets_vec_norm", self.h, float(p), C.byref(out))
-        return self.dtype.type(out.value)                 # float(real(T)) == T for the supported types
+        return np.zeros(0, self.dtype).real.dtype.type(out.value)      # float(real(T))
 
     def dot(self, other: "DBArray"):
+        """``dot(x, y)`` (conjugates ``x`` for complex element types, like Julia's)."""
+        if self.dtype.kind == "c":
+            z = (C.c_double * 2)()
+            _lib.call("djets_vec_dot_c", self.h, other.h, z)
+            return self.dtype.type(complex(z[0], z[1]))
         out = C.c_double()
         _lib.call("djets_vec_dot", self.h, other.h, C.byref(out))
         return self.dtype.type(out.value)

@@ -89,6 +89,28 @@ __device__ __forceinline__ void dot_vec(double& acc, const double2& a, const dou
   acc = fma(a.x, y.x, acc);
   acc = fma(a.y, y.y, acc);
 }
+// complex (interleaved re, im): acc += a * x for the complex rows a thread owns, x = (xr, xi)
+__device__ __forceinline__ void cfma_vec(float (&acc)[4], const float4& a, float xr, float xi) {
+  acc[0] = fmaf(-a.y, xi, fmaf(a.x, xr, acc[0]));
+  acc[1] = fmaf(a.x, xi, fmaf(a.y, xr, acc[1]));
+  acc[2] = fmaf(-a.w, xi, fmaf(a.z, xr, acc[2]));
+  acc[3] = fmaf(a.z, xi, fmaf(a.w, xr, acc[3]));
+}
+__device__ __forceinline__ void cfma_vec(double (&acc)[2], const double2& a, double xr, double xi) {
+  acc[0] = fma(-a.y, xi, fma(a.x, xr, acc[0]));
+  acc[1] = fma(a.x, xi, fma(a.y, xr, acc[1]));
+}
+// (re, im) += conj(a) * y over the complex rows of one 128-bit load
+__device__ __forceinline__ void cdot_vec(float& re, float& im, const float4& a, const float4& y) {
+  re = fmaf(a.y, y.y, fmaf(a.x, y.x, re));
+  im = fmaf(-a.y, y.x, fmaf(a.x, y.y, im));
+  re = fmaf(a.w, y.w, fmaf(a.z, y.z, re));
+  im = fmaf(-a.w, y.z, fmaf(a.z, y.w, im));
+}
+__device__ __forceinline__ void cdot_vec(double& re, double& im, const double2& a, const double2& y) {
+  re = fma(a.y, y.y, fma(a.x, y.x, re));
+  im = fma(-a.y, y.x, fma(a.x, y.y, im));
+}
 
 // ------------------------------------------------------------------------------------------------
 // Staging a contiguous slice of a vector into shared memory.  When source and length are 16-byte
@@ -249,6 +271,13 @@ __device__ __forceinline__ void stage_vector(T* __restrict__ dst, const T* __res
 // double for Float32 vectors.  COHERENT: the planes were written by other CTAs of this launch, so
 // they are read with ld.global.cg (L2), never from this SM's L1.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rn_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double rn_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float rn_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double rn_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float rn_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double rn_sub(double a, double b) { return __dsub_rn(a, b); }
+
 template <typename T, bool COHERENT>
 __device__ __forceinline__ T ld_plane(const T* p) {
   return COHERENT ? __ldcg(p) : *p;
@@ -305,6 +334,33 @@ template <typename T, bool COHERENT>
 __device__ __forceinline__ void finish_item(const FinishItem& it, const DiagTerm* __restrict__ diags,
                                             const T* __restrict__ in, const T* W, const T* __restrict__ R,
                                             T* __restrict__ out) {
+  if (it.flags & 1) {  // complex: elements are (re, im) pairs of T; planes add component-wise, diagonal terms multiply as complex
+    const bool conj = (it.flags & 2) != 0;
+    for (int e = 2 * threadIdx.x; e < it.len; e += 2 * kThreads) {
+      double sr = 0.0, si = 0.0;
+      const T* w = W + it.w0 + e;
+      for (int p = 0; p < it.nplanes; ++p) {
+        sr += (double)ld_plane<T, COHERENT>(w);
+        si += (double)ld_plane<T, COHERENT>(w + 1);
+        w += it.wstride;
+      }
+      for (int q = 0; q < it.nremote; ++q) {
+        sr += (double)R[it.r0 + q * it.rstride + e];
+        si += (double)R[it.r0 + q * it.rstride + e + 1];
+      }
+      for (int d = it.diag_begin; d < it.diag_end; ++d) {
+        const T* dd = reinterpret_cast<const T*>(diags[d].d);
+        const T dr = dd[e], di = conj ? -dd[e + 1] : dd[e + 1];
+        const T xr = in[diags[d].vin + e], xi = in[diags[d].vin + e + 1];
+        // complex product with separately rounded products and sum, like Julia's and NumPy's (no FMA contraction)
+        sr += (double)rn_sub(rn_mul(dr, xr), rn_mul(di, xi));
+        si += (double)rn_add(rn_mul(dr, xi), rn_mul(di, xr));
+      }
+      out[it.out + e] = (T)sr;
+      out[it.out + e + 1] = (T)si;
+    }
+    return;
+  }
   if (it.nplanes == 0 && it.nremote == 0 && it.diag_end > it.diag_begin && finish_item_diag_vec<T>(it, diags, in, out))
     return;
   for (int e = threadIdx.x; e < it.len; e += kThreads) {
@@ -360,7 +416,7 @@ __device__ __forceinline__ void fused_finish(int fin, const FusedFinish& ff, con
 // along the rows and TY = 256/TX column groups deep; the TY partial strips are summed in shared
 // memory in a fixed order.  U independent 128-bit loads are in flight per thread.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int TX, int POLICY>
+template <typename T, int TX, int POLICY, bool CPLX = false>
 __global__ void __launch_bounds__(kThreads, 4) gemv_n_tile_kernel(const DenseTile* __restrict__ tiles,
                                                           const T* __restrict__ in, T* W, T* __restrict__ out,
                                                           FusedFinish ff, Prefetch pf) {
@@ -409,13 +465,18 @@ __global__ void __launch_bounds__(kThreads, 4) gemv_n_tile_kernel(const DenseTil
   griddep_wait();
   wait_epoch_flags(pf);
   trace_stamp(pf.trace, blockIdx.x, 1);
-  stage_vector<T>(xs, in + t.vin, cols, cols, &bar);
+  stage_vector<T>(xs, in + t.vin, CPLX ? 2 * cols : cols, CPLX ? 2 * cols : cols, &bar);
   trace_stamp(pf.trace, blockIdx.x, 2);
 
   if (r0 < rows) {
     if (pre) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) fma_vec(acc, v0[u], xs[c + u * TY]);
+      for (int u = 0; u < U; ++u) {
+        if (CPLX)
+          cfma_vec(acc, v0[u], xs[2 * (c + u * TY)], xs[2 * (c + u * TY) + 1]);
+        else
+          fma_vec(acc, v0[u], xs[c + u * TY]);
+      }
       a += U * cstep;
       c += U * TY;
     }
@@ -424,12 +485,20 @@ __global__ void __launch_bounds__(kThreads, 4) gemv_n_tile_kernel(const DenseTil
 #pragma unroll
       for (int u = 0; u < U; ++u) v[u] = ld_stream<POLICY>(reinterpret_cast<const V*>(a + u * cstep), pol);
 #pragma unroll
-      for (int u = 0; u < U; ++u) fma_vec(acc, v[u], xs[c + u * TY]);
+      for (int u = 0; u < U; ++u) {
+        if (CPLX)
+          cfma_vec(acc, v[u], xs[2 * (c + u * TY)], xs[2 * (c + u * TY) + 1]);
+        else
+          fma_vec(acc, v[u], xs[c + u * TY]);
+      }
       a += U * cstep;
     }
     for (; c < cols; c += TY) {
       V v = ld_stream<POLICY>(reinterpret_cast<const V*>(a), pol);
-      fma_vec(acc, v, xs[c]);
+      if (CPLX)
+        cfma_vec(acc, v, xs[2 * c], xs[2 * c + 1]);
+      else
+        fma_vec(acc, v, xs[c]);
       a += cstep;
     }
   }
@@ -765,6 +834,108 @@ __global__ void __launch_bounds__(kThreads, 4) gemv_n_kernel(const DenseTile* __
 // staged once per tile in shared memory (double-buffered across tiles) and each 128-bit LDS of y is
 // reused for the CW columns; the per-lane sums are combined with a column-halving shuffle butterfly.
 // ------------------------------------------------------------------------------------------------
+// Complex adjoint tiles: partial[c] = sum_r conj(A[r,c]) y[r] on interleaved (re, im) data.  Tile extents: `rows` and
+// `ld` count reals (two per complex row), `cols` counts complex columns, outputs are 2*cols reals.  A warp owns CWC
+// complex columns at a time (2*CWC accumulators), RU row chunks unrolled; same staging and butterfly as the real kernel.
+template <typename T, int RU, int CWC, int POLICY>
+__global__ void __launch_bounds__(kThreads, 2) gemv_tc_tile_kernel(const DenseTile* __restrict__ tiles,
+                                                                   const T* __restrict__ in, T* W, T* __restrict__ out,
+                                                                   FusedFinish ff, Prefetch pf) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  constexpr int S = 32 * VEC;
+  constexpr int CW = 2 * CWC;  // real outputs per warp pass
+  __shared__ __align__(128) T ys[kAdjMaxTRBytes / sizeof(T)];
+  __shared__ __align__(8) uint64_t bar;
+
+  griddep_launch_dependents();
+  const DenseTile t = tiles[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rows = t.rows, cols = t.cols;
+  const int rowsv = (rows + VEC - 1) / VEC * VEC;
+  griddep_wait();
+  wait_epoch_flags(pf);
+  stage_vector<T>(ys, in + t.vin, rows, rowsv, &bar);
+
+  uint64_t pol = 0;
+  if (POLICY == 1) pol = make_evict_first_policy();
+
+  const long long ld = t.ld;
+  const T* A = reinterpret_cast<const T*>(t.A);
+  T* dst = (t.direct ? out : W) + t.wout;
+  const int ngroups = (cols + CWC - 1) / CWC;
+
+  for (int g = warp; g < ngroups; g += kThreads / 32) {
+    const int c0 = g * CWC;
+    const int last = cols - 1 - c0;
+    const T* base = A + (long long)c0 * ld + lane * VEC;
+    T acc[CW];
+#pragma unroll
+    for (int k = 0; k < CW; ++k) acc[k] = T(0);
+
+    int rb = 0;
+    for (; rb + RU * S <= rowsv; rb += RU * S) {
+      V a[RU][CWC];
+#pragma unroll
+      for (int u = 0; u < RU; ++u)
+#pragma unroll
+        for (int k = 0; k < CWC; ++k)
+          a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
+#pragma unroll
+        for (int k = 0; k < CWC; ++k) cdot_vec(acc[2 * k], acc[2 * k + 1], a[u][k], y);
+      }
+    }
+    if (rb < rowsv) {  // one guarded batch for the remainder
+      V a[RU][CWC];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const bool ok = rb + u * S + lane * VEC < rowsv;
+#pragma unroll
+        for (int k = 0; k < CWC; ++k) {
+          if (ok)
+            a[u][k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld + rb + u * S), pol);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        if (rb + u * S + lane * VEC < rowsv) {
+          const V y = *reinterpret_cast<const V*>(ys + rb + u * S + lane * VEC);
+#pragma unroll
+          for (int k = 0; k < CWC; ++k) cdot_vec(acc[2 * k], acc[2 * k + 1], a[u][k], y);
+        }
+      }
+    }
+    int width = CW;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      if (width > 1) {
+        width >>= 1;
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < CW / 2; ++k) {
+          if (k < width) {
+            const T send = upper ? acc[k] : acc[k + width];
+            const T keep = upper ? acc[k + width] : acc[k];
+            acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+      } else {
+        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+      }
+    }
+    constexpr int kHalvings = (CW == 16) ? 4 : (CW == 8) ? 3 : (CW == 4) ? 2 : (CW == 2) ? 1 : 0;
+    int mycol = 0;
+#pragma unroll
+    for (int h = 0; h < kHalvings; ++h) mycol |= ((lane >> (4 - h)) & 1) << (kHalvings - 1 - h);
+    const bool writer = (lane & ((32 >> kHalvings) - 1)) == 0;
+    if (writer && 2 * c0 + mycol < 2 * cols) dst[2 * c0 + mycol] = acc[0];
+  }
+  if (t.fin >= 0) fused_finish<T>(t.fin, ff, in, W, out);
+}
+
 template <typename T, int RU, int CW, int POLICY>
 __global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __restrict__ tiles, TileQueue q,
                                                              const T* __restrict__ in, T* W, T* __restrict__ out,
@@ -969,7 +1140,17 @@ __global__ void __launch_bounds__(kThreads) finish_kernel(const FinishItem* __re
 // Reductions (dot, norms, extrema, sums) in one launch: one partial per CTA, folded by the last CTA to
 // arrive.  Grid shape depends only on n, the combine order is fixed -> deterministic.
 // ------------------------------------------------------------------------------------------------
-enum { K_SUM = 0, K_MIN, K_MAX, K_ABSSUM, K_ABSMAX, K_ABSMIN, K_SUMSQ, K_NNZ, K_SUMPOW, K_SUMSQ_SHIFT, K_DOT };
+enum { K_SUM = 0, K_MIN, K_MAX, K_ABSSUM, K_ABSMAX, K_ABSMIN, K_SUMSQ, K_NNZ, K_SUMPOW, K_SUMSQ_SHIFT, K_DOT,
+       // complex data (interleaved re, im; n counts reals): |z|-based maps and Im(sum conj(x) y)
+       K_CABSSUM, K_CABSMAX, K_CABSMIN, K_CNNZ, K_CSUMPOW, K_CDOT_IM };
+template <int KIND>
+struct KindInfo {
+  static constexpr bool pairs = KIND >= K_CABSSUM;
+  static constexpr bool two = KIND == K_DOT || KIND == K_CDOT_IM;
+  // the kind whose identity / combine / map applies to |z|
+  static constexpr int base = KIND == K_CABSSUM ? K_ABSSUM : KIND == K_CABSMAX ? K_ABSMAX : KIND == K_CABSMIN ? K_ABSMIN
+                              : KIND == K_CNNZ ? K_NNZ : KIND == K_CSUMPOW ? K_SUMPOW : KIND == K_CDOT_IM ? K_SUM : KIND;
+};
 
 template <int KIND>
 __device__ __forceinline__ double red_identity() {
@@ -1003,6 +1184,25 @@ __device__ __forceinline__ double red_map(double x, double y, double param) {
   return 0.0;
 }
 
+// one 128-bit vector (or a scalar tail) worth of elements into the running value
+template <int KIND, int N, typename T>
+__device__ __forceinline__ double red_accumulate(double acc, const T* ae, const T* be, double param) {
+  constexpr int B = KindInfo<KIND>::base;
+  if (KindInfo<KIND>::pairs) {
+#pragma unroll
+    for (int k = 0; k + 1 < N; k += 2) {
+      const double v = KIND == K_CDOT_IM ? (double)ae[k] * (double)be[k + 1] - (double)ae[k + 1] * (double)be[k]
+                                         : red_map<B>(hypot((double)ae[k], (double)ae[k + 1]), 0.0, param);
+      acc = red_combine<B>(acc, KIND == K_CDOT_IM ? v : v);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      acc = red_combine<B>(acc, red_map<B>((double)ae[k], KindInfo<KIND>::two ? (double)be[k] : 0.0, param));
+  }
+  return acc;
+}
+
 template <int KIND>
 __device__ __forceinline__ double block_fold(double v) {
   __shared__ double sh[kThreads / 32];
@@ -1026,10 +1226,12 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const T* __restrict__ 
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   constexpr int U = 4;
+  constexpr int B = KindInfo<KIND>::base;
+  constexpr bool TWO = KindInfo<KIND>::two;
   const long long nvec = n / VEC;
   const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
   const long long gstride = (long long)gridDim.x * kThreads;
-  double acc = red_identity<KIND>();
+  double acc = red_identity<B>();
   const V* xv = reinterpret_cast<const V*>(x);
   const V* yv = reinterpret_cast<const V*>(y);
   long long i = gtid;
@@ -1038,29 +1240,21 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const T* __restrict__ 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       a[u] = ld_stream<0>(xv + i + u * gstride, 0);
-      if (KIND == K_DOT) b[u] = ld_stream<0>(yv + i + u * gstride, 0);
+      if (TWO) b[u] = ld_stream<0>(yv + i + u * gstride, 0);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const T* ae = reinterpret_cast<const T*>(&a[u]);
-      const T* be = reinterpret_cast<const T*>(&b[u]);
-#pragma unroll
-      for (int k = 0; k < VEC; ++k)
-        acc = red_combine<KIND>(acc, red_map<KIND>((double)ae[k], KIND == K_DOT ? (double)be[k] : 0.0, param));
-    }
+    for (int u = 0; u < U; ++u)
+      acc = red_accumulate<KIND, VEC>(acc, reinterpret_cast<const T*>(&a[u]), reinterpret_cast<const T*>(&b[u]), param);
   }
   for (; i < nvec; i += gstride) {
     V a = ld_stream<0>(xv + i, 0), b;
-    if (KIND == K_DOT) b = ld_stream<0>(yv + i, 0);
-    const T* ae = reinterpret_cast<const T*>(&a);
-    const T* be = reinterpret_cast<const T*>(&b);
-#pragma unroll
-    for (int k = 0; k < VEC; ++k)
-      acc = red_combine<KIND>(acc, red_map<KIND>((double)ae[k], KIND == K_DOT ? (double)be[k] : 0.0, param));
+    if (TWO) b = ld_stream<0>(yv + i, 0);
+    acc = red_accumulate<KIND, VEC>(acc, reinterpret_cast<const T*>(&a), reinterpret_cast<const T*>(&b), param);
   }
-  for (long long j = nvec * VEC + gtid; j < n; j += gstride)
-    acc = red_combine<KIND>(acc, red_map<KIND>((double)x[j], KIND == K_DOT ? (double)y[j] : 0.0, param));
-  const double r = block_fold<KIND>(acc);
+  constexpr int STEP = KindInfo<KIND>::pairs ? 2 : 1;  // the tail keeps (re, im) pairs together
+  for (long long j = nvec * VEC + STEP * gtid; j + STEP <= n; j += STEP * gstride)
+    acc = red_accumulate<KIND, STEP>(acc, x + j, TWO ? y + j : x + j, param);
+  const double r = block_fold<B>(acc);
   if (gridDim.x == 1) {
     if (threadIdx.x == 0) result[0] = r;
     return;
@@ -1076,9 +1270,9 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const T* __restrict__ 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  double fold = red_identity<KIND>();
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) fold = red_combine<KIND>(fold, __ldcg(partials + i));
-  const double total = block_fold<KIND>(fold);
+  double fold = red_identity<B>();
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) fold = red_combine<B>(fold, __ldcg(partials + i));
+  const double total = block_fold<B>(fold);
   if (threadIdx.x == 0) {
     result[0] = total;
     *ticket = 0u;
@@ -1113,6 +1307,12 @@ static cudaError_t launch_reduce_t(int kind, const void* x, const void* y, long 
     case 8: return launch_reduce_k<T, K_SUMPOW>(x, y, n, param, partials, ticket, result, stream);
     case 9: return launch_reduce_k<T, K_SUMSQ_SHIFT>(x, y, n, param, partials, ticket, result, stream);
     case RED_DOT: return launch_reduce_k<T, K_DOT>(x, y, n, param, partials, ticket, result, stream);
+    case RED_CABSSUM: return launch_reduce_k<T, K_CABSSUM>(x, y, n, param, partials, ticket, result, stream);
+    case RED_CABSMAX: return launch_reduce_k<T, K_CABSMAX>(x, y, n, param, partials, ticket, result, stream);
+    case RED_CABSMIN: return launch_reduce_k<T, K_CABSMIN>(x, y, n, param, partials, ticket, result, stream);
+    case RED_CNNZ: return launch_reduce_k<T, K_CNNZ>(x, y, n, param, partials, ticket, result, stream);
+    case RED_CSUMPOW: return launch_reduce_k<T, K_CSUMPOW>(x, y, n, param, partials, ticket, result, stream);
+    case RED_CDOT_IM: return launch_reduce_k<T, K_CDOT_IM>(x, y, n, param, partials, ticket, result, stream);
   }
   return cudaErrorInvalidValue;
 }
@@ -1291,6 +1491,30 @@ __global__ void __launch_bounds__(kThreads) binary_kernel(T* dest /* may alias a
   for (long long j = nvec * VEC + gtid; j < n; j += stride) dest[j] = OP == 0 ? mul_rn(a[j], b[j]) : a[j] / b[j];
 }
 
+template <typename T>
+__global__ void __launch_bounds__(kThreads) fill_complex_kernel(T* __restrict__ dest, T re, T im, long long n /* reals */) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  const long long nvec = n / VEC;
+  const long long stride = (long long)gridDim.x * kThreads;
+  const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+  V v;
+  T* ve = reinterpret_cast<T*>(&v);
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) ve[e] = (e & 1) ? im : re;
+  for (long long i = gtid; i < nvec; i += stride) reinterpret_cast<V*>(dest)[i] = v;
+  for (long long j = nvec * VEC + gtid; j < n; j += stride) dest[j] = (j & 1) ? im : re;
+}
+
+cudaError_t launch_fill_complex(int dtype, void* dest, double re, double im, long long n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (real_dtype(dtype) == 0)
+    fill_complex_kernel<float><<<stream_grid(n / 2), kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), (float)re, (float)im, 2 * n);
+  else
+    fill_complex_kernel<double><<<stream_grid(n), kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), re, im, 2 * n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_binary(int dtype, int op, void* dest, const void* a, const void* b, long long n,
                           cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
@@ -1369,10 +1593,31 @@ static cudaError_t launch_gemv_n_t(int fwd_tx, const DenseTile* tiles, int ntile
   return cudaGetLastError();
 }
 
+template <typename T, int POLICY>
+static cudaError_t launch_gemv_nc_t(int fwd_tx, const DenseTile* tiles, int ntiles, const void* in, void* W, void* out,
+                                    FusedFinish ff, Prefetch pf, cudaStream_t stream) {
+  const T* i = reinterpret_cast<const T*>(in);
+  T* w = reinterpret_cast<T*>(W);
+  T* o = reinterpret_cast<T*>(out);
+  switch (fwd_tx) {
+    case 64: return launch_tiles(gemv_n_tile_kernel<T, 64, POLICY, true>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    case 128: return launch_tiles(gemv_n_tile_kernel<T, 128, POLICY, true>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    case 256: return launch_tiles(gemv_n_tile_kernel<T, 256, POLICY, true>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, int ntiles, int grid,
                           unsigned* counter, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
                           cudaStream_t stream) {
   if (ntiles <= 0) return cudaSuccess;
+  if (is_complex(dtype)) {  // complex: one tile per CTA (the queue-driven variants are real only)
+    if (real_dtype(dtype) == 0)
+      return ld_policy ? launch_gemv_nc_t<float, 1>(fwd_tx, tiles, ntiles, in, W, out, ff, pf, stream)
+                       : launch_gemv_nc_t<float, 0>(fwd_tx, tiles, ntiles, in, W, out, ff, pf, stream);
+    return ld_policy ? launch_gemv_nc_t<double, 1>(fwd_tx, tiles, ntiles, in, W, out, ff, pf, stream)
+                     : launch_gemv_nc_t<double, 0>(fwd_tx, tiles, ntiles, in, W, out, ff, pf, stream);
+  }
   if (dtype == 0)
     return ld_policy ? launch_gemv_n_t<float, 1>(fwd_tx, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream)
                      : launch_gemv_n_t<float, 0>(fwd_tx, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream);
@@ -1416,10 +1661,27 @@ static cudaError_t launch_gemv_t_t(int adj_ru, int adj_cw, const DenseTile* tile
   return cudaErrorInvalidValue;
 }
 
+template <typename T, int POLICY>
+static cudaError_t launch_gemv_tc_t(int adj_ru, const DenseTile* tiles, int ntiles, const void* in, void* W, void* out,
+                                    FusedFinish ff, Prefetch pf, cudaStream_t stream) {
+  const T* i = reinterpret_cast<const T*>(in);
+  T* w = reinterpret_cast<T*>(W);
+  T* o = reinterpret_cast<T*>(out);
+  if (adj_ru == 1) return launch_tiles(gemv_tc_tile_kernel<T, 1, 8, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+  return launch_tiles(gemv_tc_tile_kernel<T, 4, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+}
+
 cudaError_t launch_gemv_t(int dtype, int adj_ru, int adj_cw, int ld_policy, const DenseTile* tiles, int ntiles,
                           int grid, unsigned* counter, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
                           cudaStream_t stream) {
   if (ntiles <= 0) return cudaSuccess;
+  if (is_complex(dtype)) {
+    if (real_dtype(dtype) == 0)
+      return ld_policy ? launch_gemv_tc_t<float, 1>(adj_ru, tiles, ntiles, in, W, out, ff, pf, stream)
+                       : launch_gemv_tc_t<float, 0>(adj_ru, tiles, ntiles, in, W, out, ff, pf, stream);
+    return ld_policy ? launch_gemv_tc_t<double, 1>(adj_ru, tiles, ntiles, in, W, out, ff, pf, stream)
+                     : launch_gemv_tc_t<double, 0>(adj_ru, tiles, ntiles, in, W, out, ff, pf, stream);
+  }
   if (dtype == 0)
     return ld_policy ? launch_gemv_t_t<float, 1>(adj_ru, adj_cw, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream)
                      : launch_gemv_t_t<float, 0>(adj_ru, adj_cw, tiles, ntiles, grid, counter, in, W, out, ff, pf, stream);
@@ -1551,6 +1813,13 @@ static int resident_t(int adjoint, int shape, int adj_cw) {
 }
 
 int gemv_resident_ctas(int dtype, int adjoint, int shape, int adj_cw, int ld_policy) {
+  if (is_complex(dtype)) {
+    dtype = real_dtype(dtype);
+    if (adjoint) {  // the complex adjoint has its own two shapes; the estimate only sizes the prefetch wave
+      shape = 4;
+      adj_cw = 4;
+    }
+  }
   if (dtype == 0) return ld_policy ? resident_t<float, 1>(adjoint, shape, adj_cw) : resident_t<float, 0>(adjoint, shape, adj_cw);
   return ld_policy ? resident_t<double, 1>(adjoint, shape, adj_cw) : resident_t<double, 0>(adjoint, shape, adj_cw);
 }
@@ -1558,7 +1827,7 @@ int gemv_resident_ctas(int dtype, int adjoint, int shape, int adj_cw, int ld_pol
 cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,
                           const void* W, const void* R, void* out, cudaStream_t stream) {
   if (nitems <= 0) return cudaSuccess;
-  if (dtype == 0)
+  if (real_dtype(dtype) == 0)
     finish_kernel<float><<<nitems, kThreads, 0, stream>>>(items, diags, reinterpret_cast<const float*>(in),
                                                           reinterpret_cast<const float*>(W),
                                                           reinterpret_cast<const float*>(R),

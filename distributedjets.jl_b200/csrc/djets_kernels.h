@@ -40,7 +40,7 @@ struct FinishItem {
   int nplanes, nremote;
   int diag_begin, diag_end;
   int len;
-  int pad_;
+  int flags;  // bit 0: complex (elements are (re, im) pairs, len counts reals), bit 1: conjugate the diagonal (adjoint)
 };
 
 // ---- launchers (all asynchronous on `stream`) ------------------------------------------------
@@ -87,6 +87,7 @@ struct LincombArgs {
 };
 cudaError_t launch_lincomb(int ddtype, void* dest, const LincombArgs& a, long long n, int wide, cudaStream_t stream);
 cudaError_t launch_fill(int dtype, void* dest, double a, long long n, cudaStream_t stream);
+cudaError_t launch_fill_complex(int dtype, void* dest, double re, double im, long long n, cudaStream_t stream);
 cudaError_t launch_binary(int dtype, int op, void* dest, const void* a, const void* b, long long n,
                           cudaStream_t stream);
 
@@ -139,7 +140,8 @@ cudaError_t launch_eval(int ddtype, void* dest, const EvalArgs& a, long long n, 
 
 // Reductions in one launch.  `partials` holds at least reduce_max_ctas() doubles, `ticket` one unsigned that is
 // zero between launches, `result` one double (device).  kind: DJETS_RED_* or RED_DOT (100).
-enum { RED_DOT = 100 };
+// complex kinds: |z|-based maps over (re, im) pairs (n counts complex elements) and the imaginary part of dot(x, y) = sum conj(x) y
+enum { RED_DOT = 100, RED_CABSSUM = 101, RED_CABSMAX = 102, RED_CABSMIN = 103, RED_CNNZ = 104, RED_CSUMPOW = 105, RED_CDOT_IM = 106 };
 int reduce_max_ctas();
 cudaError_t launch_reduce(int dtype, int kind, const void* x, const void* y, long long n, double param,
                           double* partials, unsigned* ticket, double* result, cudaStream_t stream);
@@ -160,8 +162,13 @@ cudaError_t launch_scalar_op(int dtype, int op, const double* a, const double* b
 cudaError_t launch_scalar_set(double v, double* out, cudaStream_t stream);
 
 // geometry helpers shared with the scheduler
-inline int vec_elems(int dtype) { return dtype == 0 ? 4 : 2; }
-inline int elem_size(int dtype) { return dtype == 0 ? 4 : 8; }
+// dtype codes: 0 Float32, 1 Float64, 2 Complex{Float32}, 3 Complex{Float64} (interleaved re, im).  Complex data is
+// processed by the real-typed kernels over twice as many real elements; the GEMV / diagonal / |z| kernels take a
+// CPLX switch for the places where the pairing matters.
+inline bool is_complex(int dtype) { return dtype >= 2; }
+inline int real_dtype(int dtype) { return dtype & 1; }
+inline int elem_size(int dtype) { return dtype == 0 ? 4 : (dtype == 3 ? 16 : 8); }
+inline int vec_elems(int dtype) { return 16 / elem_size(dtype); }
 constexpr int kThreads = 256;
 constexpr int kFwdMaxTC = 1024;   // columns of x staged in shared memory by a forward tile
 constexpr int kAdjMaxTRBytes = 32768;  // bytes of y staged in shared memory by an adjoint tile

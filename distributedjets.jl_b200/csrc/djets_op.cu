@@ -194,7 +194,7 @@ TileShape plan_shape(int dtype, int64_t m, int64_t n, bool adjoint, int64_t fwd_
   if (m <= 0 || n <= 0) return s;
   if (!adjoint) {
     const int64_t tr = fwd_tx * vec_elems(dtype);
-    const int64_t tcmax = std::max<int64_t>(1, std::min<int64_t>(fwd_tc, kFwdMaxTC));
+    const int64_t tcmax = std::max<int64_t>(1, std::min<int64_t>(fwd_tc, kFwdMaxTC / (is_complex(dtype) ? 2 : 1)));
     const int64_t npan = ceil_div(n, tcmax);
     s.tile_rows = tr;
     s.tile_cols = ceil_div(n, npan);
@@ -222,6 +222,10 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   DirPlan& plan = adjoint ? cell.adj : cell.fwd;
   free_plan(plan, op->xp_tried ? &ctx->graveyard : nullptr);
   const int es = elem_size(op->dtype);
+  // Complex operators: the kernels are real-typed and see (re, im) pairs, so every extent and offset that counts
+  // ELEMENTS of a vector, of the workspace or down a matrix column is written into the descriptors in reals (x cs);
+  // tile column counts stay in (complex) columns.  Sizes in bytes use `es` and need no scaling.
+  const int64_t cs = is_complex(op->dtype) ? 2 : 1;
   const int64_t r0 = op->row_cuts[cell.r], r1 = op->row_cuts[cell.r + 1];
   const int64_t c0 = op->isdiag ? r0 : op->col_cuts[cell.c], c1 = op->isdiag ? r1 : op->col_cuts[cell.c + 1];
   const int64_t o0 = adjoint ? c0 : r0, o1 = adjoint ? c1 : r1;  // output blocks
@@ -298,6 +302,10 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
       eff_adj_tc = std::min<int64_t>(4096, std::max<int64_t>(pass, round_up(std::max<int64_t>(want, 1), pass)));
     }
   }
+  if (cs == 2) {  // the complex adjoint kernel comes in two shapes: 4 row chunks x 4 columns, 1 x 8 for short columns
+    adj_ru = adj_ru == 1 ? 1 : 4;
+    fwd_tx = std::max<int64_t>(fwd_tx, 64);
+  }
   if (adjoint) {
     plan.adj_ru = adj_ru;
     plan.adj_cw = adj_cw;
@@ -346,23 +354,23 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
       const int first = (int)dst.size();
       for (int64_t e0 = 0; e0 < olen; e0 += chunk) {
         FinishItem it;
-        it.out = out_off[o] + e0;
-        it.w0 = wbase + e0;
-        it.wstride = olen;
-        it.r0 = out_off[o] + e0;
-        it.rstride = part_len;
+        it.out = cs * (out_off[o] + e0);
+        it.w0 = cs * (wbase + e0);
+        it.wstride = cs * olen;
+        it.r0 = cs * (out_off[o] + e0);
+        it.rstride = cs * part_len;
         it.nplanes = (int)nplanes;
         it.nremote = nremote;
         it.diag_begin = (int)diags.size();
         for (const Contribution& cb : diag) {
           DiagTerm d;
           d.d = cb.b->d + e0 * es;
-          d.vin = in_off[cb.in] + e0;
+          d.vin = cs * (in_off[cb.in] + e0);
           diags.push_back(d);
         }
         it.diag_end = (int)diags.size();
-        it.len = (int)std::min<int64_t>(chunk, olen - e0);
-        it.pad_ = 0;
+        it.len = (int)(cs * std::min<int64_t>(chunk, olen - e0));
+        it.flags = cs == 2 ? (adjoint ? 3 : 1) : 0;
         dst.push_back(it);
         if (&dst == &loose) loose_key.push_back(e0);
       }
@@ -392,12 +400,12 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
           for (int64_t row0 = 0; row0 < m; row0 += sh.tile_rows) {
             DenseTile t;
             t.A = cb.b->d + (row0 + col0 * cb.b->ld) * es;
-            t.ld = cb.b->ld;
-            t.vin = in_off[j] + col0;
-            t.rows = (int)std::min<int64_t>(sh.tile_rows, m - row0);
+            t.ld = cs * cb.b->ld;
+            t.vin = cs * (in_off[j] + col0);
+            t.rows = (int)(cs * std::min<int64_t>(sh.tile_rows, m - row0));
             t.cols = (int)std::min<int64_t>(sh.tile_cols, n - col0);
             t.direct = direct ? 1 : 0;
-            t.wout = direct ? out_off[o] + row0 : wbase + (plane + p) * olen + row0;
+            t.wout = cs * (direct ? out_off[o] + row0 : wbase + (plane + p) * olen + row0);
             t.fin = fuse ? fused_first + (int)(row0 / strip) : -1;
             tiles.push_back(t);
           }
@@ -407,12 +415,12 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
           for (int64_t col0 = 0; col0 < n; col0 += sh.tile_cols) {
             DenseTile t;
             t.A = cb.b->d + (row0 + col0 * cb.b->ld) * es;
-            t.ld = cb.b->ld;
-            t.vin = in_off[i] + row0;
-            t.rows = (int)std::min<int64_t>(sh.tile_rows, m - row0);
+            t.ld = cs * cb.b->ld;
+            t.vin = cs * (in_off[i] + row0);
+            t.rows = (int)(cs * std::min<int64_t>(sh.tile_rows, m - row0));
             t.cols = (int)std::min<int64_t>(sh.tile_cols, n - col0);
             t.direct = direct ? 1 : 0;
-            t.wout = direct ? out_off[o] + col0 : wbase + (plane + p) * olen + col0;
+            t.wout = cs * (direct ? out_off[o] + col0 : wbase + (plane + p) * olen + col0);
             t.fin = fuse ? fused_first + (int)(col0 / strip) : -1;
             tiles.push_back(t);
           }
@@ -1126,7 +1134,7 @@ extern "C" {
 int32_t djets_plan_tiles(int32_t dtype, int64_t m, int64_t n, int32_t adjoint, int64_t* tile_rows, int64_t* tile_cols,
                          int64_t* ntiles) {
   return guard([&] {
-    REQUIRE(dtype == DJETS_F32 || dtype == DJETS_F64, DJETS_ERR_INVALID, "plan_tiles: bad dtype");
+    REQUIRE(dtype >= DJETS_F32 && dtype <= DJETS_C128, DJETS_ERR_INVALID, "plan_tiles: bad dtype");
     REQUIRE(m >= 0 && n >= 0, DJETS_ERR_INVALID, "plan_tiles: negative size");
     djets_ctx_s defaults;
     const TileShape s = plan_shape(dtype, m, n, adjoint != 0, defaults.fwd_tx, defaults.fwd_tc, defaults.adj_tc);
@@ -1157,7 +1165,7 @@ int32_t djets_op_create(djets_ctx ctx, int32_t dtype, int64_t nbrow, int64_t nbc
                         const int64_t* row_cuts, const int64_t* col_cuts, int32_t isdiag, djets_op* out) {
   return guard([&] {
     REQUIRE(ctx && out && row_len && col_len, DJETS_ERR_INVALID, "op_create: null argument");
-    REQUIRE(dtype == DJETS_F32 || dtype == DJETS_F64, DJETS_ERR_INVALID, "dtype must be DJETS_F32 or DJETS_F64");
+    REQUIRE(dtype >= DJETS_F32 && dtype <= DJETS_C128, DJETS_ERR_INVALID, "dtype must be DJETS_F32, F64, C64 or C128");
     REQUIRE(nbrow >= 1 && nbcol >= 1, DJETS_ERR_INVALID, "op_create: the operator needs at least one block");
     REQUIRE(n1 >= 1 && n2 >= 1 && n1 <= nbrow && n2 <= nbcol && n1 * n2 <= ctx->world, DJETS_ERR_INVALID,
             "op_create: process grid does not fit the blocks / the job");

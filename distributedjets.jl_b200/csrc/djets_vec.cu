@@ -41,7 +41,7 @@ namespace djets {
 djets_vec make_vec(djets_ctx ctx, int dtype, int nparts, const int32_t* part_rank, const int64_t* part_nblocks,
                    const int64_t* block_len) {
   REQUIRE(ctx, DJETS_ERR_INVALID, "null context");
-  REQUIRE(dtype == DJETS_F32 || dtype == DJETS_F64, DJETS_ERR_INVALID, "dtype must be DJETS_F32 or DJETS_F64");
+  REQUIRE(dtype >= DJETS_F32 && dtype <= DJETS_C128, DJETS_ERR_INVALID, "dtype must be DJETS_F32, F64, C64 or C128");
   REQUIRE(nparts >= 1 && nparts <= kMaxParts, DJETS_ERR_INVALID, "nparts out of range");
   auto v = std::make_unique<djets_vec_s>();
   v->ctx = ctx;
@@ -118,7 +118,7 @@ bool same_layout(djets_vec a, djets_vec b) {
   return true;
 }
 
-double round_to(int dtype, double v) { return dtype == DJETS_F32 ? (double)(float)v : v; }
+double round_to(int dtype, double v) { return real_dtype(dtype) == DJETS_F32 ? (double)(float)v : v; }
 
 // Per-part partial reductions: one result per part in out_parts (all parts, after the cross-process
 // exchange when some parts live elsewhere).
@@ -175,8 +175,8 @@ void reduce_parts(djets_vec x, djets_vec y, int kind, double param, double* out_
     // without an exchange the kernel stores the part's result straight into mapped host memory: no copy to wait for
     double* res = exchange ? rc->d_result + p : rc->h_result_dev + p;
     launch_counted(ctx, *rc, DJETS_K_REDUCE, [&] {
-      return launch_reduce(x->dtype, kind, part.d, yp, part.elem_count, param, rc->d_partials, rc->d_ticket, res,
-                           rc->stream);
+      return launch_reduce(real_dtype(x->dtype), kind, part.d, yp, part.elem_count * (is_complex(x->dtype) ? 2 : 1), param,
+                           rc->d_partials, rc->d_ticket, res, rc->stream);
     });
   }
   if (exchange) {
@@ -253,6 +253,7 @@ double fold_parts(int dtype, int kind, const double* z, int np) {
 void reduce_to_scalar(djets_vec x, djets_vec y, int kind, double param, int fold_mode, double fold_p, djets_scalar out,
                       bool as_norm = false) {
   djets_ctx ctx = x->ctx;
+  REQUIRE(!is_complex(x->dtype), DJETS_ERR_UNSUPPORTED, "device-resident reductions: real element types only");
   REQUIRE(out && out->ctx == ctx, DJETS_ERR_INVALID, "reduction into a scalar of another context");
   settle(x);
   settle(y);
@@ -262,8 +263,9 @@ void reduce_to_scalar(djets_vec x, djets_vec y, int kind, double param, int fold
     const void* yp = y ? y->parts[p].d : nullptr;
     launch_counted(ctx, rc, DJETS_K_REDUCE, [&] {
       if (as_norm && x->parts[p].elem_count == 0) return launch_scalar_set(0.0, res, rc.stream);
-      return launch_reduce(x->dtype, kind, x->parts[p].d, yp, x->parts[p].elem_count, param, rc.d_partials, rc.d_ticket,
-                           res, rc.stream);
+      return launch_reduce(real_dtype(x->dtype), kind, x->parts[p].d, yp,
+                           x->parts[p].elem_count * (is_complex(x->dtype) ? 2 : 1), param, rc.d_partials, rc.d_ticket, res,
+                           rc.stream);
     });
   };
   const int np = (int)x->parts.size();
@@ -473,9 +475,25 @@ int32_t djets_vec_getblock(djets_vec x, int64_t iblock, void* host_dst) {
   return guard([&] { block_copy(x, iblock, host_dst, false); });
 }
 
+static void getindex2(djets_vec x, int64_t i, double* out2);
+
+int32_t djets_vec_getindex_c(djets_vec x, int64_t i, double* out2) {
+  return guard([&] {
+    REQUIRE(x && out2, DJETS_ERR_INVALID, "null argument");
+    getindex2(x, i, out2);
+  });
+}
+
 int32_t djets_vec_getindex(djets_vec x, int64_t i, double* out) {
   return guard([&] {
     REQUIRE(x && out, DJETS_ERR_INVALID, "null argument");
+    if (is_complex(x->dtype)) {
+      double z[2];
+      getindex2(x, i, z);
+      REQUIRE(z[1] == 0.0, DJETS_ERR_UNSUPPORTED, "getindex: complex element (use djets_vec_getindex_c)");
+      *out = z[0];
+      return;
+    }
     REQUIRE(i >= 0 && i < x->length, DJETS_ERR_INVALID, "BoundsError: index outside the DBArray");
     settle(x);
     for (VecPart& p : x->parts) {
@@ -523,6 +541,33 @@ static void bulk_copy(djets_vec x, void* host, bool to_device) {
     }
 }
 
+static void getindex2(djets_vec x, int64_t i, double* out2) {
+  REQUIRE(i >= 0 && i < x->length, DJETS_ERR_INVALID, "BoundsError: index outside the DBArray");
+  no_sync_in_capture(x->ctx, "getindex");
+  settle(x);
+  for (VecPart& p : x->parts) {
+    if (i < p.elem_first || i >= p.elem_first + p.elem_count) continue;
+    RankCtx* rc = x->ctx->local(p.rank);
+    REQUIRE(rc, DJETS_ERR_NOT_LOCAL, "getindex: element is owned by a rank of another process");
+    use(*rc);
+    const int es = elem_size(x->dtype);
+    double buf[2] = {0.0, 0.0};
+    CK(cudaMemcpyAsync(buf, p.d + (size_t)(i - p.elem_first) * es, es, cudaMemcpyDeviceToHost, rc->stream));
+    CK(cudaStreamSynchronize(rc->stream));
+    if (real_dtype(x->dtype) == DJETS_F32) {
+      float f[2];
+      memcpy(f, buf, 8);
+      out2[0] = f[0];
+      out2[1] = is_complex(x->dtype) ? f[1] : 0.0;
+    } else {
+      out2[0] = buf[0];
+      out2[1] = is_complex(x->dtype) ? buf[1] : 0.0;
+    }
+    return;
+  }
+  fail(DJETS_ERR_INVALID, "getindex: no part holds the index");
+}
+
 int32_t djets_vec_collect(djets_vec x, void* host_dst) {
   return guard([&] { bulk_copy(x, host_dst, false); });
 }
@@ -538,8 +583,27 @@ int32_t djets_vec_fill(djets_vec x, double a) {
       RankCtx* rc = x->ctx->local(p.rank);
       if (!rc) continue;
       use(*rc);
-      launch_counted(x->ctx, *rc, DJETS_K_ELTWISE,
-                     [&] { return launch_fill(x->dtype, p.d, a, p.elem_count, rc->stream); });
+      launch_counted(x->ctx, *rc, DJETS_K_ELTWISE, [&] {
+        return is_complex(x->dtype) ? launch_fill_complex(x->dtype, p.d, a, 0.0, p.elem_count, rc->stream)
+                                    : launch_fill(x->dtype, p.d, a, p.elem_count, rc->stream);
+      });
+    }
+  });
+}
+
+int32_t djets_vec_fill_c(djets_vec x, double re, double im) {
+  return guard([&] {
+    REQUIRE(x, DJETS_ERR_INVALID, "null vector");
+    REQUIRE(is_complex(x->dtype) || im == 0.0, DJETS_ERR_MISMATCH, "InexactError: complex value into a real DBArray");
+    settle(x);
+    for (VecPart& p : x->parts) {
+      RankCtx* rc = x->ctx->local(p.rank);
+      if (!rc) continue;
+      use(*rc);
+      launch_counted(x->ctx, *rc, DJETS_K_ELTWISE, [&] {
+        return is_complex(x->dtype) ? launch_fill_complex(x->dtype, p.d, re, im, p.elem_count, rc->stream)
+                                    : launch_fill(x->dtype, p.d, re, p.elem_count, rc->stream);
+      });
     }
   });
 }
@@ -553,8 +617,12 @@ int32_t djets_vec_lincomb(djets_vec dest, int32_t nterms, const double* coef, co
       REQUIRE(same_layout(dest, xs[k]), DJETS_ERR_MISMATCH,
               "DimensionMismatch: broadcast operands have different block layouts");
       settle(xs[k]);
+      REQUIRE(is_complex(xs[k]->dtype) == is_complex(dest->dtype), DJETS_ERR_UNSUPPORTED,
+              "broadcast between real and complex DBArrays is outside the closed set");
     }
     settle(dest);
+    // complex vectors with real coefficients: the same kernels over twice as many reals
+    const int cs = is_complex(dest->dtype) ? 2 : 1;
     for (size_t p = 0; p < dest->parts.size(); ++p) {
       VecPart& dp = dest->parts[p];
       RankCtx* rc = dest->ctx->local(dp.rank);
@@ -565,10 +633,11 @@ int32_t djets_vec_lincomb(djets_vec dest, int32_t nterms, const double* coef, co
       for (int k = 0; k < nterms; ++k) {
         a.x[k] = xs[k]->parts[p].d;
         a.coef[k] = coef[k];
-        a.xdtype[k] = xs[k]->dtype;
+        a.xdtype[k] = real_dtype(xs[k]->dtype);
       }
-      launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE,
-                     [&] { return launch_lincomb(dest->dtype, dp.d, a, dp.elem_count, flags & 1, rc->stream); });
+      launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE, [&] {
+        return launch_lincomb(real_dtype(dest->dtype), dp.d, a, dp.elem_count * cs, flags & 1, rc->stream);
+      });
     }
   });
 }
@@ -581,6 +650,7 @@ int32_t djets_vec_binary(djets_vec dest, int32_t op, djets_vec a, djets_vec b) {
             "DimensionMismatch: broadcast operands have different block layouts");
     REQUIRE(dest->dtype == a->dtype && dest->dtype == b->dtype, DJETS_ERR_UNSUPPORTED,
             "binary: operands must share the element type");
+    REQUIRE(!is_complex(dest->dtype), DJETS_ERR_UNSUPPORTED, "binary: real element types only");
     settle(dest);
     settle(a);
     settle(b);
@@ -600,6 +670,7 @@ int32_t djets_vec_reduce_parts(djets_vec x, int32_t kind, double param, double* 
   return guard([&] {
     REQUIRE(x && out_parts, DJETS_ERR_INVALID, "reduce: null argument");
     REQUIRE(kind >= 0 && kind <= DJETS_RED_SUMSQ_SHIFT, DJETS_ERR_INVALID, "reduce: unknown kind");
+    REQUIRE(!is_complex(x->dtype), DJETS_ERR_UNSUPPORTED, "reduce: real element types only (complex: dot, norm)");
     reduce_parts(x, nullptr, kind, param, out_parts);
   });
 }
@@ -608,15 +679,33 @@ int32_t djets_vec_reduce(djets_vec x, int32_t kind, double param, double* out) {
   return guard([&] {
     REQUIRE(x && out, DJETS_ERR_INVALID, "reduce: null argument");
     REQUIRE(kind >= 0 && kind <= DJETS_RED_SUMSQ_SHIFT, DJETS_ERR_INVALID, "reduce: unknown kind");
+    REQUIRE(!is_complex(x->dtype), DJETS_ERR_UNSUPPORTED, "reduce: real element types only (complex: dot, norm)");
     std::vector<double> z(x->parts.size());
     reduce_parts(x, nullptr, kind, param, z.data());
     *out = fold_parts(x->dtype, kind, z.data(), (int)z.size());
   });
 }
 
+int32_t djets_vec_dot_c(djets_vec x, djets_vec y, double* out2) {
+  return guard([&] {
+    REQUIRE(x && y && out2, DJETS_ERR_INVALID, "dot: null argument");
+    REQUIRE(same_layout(x, y), DJETS_ERR_MISMATCH, "DimensionMismatch: dot of DBArrays with different block layouts");
+    REQUIRE(x->dtype == y->dtype, DJETS_ERR_MISMATCH, "dot: element types differ (reference: MethodError, src:214)");
+    std::vector<double> z(x->parts.size());
+    reduce_parts(x, y, RED_DOT, 0.0, z.data());  // over the (re, im) reals: Re sum conj(x) y
+    out2[0] = fold_parts(x->dtype, DJETS_RED_SUM, z.data(), (int)z.size());
+    out2[1] = 0.0;
+    if (is_complex(x->dtype)) {
+      reduce_parts(x, y, RED_CDOT_IM, 0.0, z.data());
+      out2[1] = fold_parts(x->dtype, DJETS_RED_SUM, z.data(), (int)z.size());
+    }
+  });
+}
+
 int32_t djets_vec_dot(djets_vec x, djets_vec y, double* out) {
   return guard([&] {
     REQUIRE(x && y && out, DJETS_ERR_INVALID, "dot: null argument");
+    REQUIRE(!is_complex(x->dtype), DJETS_ERR_UNSUPPORTED, "dot: complex DBArrays return a complex value (djets_vec_dot_c)");
     REQUIRE(same_layout(x, y), DJETS_ERR_MISMATCH, "DimensionMismatch: dot of DBArrays with different block layouts");
     REQUIRE(x->dtype == y->dtype, DJETS_ERR_MISMATCH, "dot: element types differ (reference: MethodError, src:214)");
     std::vector<double> z(x->parts.size());
@@ -631,6 +720,28 @@ int32_t djets_vec_norm(djets_vec x, double p, double* out) {
     const int np = (int)x->parts.size();
     const int dt = x->dtype;
     std::vector<double> z(np);
+    if (is_complex(dt)) {  // |z| per element (Julia's norm of a complex array); same folds
+      if (p == INFINITY) {
+        reduce_parts(x, nullptr, RED_CABSMAX, 0.0, z.data(), true);
+        *out = fold_parts(dt, DJETS_RED_MAX, z.data(), np);
+      } else if (p == -INFINITY) {
+        reduce_parts(x, nullptr, RED_CABSMIN, 0.0, z.data(), true);
+        *out = fold_parts(dt, DJETS_RED_MIN, z.data(), np);
+      } else if (p == 0.0 || p == 1.0) {
+        reduce_parts(x, nullptr, p == 0.0 ? RED_CNNZ : RED_CABSSUM, 0.0, z.data(), true);
+        *out = fold_parts(dt, DJETS_RED_SUM, z.data(), np);
+      } else {
+        const double pp = round_to(dt, p);
+        reduce_parts(x, nullptr, p == 2.0 ? (int)DJETS_RED_SUMSQ : (int)RED_CSUMPOW, pp, z.data(), true);
+        double s = 0.0;
+        for (int k = 0; k < np; ++k) {
+          const double zk = round_to(dt, p == 2.0 ? sqrt(z[k]) : pow(z[k], 1.0 / pp));
+          s = round_to(dt, s + round_to(dt, p == 2.0 ? zk * zk : pow(zk, pp)));
+        }
+        *out = round_to(dt, p == 2.0 ? sqrt(s) : pow(s, round_to(dt, 1.0 / pp)));
+      }
+      return;
+    }
     if (p == INFINITY) {  // src:200-201
       reduce_parts(x, nullptr, DJETS_RED_ABSMAX, 0.0, z.data(), true);
       *out = fold_parts(dt, DJETS_RED_MAX, z.data(), np);
@@ -711,6 +822,8 @@ int32_t djets_vec_eval(djets_vec dest, const uint8_t* program, int32_t nops, con
       REQUIRE(same_layout(dest, inputs[k]), DJETS_ERR_MISMATCH,
               "DimensionMismatch: broadcast operands have different block layouts");
       settle(inputs[k]);
+      REQUIRE(is_complex(inputs[k]->dtype) == is_complex(dest->dtype), DJETS_ERR_UNSUPPORTED,
+              "broadcast between real and complex DBArrays is outside the closed set");
     }
     settle(dest);
     EvalArgs a;
@@ -770,14 +883,18 @@ int32_t djets_vec_eval(djets_vec dest, const uint8_t* program, int32_t nops, con
           for (int k = 0; k < nt; ++k) {
             la.x[k] = inputs[which[k]]->parts[p].d;
             la.coef[k] = coef[k];
-            la.xdtype[k] = inputs[which[k]]->dtype;
+            la.xdtype[k] = real_dtype(inputs[which[k]]->dtype);
           }
-          launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE,
-                         [&] { return launch_lincomb(dest->dtype, dp.d, la, dp.elem_count, flags & 1, rc->stream); });
+          const int cs = is_complex(dest->dtype) ? 2 : 1;
+          launch_counted(dest->ctx, *rc, DJETS_K_ELTWISE, [&] {
+            return launch_lincomb(real_dtype(dest->dtype), dp.d, la, dp.elem_count * cs, flags & 1, rc->stream);
+          });
         }
         return;
       }
     }
+    REQUIRE(!is_complex(dest->dtype), DJETS_ERR_UNSUPPORTED,
+            "eval: complex DBArrays support linear combinations with real coefficients only");
     for (size_t p = 0; p < dest->parts.size(); ++p) {
       VecPart& dp = dest->parts[p];
       RankCtx* rc = dest->ctx->local(dp.rank);

@@ -25,7 +25,7 @@ export DBArray, JetDSpace, blockmap, localblockindices
 # a constant: `ccall((:symbol, lib), ...)` needs the library as a compile-time constant
 const libdjets = get(ENV, "DJETS_B200_LIB", joinpath(@__DIR__, "..", "libdjets_b200.so"))
 
-const DJETS_F32, DJETS_F64 = Int32(0), Int32(1)
+const DJETS_F32, DJETS_F64, DJETS_C64, DJETS_C128 = Int32(0), Int32(1), Int32(2), Int32(3)
 const BLOCK_ZERO, BLOCK_DENSE, BLOCK_DIAG = Int32(0), Int32(1), Int32(2)
 const RED_SUM, RED_MIN, RED_MAX, RED_ABSSUM, RED_ABSMAX, RED_ABSMIN, RED_SUMSQ, RED_NNZ, RED_SUMPOW, RED_SUMSQ_SHIFT = Int32.(0:9)
 
@@ -36,7 +36,9 @@ const SC_ADD, SC_SUB, SC_MUL, SC_DIV, SC_NEG, SC_SQRT, SC_COPY, SC_ABS, SC_MAX, 
 
 dtypecode(::Type{Float32}) = DJETS_F32
 dtypecode(::Type{Float64}) = DJETS_F64
-dtypecode(::Type{T}) where {T} = error("DistributedJetsB200: element type $T is not supported (Float32, Float64)")
+dtypecode(::Type{Complex{Float32}}) = DJETS_C64
+dtypecode(::Type{Complex{Float64}}) = DJETS_C128
+dtypecode(::Type{T}) where {T} = error("DistributedJetsB200: element type $T is not supported (Float32, Float64 and their Complex types)")
 
 lasterror() = unsafe_string(ccall((:djets_last_error, libdjets), Cstring, ()))
 function check(status::Int32)
@@ -192,6 +194,12 @@ function Base.getindex(x::DBArray{T}, i::Int) where {T}                         
     @dj djets_vec_getindex (Ptr{Cvoid}, Int64, Ptr{Float64}) x.h Int64(i - 1) v
     T(v[])
 end
+function Base.getindex(x::DBArray{T}, i::Int) where {T<:Complex}
+    checkbounds(x, i)
+    z = zeros(Float64, 2)
+    @dj djets_vec_getindex_c (Ptr{Cvoid}, Int64, Ptr{Float64}) x.h Int64(i - 1) z
+    T(z[1], z[2])
+end
 function Base.similar(x::DBArray, ::Type{T}) where {T}                                      # src:181-185
     h = Ref{Ptr{Cvoid}}(C_NULL)
     @dj djets_vec_similar (Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}) x.h dtypecode(T) h
@@ -237,7 +245,8 @@ function Base.collect(x::DBArray{T}) where {T}
     end
     Jets.BlockArray(arrays, idx)
 end
-Base.fill!(x::DBArray, a) = (@dj djets_vec_fill (Ptr{Cvoid}, Float64) x.h Float64(a); x)
+Base.fill!(x::DBArray, a::Real) = (@dj djets_vec_fill (Ptr{Cvoid}, Float64) x.h Float64(a); x)
+Base.fill!(x::DBArray, a::Complex) = (@dj djets_vec_fill_c (Ptr{Cvoid}, Float64, Float64) x.h Float64(real(a)) Float64(imag(a)); x)
 # stream-ordered forms for page-locked buffers: `a` must stay alive and untouched until `synchronize()` / `waitmark`
 scatter_async!(x::DBArray{T}, a::Vector{T}) where {T} = (@dj djets_vec_scatter_async (Ptr{Cvoid}, Ptr{Cvoid}) x.h pointer(a); x)
 collect_async!(a::Vector{T}, x::DBArray{T}) where {T} = (@dj djets_vec_collect_async (Ptr{Cvoid}, Ptr{Cvoid}) x.h pointer(a); a)
@@ -306,6 +315,11 @@ function LinearAlgebra.dot(x::DBArray{T}, y::DBArray{T}) where {T}
     @dj djets_vec_dot (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}) x.h y.h v
     T(v[])
 end
+function LinearAlgebra.dot(x::DBArray{T}, y::DBArray{T}) where {T<:Complex}                  # conjugates x, like Julia's dot
+    z = zeros(Float64, 2)
+    @dj djets_vec_dot_c (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}) x.h y.h z
+    T(z[1], z[2])
+end
 Base.extrema(x::DBArray) = (reduce_kind(x, RED_MIN), reduce_kind(x, RED_MAX))
 Base.maximum(x::DBArray) = reduce_kind(x, RED_MAX)
 Base.minimum(x::DBArray) = reduce_kind(x, RED_MIN)
@@ -360,8 +374,9 @@ function scalarindex!(p::Program, a)
         push!(p.scal, 0.0); push!(p.dscal, a.h)
         a isa DScalar{Float64} && (p.wide = true)
     else
-        push!(p.scal, Float64(a)); push!(p.dscal, C_NULL)
-        a isa Float64 && (p.wide = true)                              # Int and Float32 scalars do not promote Float32 arrays
+        a isa Complex && !iszero(imag(a)) && error("DistributedJetsB200: complex coefficients in a broadcast are outside the closed set")
+        push!(p.scal, Float64(real(a))); push!(p.dscal, C_NULL)
+        (a isa Float64 || a isa Complex{Float64}) && (p.wide = true)                              # Int and Float32 scalars do not promote Float32 arrays
     end
     UInt8(length(p.scal) - 1)
 end

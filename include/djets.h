@@ -38,7 +38,8 @@ typedef struct djets_op_s* djets_op;
 typedef struct djets_scalar_s* djets_scalar; /* a scalar resident on the devices (result of dot / norm, solver coefficients) */
 typedef struct djets_graph_s* djets_graph;   /* a captured sequence of calls, replayed with one launch */
 
-enum { DJETS_F32 = 0, DJETS_F64 = 1 };
+/* element types; the complex ones are interleaved (re, im) pairs: Julia's Complex{Float32} / Complex{Float64} */
+enum { DJETS_F32 = 0, DJETS_F64 = 1, DJETS_C64 = 2, DJETS_C128 = 3 };
 enum { DJETS_BLOCK_ZERO = 0, DJETS_BLOCK_DENSE = 1, DJETS_BLOCK_DIAG = 2 };
 enum {
   DJETS_OK = 0,
@@ -202,6 +203,8 @@ int32_t djets_vec_setblock(djets_vec x, int64_t iblock, const void* host_src);
 int32_t djets_vec_getblock(djets_vec x, int64_t iblock, void* host_dst);
 /* x[i] (src:174-179). */
 int32_t djets_vec_getindex(djets_vec x, int64_t i, double* out);
+/* x[i] of a complex DBArray: out2 = {re, im}. */
+int32_t djets_vec_getindex_c(djets_vec x, int64_t i, double* out2);
 /* collect(x) / convert(Array, x) (src:310-330): parts concatenated in procs order.  Parts owned
  * by ranks of other processes are left untouched in host_dst. */
 int32_t djets_vec_collect(djets_vec x, void* host_dst);
@@ -216,6 +219,8 @@ int32_t djets_vec_scatter_async(djets_vec x, const void* host_src);
 int32_t djets_vec_collect_async(djets_vec x, void* host_dst);
 /* fill!(x, a) (src:332-339; also `x .= a`, test:329). */
 int32_t djets_vec_fill(djets_vec x, double a);
+/* fill!(x, re + im*i) for complex DBArrays. */
+int32_t djets_vec_fill_c(djets_vec x, double re, double im);
 /* Broadcast `dest .= c0*x0 .+ c1*x1 .+ ...` (src:348-376 for the expression class the
  * reference's tests and benchmark use: test:322, bench:43; also `dest .= x` with element-type
  * conversion, test:237-238).  1 <= nterms <= 4; dest may alias any x_k; all layouts must match.
@@ -239,6 +244,10 @@ int32_t djets_vec_norm_s(djets_vec x, double p, djets_scalar out);
 int32_t djets_vec_reduce_s(djets_vec x, int32_t kind, double param, djets_scalar out);
 /* dot(x, y) (src:212-223): per-rank partial, folded over ranks in rank order in the element type. */
 int32_t djets_vec_dot(djets_vec x, djets_vec y, double* out);
+/* dot(x, y) = sum conj(x) .* y of complex DBArrays: out2 = {re, im}.  norm(x, p) of a complex DBArray goes through
+ * djets_vec_norm (|z| per element); lincomb / eval accept complex vectors with real coefficients (linear forms);
+ * the other reductions and the non-linear broadcast operators are defined for real element types only. */
+int32_t djets_vec_dot_c(djets_vec x, djets_vec y, double* out2);
 /* norm(x, p) (src:189-210) with the reference's fold rules; p may be +-INFINITY, 0, 1, 2, other. */
 int32_t djets_vec_norm(djets_vec x, double p, double* out);
 /* Per-rank partial reductions folded over ranks (src:225-283): see DJETS_RED_*. */
@@ -259,10 +268,10 @@ int32_t djets_op_create(djets_ctx ctx, int32_t dtype, int64_t nbrow, int64_t nbc
                         const int64_t* col_len, int32_t n1, int32_t n2, const int32_t* grid_ranks,
                         const int64_t* row_cuts, const int64_t* col_cuts, int32_t isdiag, djets_op* out);
 /* Dense block A (row_len[i] x col_len[j], column-major, leading dimension ld): `d .= A*m`,
- * `m .= A'*d` (the reference's dense fixture JopBaz, test:30-36).  No-op on processes that do
+ * `m .= A'*d` (the reference's dense fixture JopBaz, test:30-36; `A'` is the conjugate transpose for complex operators).  No-op on processes that do
  * not drive the owner (host may be NULL there). */
 int32_t djets_op_set_dense(djets_op op, int64_t i, int64_t j, const void* host, int64_t ld);
-/* Diagonal block `d .= diag .* m` (JopFoo test:8-12, JetPack JopDiagonal docs:19). */
+/* Diagonal block `d .= diag .* m` (JopFoo test:8-12, JetPack JopDiagonal docs:19); adjoint `m .= conj(diag) .* d`. */
 int32_t djets_op_set_diag(djets_op op, int64_t i, int64_t j, const void* host);
 /* Build the tile schedules (after the last set_*; implicit on first apply). */
 int32_t djets_op_finalize(djets_op op);

@@ -249,7 +249,7 @@ def blockarray_dot(x: BlockArray, y: BlockArray):
     t = x.dtype.type
     s = t(0)
     for a, b in zip(x.arrays, y.arrays):
-        s = t(s + np.dot(a.reshape(-1, order="F"), b.reshape(-1, order="F")))
+        s = t(s + np.vdot(a.reshape(-1, order="F"), b.reshape(-1, order="F")))   # Julia's dot conjugates its first argument
     return s
 
 
