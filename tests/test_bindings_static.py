@@ -106,7 +106,7 @@ def test_shim_lowers_broadcasts_like_the_python_mirror():
     jl = re.search(r"const (EV_IN,.*?) = UInt8\.\(1:26\)", src, flags=re.S).group(1)
     assert [t.strip() for t in jl.replace("\n", " ").split(",")] == ["EV_" + n for n in names]
     assert "return fill!(dest, unref(bc.args[1]))" in src
-    assert "a isa Float64 && (p.wide = true)" in src and "defaultgrid(nblks, length(pids))" in src
+    assert "(a isa Float64 || a isa Complex{Float64}) && (p.wide = true)" in src and "defaultgrid(nblks, length(pids))" in src
 
 
 def test_shim_keeps_the_reference_exports():
