@@ -551,7 +551,7 @@ def run_cuda(args):
         if world == 1 and nblk == NBLK and os.path.exists(tpath):     # the ncu capture is of exactly this launch
             with open(tpath) as f:
                 tdoc = json.load(f)
-                tj = tdoc.get(dom + "_tile_kernel") or tdoc.get(dom + "_kernel")
+                tj = tdoc.get({"gemv_n": "djets_blockmul_fwd_tile_kernel", "gemv_t": "djets_blockmul_adj_tile_kernel"}[dom])
             if tj:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
                 traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch (profiles/traffic_current.json)"

@@ -217,7 +217,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // (16 bytes each); thread t owns vectors t, t+256, ... of the tile (a warp's accesses stay fully coalesced).
 // ring[stage][input][v][thread] holds the operands; `stages` tiles are in flight per CTA.
 template <typename T, typename ACC, int NV, int D, bool kStreamStores>
-__global__ void __launch_bounds__(kThreads) eval_vec_kernel(T* dest /* may alias an input */, EvalDev a, long long n,
+__global__ void __launch_bounds__(kThreads) djets_eval_kernel(T* dest /* may alias an input */, EvalDev a, long long n,
                                                             int stages) {
   using V = typename Vec16<T>::type;
   constexpr int VEC = Vec16<T>::N;
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kThreads) eval_vec_kernel(T* dest /* may alias
 
 // Generic path: any mix of element types (conversions); one element per thread iteration, in double.
 template <typename TD>
-__global__ void __launch_bounds__(kThreads) eval_generic_kernel(TD* dest, EvalDev a, long long n) {
+__global__ void __launch_bounds__(kThreads) djets_eval_generic_kernel(TD* dest, EvalDev a, long long n) {
   __shared__ double sc[kEvalMaxScalars];
   load_scalars<double>(a, sc);
   const long long gstride = (long long)gridDim.x * kThreads;
@@ -329,7 +329,7 @@ cudaError_t launch_vec_k(T* dest, const EvalDev& d, long long n, cudaStream_t st
   int stages = (int)std::min<size_t>(4, std::max<size_t>(2, ((size_t)ring_kb * 1024) / stage_bytes));
   const size_t smem = stage_bytes * stages;
   static const bool cs = getenv("DJETS_EVAL_CS") && atoi(getenv("DJETS_EVAL_CS"));
-  auto kernel = cs ? eval_vec_kernel<T, ACC, NV, D, true> : eval_vec_kernel<T, ACC, NV, D, false>;
+  auto kernel = cs ? djets_eval_kernel<T, ACC, NV, D, true> : djets_eval_kernel<T, ACC, NV, D, false>;
   if (smem > 40 * 1024) {  // the kernel also holds a few hundred bytes of static shared memory
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -476,9 +476,9 @@ cudaError_t launch_eval(int ddtype, void* dest, const EvalArgs& a, long long n, 
   }
   const int grid = (int)std::min<long long>((n + kThreads - 1) / kThreads, 148LL * 8);
   if (ddtype == 1)
-    eval_generic_kernel<double><<<grid, kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), d, n);
+    djets_eval_generic_kernel<double><<<grid, kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), d, n);
   else
-    eval_generic_kernel<float><<<grid, kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), d, n);
+    djets_eval_generic_kernel<float><<<grid, kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), d, n);
   return cudaGetLastError();
 }
 
@@ -491,7 +491,7 @@ namespace {
 
 __device__ __forceinline__ double round_to(int dtype, double v) { return dtype == 0 ? (double)(float)v : v; }
 
-__global__ void fold_kernel(int dtype, int mode, double p, const double* __restrict__ parts, int nparts, double* out,
+__global__ void djets_fold_kernel(int dtype, int mode, double p, const double* __restrict__ parts, int nparts, double* out,
                             ScalarPeers peers) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double r;
@@ -518,7 +518,7 @@ __global__ void fold_kernel(int dtype, int mode, double p, const double* __restr
   for (int k = 0; k < peers.n; ++k) peers.p[k][0] = r;
 }
 
-__global__ void scalar_op_kernel(int dtype, int op, const double* a, const double* b, double* out) {
+__global__ void djets_scalar_op_kernel(int dtype, int op, const double* a, const double* b, double* out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double x = a ? a[0] : 0.0, y = b ? b[0] : 0.0;
   double r = 0.0;
@@ -537,7 +537,7 @@ __global__ void scalar_op_kernel(int dtype, int op, const double* a, const doubl
   out[0] = round_to(dtype, r);
 }
 
-__global__ void scalar_set_kernel(double v, double* out) {
+__global__ void djets_scalar_set_kernel(double v, double* out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = v;
 }
 
@@ -545,18 +545,18 @@ __global__ void scalar_set_kernel(double v, double* out) {
 
 cudaError_t launch_fold(int dtype, int mode, double p, const double* parts, int nparts, double* out, ScalarPeers peers,
                         cudaStream_t stream) {
-  fold_kernel<<<1, 32, 0, stream>>>(dtype, mode, p, parts, nparts, out, peers);
+  djets_fold_kernel<<<1, 32, 0, stream>>>(dtype, mode, p, parts, nparts, out, peers);
   return cudaGetLastError();
 }
 
 cudaError_t launch_scalar_op(int dtype, int op, const double* a, const double* b, double* out, cudaStream_t stream) {
   if (op < SC_ADD || op > SC_MIN) return cudaErrorInvalidValue;
-  scalar_op_kernel<<<1, 32, 0, stream>>>(dtype, op, a, b, out);
+  djets_scalar_op_kernel<<<1, 32, 0, stream>>>(dtype, op, a, b, out);
   return cudaGetLastError();
 }
 
 cudaError_t launch_scalar_set(double v, double* out, cudaStream_t stream) {
-  scalar_set_kernel<<<1, 32, 0, stream>>>(v, out);
+  djets_scalar_set_kernel<<<1, 32, 0, stream>>>(v, out);
   return cudaGetLastError();
 }
 

@@ -417,7 +417,7 @@ __device__ __forceinline__ void fused_finish(int fin, const FusedFinish& ff, con
 // memory in a fixed order.  U independent 128-bit loads are in flight per thread.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int TX, int POLICY, bool CPLX = false>
-__global__ void __launch_bounds__(kThreads, 4) gemv_n_tile_kernel(const DenseTile* __restrict__ tiles,
+__global__ void __launch_bounds__(kThreads, 4) djets_blockmul_fwd_tile_kernel(const DenseTile* __restrict__ tiles,
                                                           const T* __restrict__ in, T* W, T* __restrict__ out,
                                                           FusedFinish ff, Prefetch pf) {
   using V = typename VecT<T>::type;
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 4) gemv_n_tile_kernel(const DenseTil
 // per-lane sums are combined with a column-halving shuffle butterfly.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int RU, int CW, int POLICY>
-__global__ void __launch_bounds__(kThreads, (RU * CW <= 8) ? 3 : 2) gemv_t_tile_kernel(const DenseTile* __restrict__ tiles,
+__global__ void __launch_bounds__(kThreads, (RU * CW <= 8) ? 3 : 2) djets_blockmul_adj_tile_kernel(const DenseTile* __restrict__ tiles,
                                                              const T* __restrict__ in, T* W, T* __restrict__ out,
                                                              FusedFinish ff, Prefetch pf) {
   using V = typename VecT<T>::type;
@@ -697,7 +697,7 @@ struct TileQueue {
 // along the rows and TY = 256/TX column groups deep; the TY partial strips are summed in shared
 // memory in a fixed order.  U independent 128-bit loads are in flight per thread.
 template <typename T, int TX, int POLICY>
-__global__ void __launch_bounds__(kThreads, 4) gemv_n_kernel(const DenseTile* __restrict__ tiles, TileQueue q,
+__global__ void __launch_bounds__(kThreads, 4) djets_blockmul_fwd_queue_kernel(const DenseTile* __restrict__ tiles, TileQueue q,
                                                              const T* __restrict__ in, T* W, T* __restrict__ out,
                                                              FusedFinish ff, Prefetch pf) {
   using V = typename VecT<T>::type;
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(kThreads, 4) gemv_n_kernel(const DenseTile* __
 // `ld` count reals (two per complex row), `cols` counts complex columns, outputs are 2*cols reals.  A warp owns CWC
 // complex columns at a time (2*CWC accumulators), RU row chunks unrolled; same staging and butterfly as the real kernel.
 template <typename T, int RU, int CWC, int POLICY>
-__global__ void __launch_bounds__(kThreads, 2) gemv_tc_tile_kernel(const DenseTile* __restrict__ tiles,
+__global__ void __launch_bounds__(kThreads, 2) djets_blockmul_adjc_tile_kernel(const DenseTile* __restrict__ tiles,
                                                                    const T* __restrict__ in, T* W, T* __restrict__ out,
                                                                    FusedFinish ff, Prefetch pf) {
   using V = typename VecT<T>::type;
@@ -937,7 +937,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_tc_tile_kernel(const DenseTi
 }
 
 template <typename T, int RU, int CW, int POLICY>
-__global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __restrict__ tiles, TileQueue q,
+__global__ void __launch_bounds__(kThreads, 2) djets_blockmul_adj_queue_kernel(const DenseTile* __restrict__ tiles, TileQueue q,
                                                              const T* __restrict__ in, T* W, T* __restrict__ out,
                                                              FusedFinish ff, Prefetch pf) {
   using V = typename VecT<T>::type;
@@ -1129,7 +1129,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_t_kernel(const DenseTile* __
 // Loose items: block rows / columns with no dense tile on this rank (diagonal-only: the fused
 // streaming `d .= diag .* m`), and every item of a rank that also sums planes received from peers.
 template <typename T>
-__global__ void __launch_bounds__(kThreads) finish_kernel(const FinishItem* __restrict__ items,
+__global__ void __launch_bounds__(kThreads) djets_segsum_kernel(const FinishItem* __restrict__ items,
                                                           const DiagTerm* __restrict__ diags,
                                                           const T* __restrict__ in, const T* __restrict__ W,
                                                           const T* __restrict__ R, T* __restrict__ out) {
@@ -1220,7 +1220,7 @@ __device__ __forceinline__ double block_fold(double v) {
 }
 
 template <typename T, int KIND>
-__global__ void __launch_bounds__(kThreads) reduce_kernel(const T* __restrict__ x, const T* __restrict__ y,
+__global__ void __launch_bounds__(kThreads) djets_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y,
                                                           long long n, double param, double* partials,
                                                           unsigned* ticket, double* __restrict__ result) {
   using V = typename VecT<T>::type;
@@ -1287,7 +1287,7 @@ static cudaError_t launch_reduce_k(const void* x, const void* y, long long n, do
   constexpr int VEC = VecT<T>::N;
   long long want = (n / VEC + (long long)kThreads * 4 - 1) / ((long long)kThreads * 4);
   int grid = (int)(want < 1 ? 1 : (want > reduce_max_ctas() ? reduce_max_ctas() : want));
-  reduce_kernel<T, KIND><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(y),
+  djets_reduce_kernel<T, KIND><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(y),
                                                         n, param, partials, ticket, result);
   return cudaGetLastError();
 }
@@ -1347,7 +1347,7 @@ __device__ __forceinline__ ACC load_as(const void* p, int dtype, long long i) {
 
 // generic path: any mix of operand element types
 template <typename TD, typename ACC>
-__global__ void __launch_bounds__(kThreads) lincomb_generic(TD* dest /* may alias an operand */, LincombDev a, long long n) {
+__global__ void __launch_bounds__(kThreads) djets_lincomb_generic_kernel(TD* dest /* may alias an operand */, LincombDev a, long long n) {
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     ACC s;
@@ -1364,7 +1364,7 @@ __global__ void __launch_bounds__(kThreads) lincomb_generic(TD* dest /* may alia
 
 // fast path: all operands and dest share one element type; 128-bit loads / stores
 template <typename T, typename ACC, int NT>
-__global__ void __launch_bounds__(kThreads) lincomb_vec(T* dest /* may alias an operand */, LincombDev a, long long n) {
+__global__ void __launch_bounds__(kThreads) djets_lincomb_kernel(T* dest /* may alias an operand */, LincombDev a, long long n) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   const long long nvec = n / VEC;
@@ -1406,10 +1406,10 @@ template <typename T, typename ACC>
 static void launch_lincomb_vec(T* dest, const LincombDev& d, long long n, cudaStream_t stream) {
   const int grid = stream_grid(n / VecT<T>::N);
   switch (d.nterms) {
-    case 1: lincomb_vec<T, ACC, 1><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
-    case 2: lincomb_vec<T, ACC, 2><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
-    case 3: lincomb_vec<T, ACC, 3><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
-    default: lincomb_vec<T, ACC, 4><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
+    case 1: djets_lincomb_kernel<T, ACC, 1><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
+    case 2: djets_lincomb_kernel<T, ACC, 2><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
+    case 3: djets_lincomb_kernel<T, ACC, 3><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
+    default: djets_lincomb_kernel<T, ACC, 4><<<grid, kThreads, 0, stream>>>(dest, d, n); break;
   }
 }
 
@@ -1439,17 +1439,17 @@ cudaError_t launch_lincomb(int ddtype, void* dest, const LincombArgs& a, long lo
   } else {
     const int grid = stream_grid(n);
     if (ddtype == 1)
-      lincomb_generic<double, double><<<grid, kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), d, n);
+      djets_lincomb_generic_kernel<double, double><<<grid, kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), d, n);
     else if (wide || !same)
-      lincomb_generic<float, double><<<grid, kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), d, n);
+      djets_lincomb_generic_kernel<float, double><<<grid, kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), d, n);
     else
-      lincomb_generic<float, float><<<grid, kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), d, n);
+      djets_lincomb_generic_kernel<float, float><<<grid, kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), d, n);
   }
   return cudaGetLastError();
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads) fill_kernel(T* __restrict__ dest, T a, long long n) {
+__global__ void __launch_bounds__(kThreads) djets_fill_kernel(T* __restrict__ dest, T a, long long n) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   const long long nvec = n / VEC;
@@ -1466,14 +1466,14 @@ __global__ void __launch_bounds__(kThreads) fill_kernel(T* __restrict__ dest, T 
 cudaError_t launch_fill(int dtype, void* dest, double a, long long n, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   if (dtype == 0)
-    fill_kernel<float><<<stream_grid(n / 4), kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), (float)a, n);
+    djets_fill_kernel<float><<<stream_grid(n / 4), kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), (float)a, n);
   else
-    fill_kernel<double><<<stream_grid(n / 2), kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), a, n);
+    djets_fill_kernel<double><<<stream_grid(n / 2), kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), a, n);
   return cudaGetLastError();
 }
 
 template <typename T, int OP>
-__global__ void __launch_bounds__(kThreads) binary_kernel(T* dest /* may alias a or b */, const T* a, const T* b, long long n) {
+__global__ void __launch_bounds__(kThreads) djets_binary_kernel(T* dest /* may alias a or b */, const T* a, const T* b, long long n) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   const long long nvec = n / VEC;
@@ -1492,7 +1492,7 @@ __global__ void __launch_bounds__(kThreads) binary_kernel(T* dest /* may alias a
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads) fill_complex_kernel(T* __restrict__ dest, T re, T im, long long n /* reals */) {
+__global__ void __launch_bounds__(kThreads) djets_fill_complex_kernel(T* __restrict__ dest, T re, T im, long long n /* reals */) {
   using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   const long long nvec = n / VEC;
@@ -1509,9 +1509,9 @@ __global__ void __launch_bounds__(kThreads) fill_complex_kernel(T* __restrict__ 
 cudaError_t launch_fill_complex(int dtype, void* dest, double re, double im, long long n, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   if (real_dtype(dtype) == 0)
-    fill_complex_kernel<float><<<stream_grid(n / 2), kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), (float)re, (float)im, 2 * n);
+    djets_fill_complex_kernel<float><<<stream_grid(n / 2), kThreads, 0, stream>>>(reinterpret_cast<float*>(dest), (float)re, (float)im, 2 * n);
   else
-    fill_complex_kernel<double><<<stream_grid(n), kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), re, im, 2 * n);
+    djets_fill_complex_kernel<double><<<stream_grid(n), kThreads, 0, stream>>>(reinterpret_cast<double*>(dest), re, im, 2 * n);
   return cudaGetLastError();
 }
 
@@ -1520,7 +1520,7 @@ cudaError_t launch_binary(int dtype, int op, void* dest, const void* a, const vo
   if (n <= 0) return cudaSuccess;
   if (op != 0 && op != 1) return cudaErrorInvalidValue;
 #define DJ_BIN(T, OP)                                                                                              \
-  binary_kernel<T, OP><<<stream_grid(n / VecT<T>::N), kThreads, 0, stream>>>(                                      \
+  djets_binary_kernel<T, OP><<<stream_grid(n / VecT<T>::N), kThreads, 0, stream>>>(                                      \
       reinterpret_cast<T*>(dest), reinterpret_cast<const T*>(a), reinterpret_cast<const T*>(b), n)
   if (dtype == 0) {
     if (op == 0) DJ_BIN(float, 0); else DJ_BIN(float, 1);
@@ -1577,17 +1577,17 @@ static cudaError_t launch_gemv_n_t(int fwd_tx, const DenseTile* tiles, int ntile
   T* o = reinterpret_cast<T*>(out);
   switch (fwd_tx) {
     case 32:
-      if (grid >= ntiles) return launch_tiles(gemv_n_tile_kernel<T, 32, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-      return launch_tiles(gemv_n_kernel<T, 32, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+      if (grid >= ntiles) return launch_tiles(djets_blockmul_fwd_tile_kernel<T, 32, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+      return launch_tiles(djets_blockmul_fwd_queue_kernel<T, 32, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
     case 64:
-      if (grid >= ntiles) return launch_tiles(gemv_n_tile_kernel<T, 64, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-      return launch_tiles(gemv_n_kernel<T, 64, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+      if (grid >= ntiles) return launch_tiles(djets_blockmul_fwd_tile_kernel<T, 64, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+      return launch_tiles(djets_blockmul_fwd_queue_kernel<T, 64, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
     case 128:
-      if (grid >= ntiles) return launch_tiles(gemv_n_tile_kernel<T, 128, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-      return launch_tiles(gemv_n_kernel<T, 128, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+      if (grid >= ntiles) return launch_tiles(djets_blockmul_fwd_tile_kernel<T, 128, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+      return launch_tiles(djets_blockmul_fwd_queue_kernel<T, 128, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
     case 256:
-      if (grid >= ntiles) return launch_tiles(gemv_n_tile_kernel<T, 256, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-      return launch_tiles(gemv_n_kernel<T, 256, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+      if (grid >= ntiles) return launch_tiles(djets_blockmul_fwd_tile_kernel<T, 256, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+      return launch_tiles(djets_blockmul_fwd_queue_kernel<T, 256, POLICY>, grid, (size_t)0, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -1600,9 +1600,9 @@ static cudaError_t launch_gemv_nc_t(int fwd_tx, const DenseTile* tiles, int ntil
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
   switch (fwd_tx) {
-    case 64: return launch_tiles(gemv_n_tile_kernel<T, 64, POLICY, true>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-    case 128: return launch_tiles(gemv_n_tile_kernel<T, 128, POLICY, true>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-    case 256: return launch_tiles(gemv_n_tile_kernel<T, 256, POLICY, true>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    case 64: return launch_tiles(djets_blockmul_fwd_tile_kernel<T, 64, POLICY, true>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    case 128: return launch_tiles(djets_blockmul_fwd_tile_kernel<T, 128, POLICY, true>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    case 256: return launch_tiles(djets_blockmul_fwd_tile_kernel<T, 256, POLICY, true>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -1635,28 +1635,28 @@ static cudaError_t launch_gemv_t_t(int adj_ru, int adj_cw, const DenseTile* tile
   T* o = reinterpret_cast<T*>(out);
   // (rows unrolled, columns per warp): tall columns stream down 4 columns, short ones fan out over 16
   if (adj_cw == 8 && adj_ru == 1) {
-    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 1, 8, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-    return launch_tiles(gemv_t_kernel<T, 1, 8, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    if (grid >= ntiles) return launch_tiles(djets_blockmul_adj_tile_kernel<T, 1, 8, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(djets_blockmul_adj_queue_kernel<T, 1, 8, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
   }
   if (adj_cw == 16 && adj_ru == 1) {
-    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 1, 16, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-    return launch_tiles(gemv_t_kernel<T, 1, 16, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    if (grid >= ntiles) return launch_tiles(djets_blockmul_adj_tile_kernel<T, 1, 16, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(djets_blockmul_adj_queue_kernel<T, 1, 16, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
   }
   if (adj_cw == 8 && adj_ru == 2) {
-    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 2, 8, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-    return launch_tiles(gemv_t_kernel<T, 2, 8, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    if (grid >= ntiles) return launch_tiles(djets_blockmul_adj_tile_kernel<T, 2, 8, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(djets_blockmul_adj_queue_kernel<T, 2, 8, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
   }
   if (adj_cw == 4 && adj_ru == 4) {
-    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 4, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-    return launch_tiles(gemv_t_kernel<T, 4, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    if (grid >= ntiles) return launch_tiles(djets_blockmul_adj_tile_kernel<T, 4, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(djets_blockmul_adj_queue_kernel<T, 4, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
   }
   if (adj_cw == 4 && adj_ru == 2) {
-    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 2, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-    return launch_tiles(gemv_t_kernel<T, 2, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    if (grid >= ntiles) return launch_tiles(djets_blockmul_adj_tile_kernel<T, 2, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(djets_blockmul_adj_queue_kernel<T, 2, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
   }
   if (adj_cw == 4 && adj_ru == 1) {
-    if (grid >= ntiles) return launch_tiles(gemv_t_tile_kernel<T, 1, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-    return launch_tiles(gemv_t_kernel<T, 1, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
+    if (grid >= ntiles) return launch_tiles(djets_blockmul_adj_tile_kernel<T, 1, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+    return launch_tiles(djets_blockmul_adj_queue_kernel<T, 1, 4, POLICY>, grid, kAdjSmemBytes, pf.pdl, stream, tiles, q, i, w, o, ff, pf);
   }
   return cudaErrorInvalidValue;
 }
@@ -1667,8 +1667,8 @@ static cudaError_t launch_gemv_tc_t(int adj_ru, const DenseTile* tiles, int ntil
   const T* i = reinterpret_cast<const T*>(in);
   T* w = reinterpret_cast<T*>(W);
   T* o = reinterpret_cast<T*>(out);
-  if (adj_ru == 1) return launch_tiles(gemv_tc_tile_kernel<T, 1, 8, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
-  return launch_tiles(gemv_tc_tile_kernel<T, 4, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+  if (adj_ru == 1) return launch_tiles(djets_blockmul_adjc_tile_kernel<T, 1, 8, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
+  return launch_tiles(djets_blockmul_adjc_tile_kernel<T, 4, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
 }
 
 cudaError_t launch_gemv_t(int dtype, int adj_ru, int adj_cw, int ld_policy, const DenseTile* tiles, int ntiles,
@@ -1692,7 +1692,7 @@ cudaError_t launch_gemv_t(int dtype, int adj_ru, int adj_cw, int ld_policy, cons
 // ------------------------------------------------------------------------------------------------
 // epoch flags of the cross-process peer-memory exchange
 // ------------------------------------------------------------------------------------------------
-__global__ void flags_wait_kernel(FlagList f, unsigned* err) {
+__global__ void djets_flags_wait_kernel(FlagList f, unsigned* err) {
   const int k = threadIdx.x;
   if (k >= f.n) return;
   unsigned long long t0, t;
@@ -1710,14 +1710,14 @@ __global__ void flags_wait_kernel(FlagList f, unsigned* err) {
   }
 }
 
-__global__ void flags_signal_kernel(FlagList f) {
+__global__ void djets_flags_signal_kernel(FlagList f) {
   const int k = threadIdx.x;
   if (k >= f.n) return;
   __threadfence_system();  // everything this stream stored before (peer stores included) is visible first
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[k]), "r"(f.v[k]) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads) xp_push_kernel(const char* __restrict__ src, size_t bytes, PushList dst,
+__global__ void __launch_bounds__(kThreads) djets_xp_push_kernel(const char* __restrict__ src, size_t bytes, PushList dst,
                                                            FlagList waits, FlagList signals, unsigned* ticket,
                                                            unsigned* err) {
   const int tid = threadIdx.x;
@@ -1766,19 +1766,19 @@ cudaError_t launch_xp_push(const char* src, size_t bytes, const PushList& dst, c
   const size_t nvec = bytes / 16;
   int grid = (int)((nvec + kThreads - 1) / kThreads);
   grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
-  xp_push_kernel<<<grid, kThreads, 0, stream>>>(src, bytes, dst, waits, signals, ticket, err);
+  djets_xp_push_kernel<<<grid, kThreads, 0, stream>>>(src, bytes, dst, waits, signals, ticket, err);
   return cudaGetLastError();
 }
 
 cudaError_t launch_flags_wait(const FlagList& f, unsigned* err, cudaStream_t stream) {
   if (f.n <= 0) return cudaSuccess;
-  flags_wait_kernel<<<1, 32, 0, stream>>>(f, err);
+  djets_flags_wait_kernel<<<1, 32, 0, stream>>>(f, err);
   return cudaGetLastError();
 }
 
 cudaError_t launch_flags_signal(const FlagList& f, cudaStream_t stream) {
   if (f.n <= 0) return cudaSuccess;
-  flags_signal_kernel<<<1, 32, 0, stream>>>(f);
+  djets_flags_signal_kernel<<<1, 32, 0, stream>>>(f);
   return cudaGetLastError();
 }
 
@@ -1796,19 +1796,19 @@ template <typename T, int POLICY>
 static int resident_t(int adjoint, int shape, int adj_cw) {
   if (!adjoint) {
     switch (shape) {
-      case 32: return resident_ctas(gemv_n_kernel<T, 32, POLICY>);
-      case 64: return resident_ctas(gemv_n_kernel<T, 64, POLICY>);
-      case 128: return resident_ctas(gemv_n_kernel<T, 128, POLICY>);
-      case 256: return resident_ctas(gemv_n_kernel<T, 256, POLICY>);
+      case 32: return resident_ctas(djets_blockmul_fwd_queue_kernel<T, 32, POLICY>);
+      case 64: return resident_ctas(djets_blockmul_fwd_queue_kernel<T, 64, POLICY>);
+      case 128: return resident_ctas(djets_blockmul_fwd_queue_kernel<T, 128, POLICY>);
+      case 256: return resident_ctas(djets_blockmul_fwd_queue_kernel<T, 256, POLICY>);
     }
     return 0;
   }
-  if (adj_cw == 8 && shape == 1) return resident_ctas(gemv_t_kernel<T, 1, 8, POLICY>, kAdjSmemBytes);
-  if (adj_cw == 16 && shape == 1) return resident_ctas(gemv_t_kernel<T, 1, 16, POLICY>, kAdjSmemBytes);
-  if (adj_cw == 8 && shape == 2) return resident_ctas(gemv_t_kernel<T, 2, 8, POLICY>, kAdjSmemBytes);
-  if (adj_cw == 4 && shape == 4) return resident_ctas(gemv_t_kernel<T, 4, 4, POLICY>, kAdjSmemBytes);
-  if (adj_cw == 4 && shape == 2) return resident_ctas(gemv_t_kernel<T, 2, 4, POLICY>, kAdjSmemBytes);
-  if (adj_cw == 4 && shape == 1) return resident_ctas(gemv_t_kernel<T, 1, 4, POLICY>, kAdjSmemBytes);
+  if (adj_cw == 8 && shape == 1) return resident_ctas(djets_blockmul_adj_queue_kernel<T, 1, 8, POLICY>, kAdjSmemBytes);
+  if (adj_cw == 16 && shape == 1) return resident_ctas(djets_blockmul_adj_queue_kernel<T, 1, 16, POLICY>, kAdjSmemBytes);
+  if (adj_cw == 8 && shape == 2) return resident_ctas(djets_blockmul_adj_queue_kernel<T, 2, 8, POLICY>, kAdjSmemBytes);
+  if (adj_cw == 4 && shape == 4) return resident_ctas(djets_blockmul_adj_queue_kernel<T, 4, 4, POLICY>, kAdjSmemBytes);
+  if (adj_cw == 4 && shape == 2) return resident_ctas(djets_blockmul_adj_queue_kernel<T, 2, 4, POLICY>, kAdjSmemBytes);
+  if (adj_cw == 4 && shape == 1) return resident_ctas(djets_blockmul_adj_queue_kernel<T, 1, 4, POLICY>, kAdjSmemBytes);
   return 0;
 }
 
@@ -1828,12 +1828,12 @@ cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const 
                           const void* W, const void* R, void* out, cudaStream_t stream) {
   if (nitems <= 0) return cudaSuccess;
   if (real_dtype(dtype) == 0)
-    finish_kernel<float><<<nitems, kThreads, 0, stream>>>(items, diags, reinterpret_cast<const float*>(in),
+    djets_segsum_kernel<float><<<nitems, kThreads, 0, stream>>>(items, diags, reinterpret_cast<const float*>(in),
                                                           reinterpret_cast<const float*>(W),
                                                           reinterpret_cast<const float*>(R),
                                                           reinterpret_cast<float*>(out));
   else
-    finish_kernel<double><<<nitems, kThreads, 0, stream>>>(items, diags, reinterpret_cast<const double*>(in),
+    djets_segsum_kernel<double><<<nitems, kThreads, 0, stream>>>(items, diags, reinterpret_cast<const double*>(in),
                                                            reinterpret_cast<const double*>(W),
                                                            reinterpret_cast<const double*>(R),
                                                            reinterpret_cast<double*>(out));

@@ -30,7 +30,7 @@ struct DiagTerm {
 // Segmented sum of one output chunk: out[out+e] = sum_p W[w0 + p*wstride + e]
 //                                               + sum_q R[r0 + q*rstride + e]     (planes received from peers)
 //                                               + sum_t d_t[e] * in[vin_t + e]    (diagonal blocks)
-// An item is either "loose" (run by finish_kernel) or "fused": the last of the `nplanes` tile CTAs
+// An item is either "loose" (run by djets_segsum_kernel) or "fused": the last of the `nplanes` tile CTAs
 // that contribute to the strip (counted with an atomic ticket) performs the sum inside the GEMV
 // kernel, always in plane order, so the result does not depend on which CTA came last.
 struct FinishItem {
