@@ -406,7 +406,7 @@ int eval_check(const EvalArgs& a, const char** why) {
 // folded into that operator (`... IN k ADD` -> `ADD_IN k`, `... IN k MULS j ADD` -> `AXPY_IN k,j`), which saves the
 // stack shift and a dispatch per operand.  Same arithmetic, same rounding: x*s == s*x and the fused forms round the
 // product and the sum separately.
-static int peephole(const EvalArgs& a, unsigned char* op, unsigned char* arg) {
+int eval_peephole(const EvalArgs& a, unsigned char* op, unsigned char* arg) {
   int n = 0;
   for (int pc = 0; pc < a.nops;) {
     const bool stacked = n > 0;  // something is already on the stack for the operand to combine with
@@ -450,7 +450,7 @@ cudaError_t launch_eval(int ddtype, void* dest, const EvalArgs& a, long long n, 
   EvalDev d;
   bool same = true;
   memset(&d, 0, sizeof(d));
-  d.nops = peephole(a, d.op, d.arg);
+  d.nops = eval_peephole(a, d.op, d.arg);
   for (int k = 0; k < kEvalMaxIn; ++k) {
     d.in[k] = k < a.nin ? a.in[k] : nullptr;
     d.in_dtype[k] = k < a.nin ? a.in_dtype[k] : ddtype;

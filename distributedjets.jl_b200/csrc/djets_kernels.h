@@ -136,6 +136,8 @@ struct EvalArgs {
 };
 // Validates a program; returns its stack depth (>= 1) or -1 with *why set.
 int eval_check(const EvalArgs& a, const char** why);
+// The program after the peephole pass (operands folded into their consumers); returns its length.
+int eval_peephole(const EvalArgs& a, unsigned char* op, unsigned char* arg);
 cudaError_t launch_eval(int ddtype, void* dest, const EvalArgs& a, long long n, int wide, cudaStream_t stream);
 
 // Reductions in one launch.  `partials` holds at least reduce_max_ctas() doubles, `ticket` one unsigned that is

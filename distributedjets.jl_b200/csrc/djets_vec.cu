@@ -807,6 +807,33 @@ int32_t djets_vec_reduce_s(djets_vec x, int32_t kind, double param, djets_scalar
   });
 }
 
+int32_t djets_plan_eval(const uint8_t* program, int32_t nops, int32_t ninputs, int32_t nscalars, int32_t* depth,
+                        int32_t* nops_fused) {
+  return guard([&] {
+    REQUIRE(program && nops >= 1 && nops <= kEvalMaxOps, DJETS_ERR_UNSUPPORTED, "eval: 1 to 48 operations per program");
+    REQUIRE(ninputs >= 0 && ninputs <= kEvalMaxIn && nscalars >= 0 && nscalars <= kEvalMaxScalars, DJETS_ERR_UNSUPPORTED,
+            "eval: at most 8 input vectors and 16 scalars");
+    EvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nops = nops;
+    a.nin = ninputs;
+    a.nsc = nscalars;
+    for (int k = 0; k < nops; ++k) {
+      a.op[k] = program[2 * k];
+      a.arg[k] = program[2 * k + 1];
+    }
+    const char* why = nullptr;
+    const int d0 = eval_check(a, &why);
+    REQUIRE(d0 >= 0, DJETS_ERR_UNSUPPORTED, why ? why : "eval: malformed program");
+    EvalArgs b = a;
+    b.nops = eval_peephole(a, b.op, b.arg);
+    const int d1 = eval_check(b, &why);
+    REQUIRE(d1 >= 0, DJETS_ERR_INVALID, "eval: the peephole pass produced a malformed program");
+    if (depth) *depth = d1;
+    if (nops_fused) *nops_fused = b.nops;
+  });
+}
+
 // ---- the closed elementwise program (src:363-375) --------------------------------------------------------------
 int32_t djets_vec_eval(djets_vec dest, const uint8_t* program, int32_t nops, const djets_vec* inputs, int32_t ninputs,
                        const double* scalars, const djets_scalar* dscalars, int32_t nscalars, int32_t flags) {

@@ -115,6 +115,11 @@ int32_t djets_plan_tiles(int32_t dtype, int64_t m, int64_t n, int32_t adjoint, i
 int32_t djets_plan_exchange(int32_t n1, int32_t n2, int32_t isdiag, int32_t adjoint, int32_t phase, int32_t* out6,
                             int32_t capacity, int32_t* count);
 
+/* Validates an elementwise program for djets_vec_eval without a device: stack depth it needs, and the number of
+ * operations left after the peephole pass that folds pushed operands into their consumers. */
+int32_t djets_plan_eval(const uint8_t* program, int32_t nops, int32_t ninputs, int32_t nscalars, int32_t* depth,
+                        int32_t* nops_fused);
+
 /* ---- context ------------------------------------------------------------------------------ */
 int32_t djets_device_count(int32_t* n);
 /* 128-byte NCCL unique id, to be generated on one process and handed to every process'

@@ -174,3 +174,52 @@ def test_plain_c_client_on_gpu(dj, tmp_path):
     exe = _build_c_client(tmp_path)
     out = subprocess.run([exe, dj.LIB_PATH], capture_output=True, text=True)
     assert out.returncode == 0 and "c abi ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_broadcast_lowering_without_a_device(dj):
+    """The Python mirror lowers lazy expressions to the postfix program of djets_vec_eval; the library validates it and
+    runs its peephole pass on the host (djets_plan_eval): no GPU involved.  Vectors are stand-ins (only identity and
+    dtype matter to the lowering)."""
+    import ctypes as C
+    import numpy as np
+    from djets_b200 import _lib as L, core
+
+    class FakeVec:
+        def __init__(self, dtype):
+            self.dtype = np.dtype(dtype)
+            self.h = None
+    x, y, z = (core.Expr("in", FakeVec(np.float64)) for _ in range(3))
+
+    def plan(expr):
+        prog, vecs, scal, dscal, f64 = core._lower(expr)
+        buf = (C.c_uint8 * len(prog))(*prog)
+        depth, fused = C.c_int32(), C.c_int32()
+        L.call("djets_plan_eval", buf, len(prog) // 2, len(vecs), len(scal), C.byref(depth), C.byref(fused))
+        return prog, len(vecs), scal, depth.value, fused.value
+
+    # benchmark/benchmarks.jl:43  d4 .= a1*d1 .+ a2*d2 .- a3*d3: 8 operations, 4 after the operands are folded in
+    prog, nin, scal, depth, fused = plan(0.3 * x + 0.5 * y - 0.7 * z)
+    assert nin == 3 and scal == [0.3, 0.5, 0.7] and len(prog) // 2 == 8 and fused == 4 and depth == 1
+    assert prog[:4] == [L.EV_IN, 0, L.EV_RMULS, 0] and prog[-2] == L.EV_SUB
+    # x.^2, x.^3 are products (Julia's literal_pow); other powers call pow
+    assert plan(x ** 2)[0] == [L.EV_IN, 0, L.EV_SQUARE, 0] and plan(x ** 3)[0][2] == L.EV_CUBE
+    assert plan(x ** 1.5)[0][2] == L.EV_POWS
+    # scalar on the left of a non-commutative operator
+    assert plan(2.0 - x)[0] == [L.EV_IN, 0, L.EV_RSUBS, 0] and plan(2.0 / x)[0][2] == L.EV_RDIVS
+    # the same vector is one input however often it appears; scalars fold like Julia's per-element arithmetic
+    prog, nin, scal, depth, fused = plan((x * x + x) * (2.0 * 3.0))
+    assert nin == 1 and scal == [6.0]
+    # depth grows with parenthesised right operands, never past the limit silently
+    deep = x
+    for _ in range(3):
+        deep = y * (z + deep)
+    assert plan(deep)[3] >= 2
+    import pytest
+    too_long = x
+    for _ in range(30):
+        too_long = too_long * y + z
+    with pytest.raises(dj.DJetsError):
+        plan(too_long)
+    with pytest.raises(dj.DJetsError):                      # malformed programs are refused
+        buf = (C.c_uint8 * 2)(L.EV_ADD, 0)
+        L.call("djets_plan_eval", buf, 1, 0, 0, None, None)
