@@ -330,11 +330,11 @@ __device__ __forceinline__ bool finish_item_diag_vec(const FinishItem& it, const
   return true;
 }
 
-template <typename T, bool COHERENT>
+template <typename T, bool COHERENT, bool CPLX = false>
 __device__ __forceinline__ void finish_item(const FinishItem& it, const DiagTerm* __restrict__ diags,
                                             const T* __restrict__ in, const T* W, const T* __restrict__ R,
                                             T* __restrict__ out) {
-  if (it.flags & 1) {  // complex: elements are (re, im) pairs of T; planes add component-wise, diagonal terms multiply as complex
+  if (CPLX) {  // complex: elements are (re, im) pairs of T; planes add component-wise, diagonal terms multiply as complex
     const bool conj = (it.flags & 2) != 0;
     for (int e = 2 * threadIdx.x; e < it.len; e += 2 * kThreads) {
       double sr = 0.0, si = 0.0;
@@ -391,7 +391,7 @@ __device__ __forceinline__ void finish_item(const FinishItem& it, const DiagTerm
 
 // Ticket protocol of a fused strip: every contributing CTA publishes its plane (fence), takes a
 // ticket, and the CTA holding the last ticket sums all planes and rearms the ticket for the next apply.
-template <typename T>
+template <typename T, bool CPLX = false>
 __device__ __forceinline__ void fused_finish(int fin, const FusedFinish& ff, const T* __restrict__ in,
                                              const T* W, T* __restrict__ out) {
   __shared__ int s_last;
@@ -404,7 +404,7 @@ __device__ __forceinline__ void fused_finish(int fin, const FusedFinish& ff, con
   __syncthreads();
   if (s_last) {
     __threadfence();
-    finish_item<T, true>(ff.items[fin], ff.diags, in, W, nullptr, out);
+    finish_item<T, true, CPLX>(ff.items[fin], ff.diags, in, W, nullptr, out);
     if (threadIdx.x == 0) ff.tickets[fin] = 0u;
   }
 }
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 4) djets_blockmul_fwd_tile_kernel(co
     for (int k = 0; k < VEC; ++k)
       if (r0 + k < rows) dst[r0 + k] = acc[k];
   }
-  if (t.fin >= 0) fused_finish<T>(t.fin, ff, in, W, out);
+  if (t.fin >= 0) fused_finish<T, CPLX>(t.fin, ff, in, W, out);
   trace_stamp(pf.trace, blockIdx.x, 3);
 }
 
@@ -933,7 +933,7 @@ __global__ void __launch_bounds__(kThreads, 2) djets_blockmul_adjc_tile_kernel(c
     const bool writer = (lane & ((32 >> kHalvings) - 1)) == 0;
     if (writer && 2 * c0 + mycol < 2 * cols) dst[2 * c0 + mycol] = acc[0];
   }
-  if (t.fin >= 0) fused_finish<T>(t.fin, ff, in, W, out);
+  if (t.fin >= 0) fused_finish<T, true>(t.fin, ff, in, W, out);
 }
 
 template <typename T, int RU, int CW, int POLICY>
@@ -1128,12 +1128,12 @@ __global__ void __launch_bounds__(kThreads, 2) djets_blockmul_adj_queue_kernel(c
 
 // Loose items: block rows / columns with no dense tile on this rank (diagonal-only: the fused
 // streaming `d .= diag .* m`), and every item of a rank that also sums planes received from peers.
-template <typename T>
+template <typename T, bool CPLX>
 __global__ void __launch_bounds__(kThreads) djets_segsum_kernel(const FinishItem* __restrict__ items,
-                                                          const DiagTerm* __restrict__ diags,
-                                                          const T* __restrict__ in, const T* __restrict__ W,
-                                                          const T* __restrict__ R, T* __restrict__ out) {
-  finish_item<T, false>(items[blockIdx.x], diags, in, W, R, out);
+                                                                const DiagTerm* __restrict__ diags,
+                                                                const T* __restrict__ in, const T* __restrict__ W,
+                                                                const T* __restrict__ R, T* __restrict__ out) {
+  finish_item<T, false, CPLX>(items[blockIdx.x], diags, in, W, R, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1827,16 +1827,16 @@ int gemv_resident_ctas(int dtype, int adjoint, int shape, int adj_cw, int ld_pol
 cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,
                           const void* W, const void* R, void* out, cudaStream_t stream) {
   if (nitems <= 0) return cudaSuccess;
-  if (real_dtype(dtype) == 0)
-    djets_segsum_kernel<float><<<nitems, kThreads, 0, stream>>>(items, diags, reinterpret_cast<const float*>(in),
-                                                          reinterpret_cast<const float*>(W),
-                                                          reinterpret_cast<const float*>(R),
-                                                          reinterpret_cast<float*>(out));
-  else
-    djets_segsum_kernel<double><<<nitems, kThreads, 0, stream>>>(items, diags, reinterpret_cast<const double*>(in),
-                                                           reinterpret_cast<const double*>(W),
-                                                           reinterpret_cast<const double*>(R),
-                                                           reinterpret_cast<double*>(out));
+#define DJ_SEGSUM(T, C)                                                                                      \
+  djets_segsum_kernel<T, C><<<nitems, kThreads, 0, stream>>>(items, diags, reinterpret_cast<const T*>(in), \
+                                                             reinterpret_cast<const T*>(W),                \
+                                                             reinterpret_cast<const T*>(R), reinterpret_cast<T*>(out))
+  if (real_dtype(dtype) == 0) {
+    if (is_complex(dtype)) DJ_SEGSUM(float, true); else DJ_SEGSUM(float, false);
+  } else {
+    if (is_complex(dtype)) DJ_SEGSUM(double, true); else DJ_SEGSUM(double, false);
+  }
+#undef DJ_SEGSUM
   return cudaGetLastError();
 }
 

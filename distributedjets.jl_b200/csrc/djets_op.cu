@@ -313,6 +313,38 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     plan.fwd_tx = (int)fwd_tx;
   }
   plan.wave = gemv_resident_ctas(op->dtype, adjoint ? 1 : 0, adjoint ? adj_ru : (int)fwd_tx, adj_cw, (int)op->p_ld_policy);
+  // Wave fit: a tile count between one and two resident waves leaves the second wave part empty and its CTAs finish
+  // one by one (profiles/r02_trace_boundary_8blocks.txt).  If slightly larger tiles bring the whole cell into ONE wave,
+  // take them (0.5 GiB shard of the bench operator: 1024 -> 512 forward tiles, 512 -> 296 adjoint tiles, -1 % per step).
+  if (ctx->auto_tile && ctx->wave_fit && plan.wave > 0) {
+    auto count_tiles = [&](int64_t ftc, int64_t atc) {
+      int64_t nt = 0;
+      for (int64_t i = r0; i < r1; ++i)
+        for (int64_t j = c0; j < c1; ++j) {
+          if (op->isdiag && i != j) continue;
+          if (op->block(i, j).kind != DJETS_BLOCK_DENSE) continue;
+          nt += plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, fwd_tx, ftc, atc).ntiles;
+        }
+      return nt;
+    };
+    const int64_t nt0 = count_tiles(eff_fwd_tc, eff_adj_tc);
+    if (nt0 > plan.wave && 10 * nt0 <= 16 * (int64_t)plan.wave) {  // second wave less than 60 % full
+      if (!adjoint) {
+        for (int64_t tc = eff_fwd_tc + 64; tc <= kFwdMaxTC / cs; tc += 64)
+          if (count_tiles(tc, eff_adj_tc) <= plan.wave) {
+            eff_fwd_tc = tc;
+            break;
+          }
+      } else {
+        const int64_t step = adj_cw == kAdjCW ? 16 : 8 * adj_cw;
+        for (int64_t tc = eff_adj_tc + step; tc <= 2 * eff_adj_tc; tc += step)
+          if (count_tiles(eff_fwd_tc, tc) <= plan.wave) {
+            eff_adj_tc = tc;
+            break;
+          }
+      }
+    }
+  }
   std::vector<DenseTile> tiles;
   std::vector<FinishItem> loose, fused;
   std::vector<int64_t> loose_key;  // offset of the item's chunk inside its block: the launch order of the loose items
