@@ -133,11 +133,38 @@ if args.cgls:
     barrier()
     per_iter = reduce_max((time.perf_counter() - t0) / iters)
     drop = float(r.norm()) / r0
+    # the same iteration with device-resident scalars: no host round trip (the dots are all-reduced in stream order)
+    L = dj.lazy
+    SC = sys.modules["djets_b200._lib"]
+    g, g2s, dl, al, be = (dj.Scalar(1.0, dt, ctx) for _ in range(5))
+    s_.dot_s(s_, g)
+
+    def device_iter():
+        A.mul(q, p)
+        q.dot_s(q, dl)
+        al.assign(SC.SC_DIV, g, dl)
+        sol.assign(L(sol) + al * L(p))
+        r.assign(L(r) - al * L(q))
+        A.mul_adjoint(s_, r)
+        s_.dot_s(s_, g2s)
+        be.assign(SC.SC_DIV, g2s, g)
+        p.assign(L(s_) + be * L(p))
+        g.assign(SC.SC_COPY, g2s)
+    for _ in range(3):
+        device_iter()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        device_iter()
+    barrier()
+    per_iter_dev = reduce_max((time.perf_counter() - t0) / iters)
     if rank == 0:
         print(json.dumps({"config": 5, "grid": [n1, n2], "n_gpus": world, "mode": "one process" if dist is None else "spmd+nccl",
                           "blocks": [nb, nb], "block": [bs, bs], "bytes_per_apply": nbytes, "forward_ms": tf, "adjoint_ms": ta,
                           "GBps_forward": nbytes / tf / 1e6, "GBps_adjoint": nbytes / ta / 1e6,
                           "cgls_iteration_ms": per_iter * 1e3, "cgls_GBps": 2 * nbytes / per_iter / 1e9,
+                          "cgls_iteration_device_scalars_ms": per_iter_dev * 1e3,
+                          "cgls_device_scalars_GBps": 2 * nbytes / per_iter_dev / 1e9,
                           "residual_drop_after_10_iters": drop}), flush=True)
     if dist is not None:
         dist.barrier()

@@ -49,7 +49,13 @@ res = {"config": 4, "n_gpus": world, "n": n,
        "sum_relerr": abs(float(x.sum()) - want_sum) / want_sum,
        "dot_relerr": abs(float(x.dot(y)) - 2 * want_sum) / (2 * want_sum),
        "norm_ok": bool(float(x.norm(math.inf)) == float(nb + ramp[-1]) and float(y.norm(2)) == math.sqrt(4.0 * n))}
+sc = dj.Scalar(0.0, np.float64, ctx)
+L = dj.lazy
 for name, fn, nbytes in (("dot", lambda: x.dot(y), 2 * n * 8), ("norm2", lambda: x.norm(2), n * 8),
+                         ("norm2 again", lambda: x.norm(2), n * 8), ("dot again", lambda: x.dot(y), 2 * n * 8),
+                         ("dot_s (device-resident, all-reduced in stream order)", lambda: x.dot_s(y, sc), 2 * n * 8),
+                         ("norm_s", lambda: x.norm_s(2, sc), n * 8),
+                         ("eval abs.(x) .* y .+ 1", lambda: out.assign(abs(L(x)) * L(y) + 1.0), 3 * n * 8),
                          ("axpy", lambda: y.lincomb_([0.5, 1.0], [x, y]), 3 * n * 8),
                          ("sum3", lambda: out.lincomb_([0.1, 0.2, 0.3], [x, y, z]), 4 * n * 8)):
     ms = timed(fn)
