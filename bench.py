@@ -599,7 +599,7 @@ def quiet_stdout():
     return os.fdopen(keep, "w")
 
 
-TUNABLES = ("fwd_tx", "fwd_tc", "adj_ru", "adj_tc", "ld_policy", "pdl", "graphs", "p2p", "auto_tile", "prefetch", "ipc", "wave_fit",
+TUNABLES = ("fwd_tx", "fwd_tc", "adj_ru", "adj_tc", "ld_policy", "pdl", "graphs", "p2p", "auto_tile", "prefetch", "ipc", "wave_fit", "l2_keep",
             "persistent")
 
 

@@ -675,6 +675,9 @@ int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
     } else if (n == "prefetch") {
       REQUIRE(value >= 0 && value <= (1 << 20), DJETS_ERR_INVALID, "prefetch in 0..1048576 bytes");
       ctx->prefetch = value;
+    } else if (n == "l2_keep") {
+      REQUIRE(value >= 0 && value <= 120, DJETS_ERR_INVALID, "l2_keep in 0..120 MB");
+      ctx->l2_keep = value;
     } else if (n == "wave_fit") {
       REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "wave_fit in {0,1}");
       ctx->wave_fit = value;

@@ -42,6 +42,15 @@ __device__ __forceinline__ uint64_t make_evict_first_policy() {
   return pol;
 }
 
+__device__ __forceinline__ uint64_t make_evict_last_policy() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// Streaming tiles are tagged evict-first; the last tiles of a launch evict-last, so that the next apply of the operator
+// (which walks the tiles in the opposite order) finds them in L2.
+__device__ __forceinline__ uint64_t tile_policy(int keep) { return keep ? make_evict_last_policy() : make_evict_first_policy(); }
+
 template <int POLICY>
 __device__ __forceinline__ float4 ld_stream(const float4* p, uint64_t pol) {
   float4 r;
@@ -436,7 +445,7 @@ __global__ void __launch_bounds__(kThreads, 4) djets_blockmul_fwd_tile_kernel(co
   const int rows = t.rows, cols = t.cols;
 
   uint64_t pol = 0;
-  if (POLICY == 1) pol = make_evict_first_policy();
+  if (POLICY == 1) pol = tile_policy(t.keep);
 
   const int tx = tid % TX, ty = tid / TX;
   const int r0 = tx * VEC;
@@ -564,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, (RU * CW <= 8) ? 3 : 2) djets_blockm
   trace_stamp(pf.trace, blockIdx.x, 2);
 
   uint64_t pol = 0;
-  if (POLICY == 1) pol = make_evict_first_policy();
+  if (POLICY == 1) pol = tile_policy(t.keep);
 
   const long long ld = t.ld;
   const T* A = reinterpret_cast<const T*>(t.A);
@@ -858,7 +867,7 @@ __global__ void __launch_bounds__(kThreads, 2) djets_blockmul_adjc_tile_kernel(c
   stage_vector<T>(ys, in + t.vin, rows, rowsv, &bar);
 
   uint64_t pol = 0;
-  if (POLICY == 1) pol = make_evict_first_policy();
+  if (POLICY == 1) pol = tile_policy(t.keep);
 
   const long long ld = t.ld;
   const T* A = reinterpret_cast<const T*>(t.A);

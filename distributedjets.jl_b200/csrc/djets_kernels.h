@@ -19,6 +19,9 @@ struct DenseTile {
   int rows, cols;     // tile extents
   int direct;
   int fin;            // >= 0: finish item this tile's strip belongs to (fused segmented sum), else -1
+  int keep;           // 1: one of the last tiles of the launch -- loaded with an L2 evict-last hint, because the next
+                      // apply of the operator (the other direction) starts with exactly these tiles
+  int pad_;
 };
 
 // One term of a diagonal block inside a finish item: out[e] += d[e] * in[vin + e].

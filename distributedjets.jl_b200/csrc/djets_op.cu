@@ -477,6 +477,22 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     for (size_t k : order) sorted.push_back(loose[k]);
     loose.swap(sorted);
   }
+  // L2 hand-over between consecutive applies.  A solver alternates mul!(d, A, m) and mul!(m, A', d): the forward walks
+  // the cell's blocks in ascending order, the adjoint in DESCENDING order, so each launch starts on the tiles the
+  // previous one finished with; those last `l2_keep` MB are loaded evict-last (everything else evict-first), and the
+  // next launch finds them in the 126 MB L2 instead of HBM.
+  for (DenseTile& t : tiles) {
+    t.keep = 0;
+    t.pad_ = 0;
+  }
+  if (ctx->l2_keep > 0) {
+    if (adjoint) std::reverse(tiles.begin(), tiles.end());
+    int64_t budget = ctx->l2_keep << 20;
+    for (size_t k = tiles.size(); k-- > 0 && budget > 0;) {
+      tiles[k].keep = 1;
+      budget -= (int64_t)tiles[k].rows * tiles[k].cols * (es / cs);
+    }
+  }
   // loose items first, fused items after them; tiles index the concatenated table
   const int nloose = (int)loose.size();
   for (DenseTile& t : tiles)

@@ -14,7 +14,7 @@ dj = djets_loader.load()
 nblk = int(sys.argv[1])
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 settings = sys.argv[3:] or ["prefetch=0", "prefetch=65536"]
-DEFAULTS = {"persistent": 0, "wave_fit": 1, "auto_tile": 1, "fwd_tc": 512, "adj_tc": 64, "fwd_tx": 64, "adj_ru": 4, "prefetch": 32768, "pdl": 1,
+DEFAULTS = {"persistent": 0, "l2_keep": 96, "wave_fit": 1, "auto_tile": 1, "fwd_tc": 512, "adj_tc": 64, "fwd_tx": 64, "adj_ru": 4, "prefetch": 32768, "pdl": 1,
             "ld_policy": 1}
 ctx = dj.init(world=1, devices=[0])
 rng = np.random.default_rng(0)
