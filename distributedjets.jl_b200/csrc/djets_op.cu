@@ -12,7 +12,8 @@ struct Block {
 };
 
 struct DirPlan {
-  DenseTile* d_tiles = nullptr;
+  DenseTile* d_tiles = nullptr;      // tiles in ascending block order ...
+  DenseTile* d_tiles_rev = nullptr;  // ... and the same tiles in descending order (L2 hand-over, see build_plan)
   int ntiles = 0;
   FinishItem* d_items = nullptr;  // loose items first (finish_kernel), then the fused ones
   int nitems = 0, nloose = 0;
@@ -34,6 +35,7 @@ struct DirPlan {
 struct Cell {
   int r = 0, c = 0, rank = 0;
   DirPlan fwd, adj;
+  bool at_end = false;  // the cell's previous tile launch (either direction) ended on its LAST blocks: the next walks backwards
   cudaEvent_t pt0 = nullptr, pt1 = nullptr;  // perfstat: bracket of this cell's work in the last apply
   bool ptimed = false;
 };
@@ -148,6 +150,7 @@ void run_transfers(djets_ctx ctx, const std::vector<Transfer>& ts) {
 // peer may still hold them mapped; they are freed with the context.
 void free_plan(DirPlan& p, std::vector<void*>* keep = nullptr) {
   cudaFree(p.d_tiles);
+  cudaFree(p.d_tiles_rev);
   cudaFree(p.d_items);
   cudaFree(p.d_tickets);
   cudaFree(p.d_counter);
@@ -346,6 +349,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     }
   }
   std::vector<DenseTile> tiles;
+  std::vector<int64_t> tile_key;  // block (i, j) of every tile, row-major: both directions walk the blocks in this order
   std::vector<FinishItem> loose, fused;
   std::vector<int64_t> loose_key;  // offset of the item's chunk inside its block: the launch order of the loose items
   std::vector<DiagTerm> diags;
@@ -440,6 +444,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
             t.wout = cs * (direct ? out_off[o] + row0 : wbase + (plane + p) * olen + row0);
             t.fin = fuse ? fused_first + (int)(row0 / strip) : -1;
             tiles.push_back(t);
+            tile_key.push_back(i * op->nbcol + j);
           }
         }
       } else {
@@ -455,6 +460,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
             t.wout = cs * (direct ? out_off[o] + col0 : wbase + (plane + p) * olen + col0);
             t.fin = fuse ? fused_first + (int)(col0 / strip) : -1;
             tiles.push_back(t);
+            tile_key.push_back(i * op->nbcol + j);
           }
         }
       }
@@ -477,32 +483,44 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     for (size_t k : order) sorted.push_back(loose[k]);
     loose.swap(sorted);
   }
-  // L2 hand-over between consecutive applies.  A solver alternates mul!(d, A, m) and mul!(m, A', d): the forward walks
-  // the cell's blocks in ascending order, the adjoint in DESCENDING order, so each launch starts on the tiles the
-  // previous one finished with; those last `l2_keep` MB are loaded evict-last (everything else evict-first), and the
-  // next launch finds them in the 126 MB L2 instead of HBM.
-  for (DenseTile& t : tiles) {
-    t.keep = 0;
-    t.pad_ = 0;
+  // L2 hand-over between consecutive applies.  A solver alternates mul!(d, A, m) and mul!(m, A', d) (or repeats one of
+  // them): both directions list their tiles in the same block order, every launch walks the table in the direction
+  // opposite to the cell's previous launch -- it starts on the blocks that launch finished with -- and the last
+  // `l2_keep` MB of a walk are loaded evict-last (everything else evict-first), so the next launch finds them in the
+  // 126 MB L2 instead of HBM.
+  {
+    std::vector<size_t> order(tiles.size());
+    for (size_t k = 0; k < order.size(); ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tile_key[a] < tile_key[b]; });
+    std::vector<DenseTile> sorted;
+    sorted.reserve(tiles.size());
+    for (size_t k : order) sorted.push_back(tiles[k]);
+    tiles.swap(sorted);
   }
-  if (ctx->l2_keep > 0) {
-    if (adjoint) std::reverse(tiles.begin(), tiles.end());
+  std::vector<DenseTile> tiles_rev(tiles.rbegin(), tiles.rend());
+  for (std::vector<DenseTile>* table : {&tiles, &tiles_rev}) {
     int64_t budget = ctx->l2_keep << 20;
-    for (size_t k = tiles.size(); k-- > 0 && budget > 0;) {
-      tiles[k].keep = 1;
-      budget -= (int64_t)tiles[k].rows * tiles[k].cols * (es / cs);
+    for (DenseTile& t : *table) {
+      t.keep = 0;
+      t.pad_ = 0;
+    }
+    for (size_t k = table->size(); k-- > 0 && budget > 0;) {
+      (*table)[k].keep = 1;
+      budget -= (int64_t)(*table)[k].rows * (*table)[k].cols * (es / cs);
     }
   }
   // loose items first, fused items after them; tiles index the concatenated table
   const int nloose = (int)loose.size();
-  for (DenseTile& t : tiles)
-    if (t.fin >= 0) t.fin += nloose;
+  for (std::vector<DenseTile>* table : {&tiles, &tiles_rev})
+    for (DenseTile& t : *table)
+      if (t.fin >= 0) t.fin += nloose;
   std::vector<FinishItem> items(loose);
   items.insert(items.end(), fused.begin(), fused.end());
   plan.nloose = nloose;
   plan.ntiles = (int)tiles.size();
   plan.nitems = (int)items.size();
   plan.d_tiles = upload(tiles);
+  plan.d_tiles_rev = ctx->l2_keep > 0 ? upload(tiles_rev) : nullptr;
   plan.d_items = upload(items);
   plan.d_tickets = reinterpret_cast<unsigned*>(dalloc(items.size() * sizeof(unsigned)));
   plan.d_counter = reinterpret_cast<unsigned*>(dalloc(sizeof(unsigned)));
@@ -718,6 +736,13 @@ void perfstat_mark(djets_op op, bool begin) {
 
 int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint);
 
+// The tile table of a cell's next launch: opposite to the walk of its previous launch (L2 hand-over).
+const DenseTile* walk(Cell& cell, const DirPlan& plan) {
+  const bool backwards = cell.at_end && plan.d_tiles_rev;
+  cell.at_end = !backwards && plan.d_tiles_rev != nullptr;
+  return backwards ? plan.d_tiles_rev : plan.d_tiles;
+}
+
 // CTAs launched for a cell's tile kernel: one resident wave that walks the tile table (persistent), or one
 // CTA per tile.
 int tile_grid(djets_ctx ctx, const DirPlan& plan) {
@@ -848,12 +873,12 @@ int apply_enqueue_xp(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
     const FusedFinish ff{plan.d_items, plan.d_diags, plan.d_tickets};
     if (!adjoint)
       launch_counted(ctx, rc, DJETS_K_GEMV_N, [&] {
-        return launch_gemv_n(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles, tile_grid(ctx, plan),
+        return launch_gemv_n(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, walk(cell, plan), plan.ntiles, tile_grid(ctx, plan),
                              plan.d_counter, inp, plan.W, outp, ff, pf, rc.stream);
       });
     else
       launch_counted(ctx, rc, DJETS_K_GEMV_T, [&] {
-        return launch_gemv_t(op->dtype, plan.adj_ru, plan.adj_cw, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles,
+        return launch_gemv_t(op->dtype, plan.adj_ru, plan.adj_cw, (int)op->p_ld_policy, walk(cell, plan), plan.ntiles,
                              tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, ff, pf, rc.stream);
       });
   }
@@ -963,7 +988,7 @@ int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
         ++nops;
         if (!adjoint)
           launch_counted(ctx, *rc, DJETS_K_GEMV_N, [&] {
-            return launch_gemv_n(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles,
+            return launch_gemv_n(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, walk(cell, plan), plan.ntiles,
                                  tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets},
                                  Prefetch{plan.wave, (int)ctx->prefetch, (int)ctx->pdl,
                                           trace_slot(*rc, DJETS_K_GEMV_N, plan.ntiles), {nullptr, nullptr}, {0u, 0u}, 0, nullptr},
@@ -971,7 +996,7 @@ int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
           });
         else
           launch_counted(ctx, *rc, DJETS_K_GEMV_T, [&] {
-            return launch_gemv_t(op->dtype, plan.adj_ru, plan.adj_cw, (int)op->p_ld_policy, plan.d_tiles, plan.ntiles,
+            return launch_gemv_t(op->dtype, plan.adj_ru, plan.adj_cw, (int)op->p_ld_policy, walk(cell, plan), plan.ntiles,
                                  tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets},
                                  Prefetch{plan.wave, (int)ctx->prefetch, (int)ctx->pdl,
                                           trace_slot(*rc, DJETS_K_GEMV_T, plan.ntiles), {nullptr, nullptr}, {0u, 0u}, 0, nullptr},
