@@ -681,6 +681,9 @@ int32_t djets_ctx_set_param(djets_ctx ctx, const char* name, int64_t value) {
     } else if (n == "wave_fit") {
       REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "wave_fit in {0,1}");
       ctx->wave_fit = value;
+    } else if (n == "chain") {
+      REQUIRE(value >= 0 && value <= kChainMax, DJETS_ERR_INVALID, "chain in 0..16");
+      ctx->chain = value;
     } else if (n == "adj_light") {
       REQUIRE(value == 0 || value == 1, DJETS_ERR_INVALID, "adj_light in {0,1}");
       ctx->adj_light = value;

@@ -132,6 +132,7 @@ struct djets_ctx_s {
   bool timing = false;
   int64_t fwd_tx = 64, fwd_tc = 512, adj_ru = 4, adj_tc = 64, ld_policy = 1;
   int64_t adj_light = 1;  // adjoint of blocks with very short columns: (RU,CW) = (1,8) variant at three CTAs per SM
+  int64_t chain = 0;  // small blocks: blocks per chained tile (0 = sized by the planner, 1 = off, k = forced)
   int64_t l2_keep = 96;   // MB of a cell's last tiles loaded evict-last, for the next apply (which walks the tiles the other way round); 0: off
   int64_t wave_fit = 1;   // auto_tile: grow the tiles of a cell that would need between one and two resident waves into one wave
   int64_t auto_tile = 1;  // shrink tiles of small operators so a launch still fills the SMs

@@ -687,6 +687,246 @@ __global__ void __launch_bounds__(kThreads, (RU * CW <= 8) ? 3 : 2) djets_blockm
 }
 
 // ------------------------------------------------------------------------------------------------
+// Adjoint over chains of small blocks (every block at most 2 warp-loads tall: 128 Float64 / 256 Float32 rows).
+// A tile is a head block plus up to kChainMax-1 further blocks of the same block column (ChainLink); a warp owns CW
+// columns and walks down the chain with them, 2*CW 128-bit loads in flight per lane -- the two row chunks of one
+// block, or (PAIR: blocks of one warp-load) the single chunks of two blocks -- and reduces / stores once per chain.
+// The first batch is issued before the dependency wait and the staging of the y slices (plain coalesced loads into
+// zero-padded shared-memory rows, one per block), so the fixed costs of a CTA (descriptor, staging, ticket) are paid
+// once per chain and overlap its first loads.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CW, int POLICY>
+__device__ __forceinline__ void chain_load_slot(typename VecT<T>::type (&a)[CW], const T* base, long long ld, int last,
+                                                bool ok, uint64_t pol) {
+  using V = typename VecT<T>::type;
+#pragma unroll
+  for (int k = 0; k < CW; ++k) {
+    if (ok)
+      a[k] = ld_stream<POLICY>(reinterpret_cast<const V*>(base + (long long)min(k, last) * ld), pol);
+    else
+      a[k] = V{};
+  }
+}
+
+template <typename T, int CW, bool PAIR, int POLICY>
+__global__ void __launch_bounds__(kThreads, 2) djets_blockmul_adj_chain_kernel(const DenseTile* __restrict__ tiles,
+                                                                               const ChainLink* __restrict__ links,
+                                                                               const T* __restrict__ in, T* W,
+                                                                               T* __restrict__ out, FusedFinish ff,
+                                                                               Prefetch pf) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  constexpr int S = 32 * VEC;
+  constexpr int YS = PAIR ? S : 2 * S;  // one zero-padded row of shared memory per block of the chain
+  __shared__ __align__(16) T ys[kChainMax * YS];
+  __shared__ ChainLink sl[kChainMax];
+
+  griddep_launch_dependents();
+  trace_stamp(pf.trace, blockIdx.x, 0);
+  const DenseTile t = tiles[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cols = t.cols, nblk = 1 + t.chain;
+  const int ngroups = (cols + CW - 1) / CW;
+  uint64_t pol = 0;
+  if (POLICY == 1) pol = tile_policy(t.keep);
+
+  // slot u of a batch: row chunk u of block l, or (PAIR) the only chunk of block l + u
+  V a[2][CW];
+  auto load_batch = [&](int c0, const void* A0, long long ld0, int n0, const void* A1, long long ld1, int n1) {
+    const int last = cols - 1 - c0;
+    const T* base = reinterpret_cast<const T*>(A0) + (long long)c0 * ld0 + lane * VEC;
+    chain_load_slot<T, CW, POLICY>(a[0], base, ld0, last, lane * VEC < n0, pol);
+    if (PAIR)  // n1 == 0: there is no second block
+      chain_load_slot<T, CW, POLICY>(a[1], reinterpret_cast<const T*>(A1) + (long long)c0 * ld1 + lane * VEC, ld1, last,
+                                     lane * VEC < n1, pol);
+    else
+      chain_load_slot<T, CW, POLICY>(a[1], base + S, ld0, last, S + lane * VEC < n0, pol);
+  };
+  // the first batch goes out before anything else is looked at (payloads and tables are immutable)
+  const bool pre = warp < ngroups;
+  if (pre) {
+    const void* A1 = t.A;
+    long long ld1 = t.ld;
+    int n1 = 0;
+    if (PAIR && t.chain > 0) {
+      A1 = links[t.link0].A;
+      ld1 = links[t.link0].ld;
+      n1 = links[t.link0].n;
+    }
+    load_batch(warp * CW, t.A, t.ld, t.rows, A1, ld1, n1);
+  }
+  if (tid == 0) sl[0] = ChainLink{t.A, t.ld, t.vin, t.rows, 0};
+  for (int l = tid; l < t.chain; l += kThreads) sl[1 + l] = links[t.link0 + l];
+  griddep_wait();
+  wait_epoch_flags(pf);
+  __syncthreads();
+  trace_stamp(pf.trace, blockIdx.x, 1);
+  for (int idx = tid; idx < nblk * YS; idx += kThreads) {
+    const int l = idx / YS, e = idx % YS;
+    ys[idx] = e < sl[l].n ? in[sl[l].vin + e] : T(0);
+  }
+  __syncthreads();
+  trace_stamp(pf.trace, blockIdx.x, 2);
+
+  T* dst = (t.direct ? out : W) + t.wout;
+  for (int g = warp; g < ngroups; g += kThreads / 32) {
+    const int c0 = g * CW;
+    T acc[CW];
+#pragma unroll
+    for (int k = 0; k < CW; ++k) acc[k] = T(0);
+    for (int l = 0; l < nblk; l += PAIR ? 2 : 1) {
+      if (!(l == 0 && g == warp)) {
+        const int l1 = (PAIR && l + 1 < nblk) ? l + 1 : l;
+        load_batch(c0, sl[l].A, sl[l].ld, sl[l].n, sl[l1].A, sl[l1].ld, l1 != l ? sl[l1].n : 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (PAIR && l + u >= nblk) break;  // no such block: its shared-memory row was never written
+        const V y = *reinterpret_cast<const V*>(ys + (PAIR ? (l + u) * YS : l * YS + u * S) + lane * VEC);
+#pragma unroll
+        for (int k = 0; k < CW; ++k) dot_vec(acc[k], a[u][k], y);
+      }
+    }
+    // the column-halving butterfly of the tile kernel
+    int width = CW;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      if (width > 1) {
+        width >>= 1;
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < CW / 2; ++k) {
+          if (k < width) {
+            const T send = upper ? acc[k] : acc[k + width];
+            const T keep = upper ? acc[k + width] : acc[k];
+            acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+      } else {
+        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+      }
+    }
+    constexpr int kHalvings = (CW == 16) ? 4 : (CW == 8) ? 3 : (CW == 4) ? 2 : (CW == 2) ? 1 : 0;
+    int mycol = 0;
+#pragma unroll
+    for (int h = 0; h < kHalvings; ++h) mycol |= ((lane >> (4 - h)) & 1) << (kHalvings - 1 - h);
+    const bool writer = (lane & ((32 >> kHalvings) - 1)) == 0;
+    if (writer && c0 + mycol < cols) dst[c0 + mycol] = acc[0];
+  }
+  if (t.fin >= 0) fused_finish<T>(t.fin, ff, in, W, out);
+  trace_stamp(pf.trace, blockIdx.x, 3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward over chains of small blocks: a head block plus further blocks of the same block row.  The columns of
+// the chain are laid end to end (at most kFwdMaxTC): their x slices are staged side by side in shared memory next
+// to a table of column addresses, and the CTA walks the concatenated columns exactly like the tile kernel walks
+// the columns of one tile (a thread owns VEC rows, TY column groups, U loads in flight), so block boundaries cost
+// nothing.  One partial per chain.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int TX, int POLICY>
+__global__ void __launch_bounds__(kThreads, 3) djets_blockmul_fwd_chain_kernel(const DenseTile* __restrict__ tiles,
+                                                                               const ChainLink* __restrict__ links,
+                                                                               const T* __restrict__ in, T* W,
+                                                                               T* __restrict__ out, FusedFinish ff,
+                                                                               Prefetch pf) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  constexpr int TY = kThreads / TX;
+  constexpr int TR = TX * VEC;
+  constexpr int U = 8;
+  __shared__ __align__(16) T xs[kFwdMaxTC];
+  __shared__ const T* colp[kFwdMaxTC];  // address of row 0 of every column of the chain
+  __shared__ __align__(16) T red[TY * TR];
+  __shared__ ChainLink sl[kChainMax];
+  __shared__ int first_col[kChainMax + 1];  // position of every block's first column in the chain
+
+  griddep_launch_dependents();
+  trace_stamp(pf.trace, blockIdx.x, 0);
+  const DenseTile t = tiles[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int rows = t.rows, nblk = 1 + t.chain;
+  uint64_t pol = 0;
+  if (POLICY == 1) pol = tile_policy(t.keep);
+
+  const int tx = tid % TX, ty = tid / TX;
+  const int r0 = tx * VEC;
+  T acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = T(0);
+
+  // first batch: columns of the head block, issued before anything else is looked at
+  const bool pre = (r0 < rows) && (ty + (U - 1) * TY < t.cols);
+  V v0[U];
+  if (pre) {
+    const T* a = reinterpret_cast<const T*>(t.A) + r0 + (long long)ty * t.ld;
+#pragma unroll
+    for (int u = 0; u < U; ++u) v0[u] = ld_stream<POLICY>(reinterpret_cast<const V*>(a + (long long)(u * TY) * t.ld), pol);
+  }
+  if (tid == 0) {
+    sl[0] = ChainLink{t.A, t.ld, t.vin, t.cols, 0};
+    first_col[0] = 0;
+  }
+  for (int l = tid; l < t.chain; l += kThreads) sl[1 + l] = links[t.link0 + l];
+  griddep_wait();
+  wait_epoch_flags(pf);
+  __syncthreads();
+  if (tid == 0) {
+    int p = 0;
+    for (int l = 0; l < nblk; ++l) {
+      first_col[l] = p;
+      p += sl[l].n;
+    }
+    first_col[nblk] = p;
+  }
+  __syncthreads();
+  trace_stamp(pf.trace, blockIdx.x, 1);
+  const int ncols = first_col[nblk];
+  for (int f = tid; f < ncols; f += kThreads) {
+    int l = 0;
+    while (f >= first_col[l + 1]) ++l;
+    const int c = f - first_col[l];
+    xs[f] = in[sl[l].vin + c];
+    colp[f] = reinterpret_cast<const T*>(sl[l].A) + (long long)c * sl[l].ld;
+  }
+  __syncthreads();
+  trace_stamp(pf.trace, blockIdx.x, 2);
+
+  if (r0 < rows) {
+    int f = ty;
+    if (pre) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) fma_vec(acc, v0[u], xs[f + u * TY]);
+      f += U * TY;
+    }
+    for (; f + (U - 1) * TY < ncols; f += U * TY) {
+      V v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = ld_stream<POLICY>(reinterpret_cast<const V*>(colp[f + u * TY] + r0), pol);
+#pragma unroll
+      for (int u = 0; u < U; ++u) fma_vec(acc, v[u], xs[f + u * TY]);
+    }
+    for (; f < ncols; f += TY) {
+      const V v = ld_stream<POLICY>(reinterpret_cast<const V*>(colp[f] + r0), pol);
+      fma_vec(acc, v, xs[f]);
+    }
+  }
+
+  T* dst = (t.direct ? out : W) + t.wout;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) red[ty * TR + r0 + k] = acc[k];
+  __syncthreads();
+  for (int r = tid; r < rows; r += kThreads) {  // rows <= TR
+    T s = red[r];
+#pragma unroll
+    for (int y = 1; y < TY; ++y) s += red[y * TR + r];
+    dst[r] = s;
+  }
+  if (t.fin >= 0) fused_finish<T>(t.fin, ff, in, W, out);
+  trace_stamp(pf.trace, blockIdx.x, 3);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Persistent tile loop shared by both GEMV kernels.  The grid is one resident wave of CTAs (or fewer);
 // CTA b starts on tile b and then draws further tiles from an atomic counter, so tiles are handed out
 // in table order -- largest first, the last wave's worth cut finer by the scheduler -- to whichever CTA
@@ -1680,6 +1920,53 @@ static cudaError_t launch_gemv_tc_t(int adj_ru, const DenseTile* tiles, int ntil
   return launch_tiles(djets_blockmul_adjc_tile_kernel<T, 4, 4, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, i, w, o, ff, pf);
 }
 
+template <typename T, int POLICY>
+static cudaError_t launch_gemv_t_chain_t(int pair, const DenseTile* tiles, const ChainLink* links, int ntiles,
+                                         const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                                         cudaStream_t stream) {
+  const T* i = reinterpret_cast<const T*>(in);
+  T* w = reinterpret_cast<T*>(W);
+  T* o = reinterpret_cast<T*>(out);
+  if (pair) return launch_tiles(djets_blockmul_adj_chain_kernel<T, 8, true, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, links, i, w, o, ff, pf);
+  return launch_tiles(djets_blockmul_adj_chain_kernel<T, 8, false, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, links, i, w, o, ff, pf);
+}
+
+cudaError_t launch_gemv_t_chain(int dtype, int pair, int ld_policy, const DenseTile* tiles, const ChainLink* links,
+                                int ntiles, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                                cudaStream_t stream) {
+  if (ntiles <= 0) return cudaSuccess;
+  if (is_complex(dtype)) return cudaErrorInvalidValue;
+  if (dtype == 0)
+    return ld_policy ? launch_gemv_t_chain_t<float, 1>(pair, tiles, links, ntiles, in, W, out, ff, pf, stream)
+                     : launch_gemv_t_chain_t<float, 0>(pair, tiles, links, ntiles, in, W, out, ff, pf, stream);
+  return ld_policy ? launch_gemv_t_chain_t<double, 1>(pair, tiles, links, ntiles, in, W, out, ff, pf, stream)
+                   : launch_gemv_t_chain_t<double, 0>(pair, tiles, links, ntiles, in, W, out, ff, pf, stream);
+}
+
+template <typename T, int POLICY>
+static cudaError_t launch_gemv_n_chain_t(int fwd_tx, const DenseTile* tiles, const ChainLink* links, int ntiles,
+                                         const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                                         cudaStream_t stream) {
+  const T* i = reinterpret_cast<const T*>(in);
+  T* w = reinterpret_cast<T*>(W);
+  T* o = reinterpret_cast<T*>(out);
+  if (fwd_tx == 32) return launch_tiles(djets_blockmul_fwd_chain_kernel<T, 32, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, links, i, w, o, ff, pf);
+  if (fwd_tx == 64) return launch_tiles(djets_blockmul_fwd_chain_kernel<T, 64, POLICY>, ntiles, (size_t)0, pf.pdl, stream, tiles, links, i, w, o, ff, pf);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_gemv_n_chain(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, const ChainLink* links,
+                                int ntiles, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                                cudaStream_t stream) {
+  if (ntiles <= 0) return cudaSuccess;
+  if (is_complex(dtype)) return cudaErrorInvalidValue;
+  if (dtype == 0)
+    return ld_policy ? launch_gemv_n_chain_t<float, 1>(fwd_tx, tiles, links, ntiles, in, W, out, ff, pf, stream)
+                     : launch_gemv_n_chain_t<float, 0>(fwd_tx, tiles, links, ntiles, in, W, out, ff, pf, stream);
+  return ld_policy ? launch_gemv_n_chain_t<double, 1>(fwd_tx, tiles, links, ntiles, in, W, out, ff, pf, stream)
+                   : launch_gemv_n_chain_t<double, 0>(fwd_tx, tiles, links, ntiles, in, W, out, ff, pf, stream);
+}
+
 cudaError_t launch_gemv_t(int dtype, int adj_ru, int adj_cw, int ld_policy, const DenseTile* tiles, int ntiles,
                           int grid, unsigned* counter, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
                           cudaStream_t stream) {
@@ -1819,6 +2106,18 @@ static int resident_t(int adjoint, int shape, int adj_cw) {
   if (adj_cw == 4 && shape == 2) return resident_ctas(djets_blockmul_adj_queue_kernel<T, 2, 4, POLICY>, kAdjSmemBytes);
   if (adj_cw == 4 && shape == 1) return resident_ctas(djets_blockmul_adj_queue_kernel<T, 1, 4, POLICY>, kAdjSmemBytes);
   return 0;
+}
+
+int gemv_chain_resident_ctas(int dtype, int adjoint, int ld_policy) {
+  if (is_complex(dtype)) return 0;
+  if (!adjoint) {
+    if (dtype == 0)
+      return ld_policy ? resident_ctas(djets_blockmul_fwd_chain_kernel<float, 64, 1>) : resident_ctas(djets_blockmul_fwd_chain_kernel<float, 64, 0>);
+    return ld_policy ? resident_ctas(djets_blockmul_fwd_chain_kernel<double, 64, 1>) : resident_ctas(djets_blockmul_fwd_chain_kernel<double, 64, 0>);
+  }
+  if (dtype == 0)
+    return ld_policy ? resident_ctas(djets_blockmul_adj_chain_kernel<float, 8, false, 1>) : resident_ctas(djets_blockmul_adj_chain_kernel<float, 8, false, 0>);
+  return ld_policy ? resident_ctas(djets_blockmul_adj_chain_kernel<double, 8, false, 1>) : resident_ctas(djets_blockmul_adj_chain_kernel<double, 8, false, 0>);
 }
 
 int gemv_resident_ctas(int dtype, int adjoint, int shape, int adj_cw, int ld_policy) {

@@ -21,8 +21,25 @@ struct DenseTile {
   int fin;            // >= 0: finish item this tile's strip belongs to (fused segmented sum), else -1
   int keep;           // 1: one of the last tiles of the launch -- loaded with an L2 evict-last hint, because the next
                       // apply of the operator (the other direction) starts with exactly these tiles
+  int chain;          // adjoint tiles over small blocks: number of further blocks (ChainLink entries from `link0` on)
+  int link0;          // the same CTA multiplies and accumulates into this tile's partial; 0 everywhere else
   int pad_;
 };
+
+// A further block of a chained tile.  Adjoint: same columns as the head tile, its own rows and input slice,
+//   partial[c] = sum_r A_head[r,c] in[vin_head + r] + sum_links sum_r A_l[r,c] in[vin_l + r];
+// forward: same rows as the head tile, its own columns and input slice,
+//   partial[r] = sum_c A_head[r,c] in[vin_head + c] + sum_links sum_c A_l[r,c] in[vin_l + c].
+// Small blocks (100x100 Float64 = 80 KB) leave a CTA more time in its fixed costs (descriptor, staging, ticket)
+// than in its loads; a chain of K blocks of one block column / row pays them once and writes one partial instead of K.
+struct ChainLink {
+  const void* A;
+  long long ld;
+  long long vin;
+  int n;  // rows of the block (adjoint) / columns of the block (forward)
+  int pad_;
+};
+constexpr int kChainMax = 16;  // blocks per chained tile, head included
 
 // One term of a diagonal block inside a finish item: out[e] += d[e] * in[vin + e].
 struct DiagTerm {
@@ -76,6 +93,17 @@ cudaError_t launch_gemv_n(int dtype, int fwd_tx, int ld_policy, const DenseTile*
 cudaError_t launch_gemv_t(int dtype, int adj_ru, int adj_cw, int ld_policy, const DenseTile* tiles, int ntiles,
                           int grid, unsigned* counter, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
                           cudaStream_t stream);
+// Chained tiles (blocks of at most 64 * VEC rows), one tile per CTA.  Adjoint: `pair` = every block is at most
+// 32 * VEC rows tall (one warp-load), two blocks are loaded per batch.  Forward: fwd_tx in {32, 64}, the columns of a
+// chain add up to at most kFwdMaxTC.
+cudaError_t launch_gemv_t_chain(int dtype, int pair, int ld_policy, const DenseTile* tiles, const ChainLink* links,
+                                int ntiles, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                                cudaStream_t stream);
+cudaError_t launch_gemv_n_chain(int dtype, int fwd_tx, int ld_policy, const DenseTile* tiles, const ChainLink* links,
+                                int ntiles, const void* in, void* W, void* out, FusedFinish ff, Prefetch pf,
+                                cudaStream_t stream);
+int gemv_chain_resident_ctas(int dtype, int adjoint, int ld_policy);
+inline int chain_max_rows(int dtype) { return 64 * (dtype == 0 ? 4 : 2); }
 // CTAs of the tile kernel variant that fit on the current device at once (occupancy x SM count).
 int gemv_resident_ctas(int dtype, int adjoint, int shape /* fwd_tx | adj_ru */, int adj_cw, int ld_policy);
 cudaError_t launch_finish(int dtype, const FinishItem* items, int nitems, const DiagTerm* diags, const void* in,

@@ -14,6 +14,7 @@ struct Block {
 struct DirPlan {
   DenseTile* d_tiles = nullptr;      // tiles in ascending block order ...
   DenseTile* d_tiles_rev = nullptr;  // ... and the same tiles in descending order (L2 hand-over, see build_plan)
+  ChainLink* d_links = nullptr;      // further blocks of chained adjoint tiles (small blocks); nullptr: no chains
   int ntiles = 0;
   FinishItem* d_items = nullptr;  // loose items first (finish_kernel), then the fused ones
   int nitems = 0, nloose = 0;
@@ -30,6 +31,8 @@ struct DirPlan {
   int adj_ru = 4, adj_cw = 4;  // adjoint kernel shape chosen for this cell (rows unrolled, columns per warp)
   int fwd_tx = 64;             // forward kernel shape chosen for this cell (threads along the rows)
   int wave = 0;                // CTAs of this cell's tile kernel that are resident at once (first wave)
+  bool chained = false;        // tiles are chains of small blocks (djets_blockmul_fwd/adj_chain_kernel)
+  bool chain_pair = false;     // ... none taller than one warp-load: the adjoint loads two blocks per batch
 };
 
 struct Cell {
@@ -151,6 +154,7 @@ void run_transfers(djets_ctx ctx, const std::vector<Transfer>& ts) {
 void free_plan(DirPlan& p, std::vector<void*>* keep = nullptr) {
   cudaFree(p.d_tiles);
   cudaFree(p.d_tiles_rev);
+  cudaFree(p.d_links);
   cudaFree(p.d_items);
   cudaFree(p.d_tickets);
   cudaFree(p.d_counter);
@@ -316,10 +320,41 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     plan.fwd_tx = (int)fwd_tx;
   }
   plan.wave = gemv_resident_ctas(op->dtype, adjoint ? 1 : 0, adjoint ? adj_ru : (int)fwd_tx, adj_cw, (int)op->p_ld_policy);
+  // Chained tiles: when every dense block of the cell is at most two warp-loads tall (128 Float64 / 256 Float32 rows)
+  // a CTA multiplies up to chain_k blocks of one block column (adjoint) / block row (forward) and writes one partial --
+  // enough blocks to make a tile of ~512 KB, but never so many that the cell is left with fewer than four waves of
+  // CTAs ("chain": 0 = this rule, 1 = off, k > 1 = k blocks whatever the operator's size).  90,000 blocks of 100x100
+  // Float64: adjoint 5.0 -> 6.7 TB/s (profiles/r02_block_shapes_1gpu.jsonl).
+  int64_t chain_k = 1;
+  bool chain_pair = false;
+  if (cs == 1 && ctx->chain != 1) {
+    int64_t nblk = 0, max_rows = 0, max_cols = 0, max_bytes = 1;
+    for (int64_t i = r0; i < r1; ++i)
+      for (int64_t j = c0; j < c1; ++j) {
+        if (op->isdiag && i != j) continue;
+        if (op->block(i, j).kind != DJETS_BLOCK_DENSE || op->row_len[i] == 0 || op->col_len[j] == 0) continue;
+        ++nblk;
+        max_rows = std::max(max_rows, op->row_len[i]);
+        max_cols = std::max(max_cols, op->col_len[j]);
+        max_bytes = std::max(max_bytes, op->row_len[i] * op->col_len[j] * es);
+      }
+    if (nblk > 0 && max_rows <= chain_max_rows(op->dtype) && (adjoint || max_cols <= kFwdMaxTC / 2)) {
+      const int chain_wave = gemv_chain_resident_ctas(op->dtype, adjoint ? 1 : 0, (int)op->p_ld_policy);
+      if (ctx->chain > 1)
+        chain_k = std::min<int64_t>(ctx->chain, kChainMax);
+      else if (ctx->auto_tile && chain_wave > 0)
+        chain_k = std::max<int64_t>(1, std::min<int64_t>({(int64_t)kChainMax, (512 * 1024) / max_bytes, nblk / (4 * (int64_t)chain_wave)}));
+      if (chain_k > 1) {
+        plan.wave = chain_wave;
+        chain_pair = max_rows <= chain_max_rows(op->dtype) / 2;
+        if (!adjoint) plan.fwd_tx = chain_pair ? 32 : 64;  // one row strip covers the tallest block
+      }
+    }
+  }
   // Wave fit: a tile count between one and two resident waves leaves the second wave part empty and its CTAs finish
   // one by one (profiles/r02_trace_boundary_8blocks.txt).  If slightly larger tiles bring the whole cell into ONE wave,
   // take them (0.5 GiB shard of the bench operator: 1024 -> 512 forward tiles, 512 -> 296 adjoint tiles, -1 % per step).
-  if (ctx->auto_tile && ctx->wave_fit && plan.wave > 0) {
+  if (ctx->auto_tile && ctx->wave_fit && plan.wave > 0 && chain_k == 1) {
     auto count_tiles = [&](int64_t ftc, int64_t atc) {
       int64_t nt = 0;
       for (int64_t i = r0; i < r1; ++i)
@@ -349,6 +384,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     }
   }
   std::vector<DenseTile> tiles;
+  std::vector<ChainLink> links;
   std::vector<int64_t> tile_key;  // block (i, j) of every tile, row-major: both directions walk the blocks in this order
   std::vector<FinishItem> loose, fused;
   std::vector<int64_t> loose_key;  // offset of the item's chunk inside its block: the launch order of the loose items
@@ -373,13 +409,25 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
       Block& b = op->block(i, j);
       if (b.kind == DJETS_BLOCK_DENSE && op->row_len[i] > 0 && op->col_len[j] > 0) {
         dense.push_back({in, &b});
-        nplanes += plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, fwd_tx, eff_fwd_tc,
-                              eff_adj_tc)
-                       .nplanes;
+        if (chain_k == 1)
+          nplanes += plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, fwd_tx, eff_fwd_tc, eff_adj_tc)
+                         .nplanes;
       } else if (b.kind == DJETS_BLOCK_DIAG) {
         diag.push_back({in, &b});
       }
     }
+    // chains: runs of up to chain_k blocks (forward: as long as their columns fit the staging buffer), one plane each
+    auto extent = [&](const Contribution& cb) { return adjoint ? op->row_len[cb.in] : op->col_len[cb.in]; };
+    std::vector<std::pair<size_t, size_t>> chains;
+    for (size_t first = 0; chain_k > 1 && first < dense.size();) {
+      size_t end = first + 1;
+      int64_t span = extent(dense[first]);
+      while (end < dense.size() && (int64_t)(end - first) < chain_k && (adjoint || span + extent(dense[end]) <= kFwdMaxTC))
+        span += extent(dense[end++]);
+      chains.push_back({first, end});
+      first = end;
+    }
+    if (chain_k > 1) nplanes = (int64_t)chains.size();
     const bool direct = (nplanes == 1 && diag.empty() && nremote == 0);
     const bool fuse = can_fuse && !direct && !dense.empty();
     const int64_t wbase = wtotal;
@@ -420,13 +468,34 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
       const int64_t i = adjoint ? cb.in : o, j = adjoint ? o : cb.in;
       const TileShape sh = plan_shape(op->dtype, op->row_len[i], op->col_len[j], adjoint, fwd_tx, eff_fwd_tc,
                                       eff_adj_tc);
-      strip = adjoint ? sh.tile_cols : sh.tile_rows;
+      strip = chain_k > 1 ? olen : (adjoint ? sh.tile_cols : sh.tile_rows);
       fused_first = emit_items(fused, strip);
     } else if (!direct) {
       emit_items(loose, kFinishChunk);
     }
 
     int64_t plane = 0;
+    for (const auto& [first, end] : chains) {
+      const Contribution& head = dense[first];
+      const int64_t i = adjoint ? head.in : o, j = adjoint ? o : head.in;
+      DenseTile t;
+      t.A = head.b->d;
+      t.ld = head.b->ld;
+      t.vin = in_off[head.in];
+      t.rows = (int)op->row_len[i];
+      t.cols = (int)op->col_len[j];
+      t.direct = direct ? 1 : 0;
+      t.wout = direct ? out_off[o] : wbase + plane * olen;
+      t.fin = fuse ? fused_first : -1;
+      t.chain = (int)(end - first - 1);
+      t.link0 = (int)links.size();
+      for (size_t k = first + 1; k < end; ++k)
+        links.push_back({dense[k].b->d, dense[k].b->ld, in_off[dense[k].in], (int)extent(dense[k]), 0});
+      tiles.push_back(t);
+      tile_key.push_back(i * op->nbcol + j);
+      ++plane;
+    }
+    if (chain_k > 1) continue;
     for (const Contribution& cb : dense) {
       const int64_t i = adjoint ? cb.in : o, j = adjoint ? o : cb.in;
       const int64_t m = op->row_len[i], n = op->col_len[j];
@@ -443,6 +512,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
             t.direct = direct ? 1 : 0;
             t.wout = cs * (direct ? out_off[o] + row0 : wbase + (plane + p) * olen + row0);
             t.fin = fuse ? fused_first + (int)(row0 / strip) : -1;
+            t.chain = t.link0 = 0;
             tiles.push_back(t);
             tile_key.push_back(i * op->nbcol + j);
           }
@@ -459,6 +529,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
             t.direct = direct ? 1 : 0;
             t.wout = cs * (direct ? out_off[o] + col0 : wbase + (plane + p) * olen + col0);
             t.fin = fuse ? fused_first + (int)(col0 / strip) : -1;
+            t.chain = t.link0 = 0;
             tiles.push_back(t);
             tile_key.push_back(i * op->nbcol + j);
           }
@@ -506,7 +577,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     }
     for (size_t k = table->size(); k-- > 0 && budget > 0;) {
       (*table)[k].keep = 1;
-      budget -= (int64_t)(*table)[k].rows * (*table)[k].cols * (es / cs);
+      budget -= (int64_t)(*table)[k].rows * (*table)[k].cols * (es / cs) * (1 + (*table)[k].chain);
     }
   }
   // loose items first, fused items after them; tiles index the concatenated table
@@ -521,6 +592,9 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   plan.nitems = (int)items.size();
   plan.d_tiles = upload(tiles);
   plan.d_tiles_rev = ctx->l2_keep > 0 ? upload(tiles_rev) : nullptr;
+  plan.d_links = upload(links);
+  plan.chained = chain_k > 1;
+  plan.chain_pair = chain_pair;
   plan.d_items = upload(items);
   plan.d_tickets = reinterpret_cast<unsigned*>(dalloc(items.size() * sizeof(unsigned)));
   plan.d_counter = reinterpret_cast<unsigned*>(dalloc(sizeof(unsigned)));
@@ -746,7 +820,7 @@ const DenseTile* walk(Cell& cell, const DirPlan& plan) {
 // CTAs launched for a cell's tile kernel: one resident wave that walks the tile table (persistent), or one
 // CTA per tile.
 int tile_grid(djets_ctx ctx, const DirPlan& plan) {
-  if (!ctx->persistent || plan.wave <= 0) return plan.ntiles;
+  if (!ctx->persistent || plan.wave <= 0 || plan.chained) return plan.ntiles;
   return std::min(plan.ntiles, plan.wave);
 }
 
@@ -873,11 +947,17 @@ int apply_enqueue_xp(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
     const FusedFinish ff{plan.d_items, plan.d_diags, plan.d_tickets};
     if (!adjoint)
       launch_counted(ctx, rc, DJETS_K_GEMV_N, [&] {
+        if (plan.chained)
+          return launch_gemv_n_chain(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, walk(cell, plan), plan.d_links,
+                                     plan.ntiles, inp, plan.W, outp, ff, pf, rc.stream);
         return launch_gemv_n(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, walk(cell, plan), plan.ntiles, tile_grid(ctx, plan),
                              plan.d_counter, inp, plan.W, outp, ff, pf, rc.stream);
       });
     else
       launch_counted(ctx, rc, DJETS_K_GEMV_T, [&] {
+        if (plan.chained)
+          return launch_gemv_t_chain(op->dtype, plan.chain_pair ? 1 : 0, (int)op->p_ld_policy, walk(cell, plan), plan.d_links,
+                                     plan.ntiles, inp, plan.W, outp, ff, pf, rc.stream);
         return launch_gemv_t(op->dtype, plan.adj_ru, plan.adj_cw, (int)op->p_ld_policy, walk(cell, plan), plan.ntiles,
                              tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, ff, pf, rc.stream);
       });
@@ -988,19 +1068,25 @@ int apply_enqueue(djets_op op, djets_vec out, djets_vec in, bool adjoint) {
         ++nops;
         if (!adjoint)
           launch_counted(ctx, *rc, DJETS_K_GEMV_N, [&] {
+            const FusedFinish ff{plan.d_items, plan.d_diags, plan.d_tickets};
+            const Prefetch pf{plan.wave, (int)ctx->prefetch, (int)ctx->pdl, trace_slot(*rc, DJETS_K_GEMV_N, plan.ntiles),
+                              {nullptr, nullptr}, {0u, 0u}, 0, nullptr};
+            if (plan.chained)
+              return launch_gemv_n_chain(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, walk(cell, plan), plan.d_links,
+                                         plan.ntiles, inp, plan.W, outp, ff, pf, rc->stream);
             return launch_gemv_n(op->dtype, plan.fwd_tx, (int)op->p_ld_policy, walk(cell, plan), plan.ntiles,
-                                 tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets},
-                                 Prefetch{plan.wave, (int)ctx->prefetch, (int)ctx->pdl,
-                                          trace_slot(*rc, DJETS_K_GEMV_N, plan.ntiles), {nullptr, nullptr}, {0u, 0u}, 0, nullptr},
-                                 rc->stream);
+                                 tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, ff, pf, rc->stream);
           });
         else
           launch_counted(ctx, *rc, DJETS_K_GEMV_T, [&] {
+            const FusedFinish ff{plan.d_items, plan.d_diags, plan.d_tickets};
+            const Prefetch pf{plan.wave, (int)ctx->prefetch, (int)ctx->pdl, trace_slot(*rc, DJETS_K_GEMV_T, plan.ntiles),
+                              {nullptr, nullptr}, {0u, 0u}, 0, nullptr};
+            if (plan.chained)
+              return launch_gemv_t_chain(op->dtype, plan.chain_pair ? 1 : 0, (int)op->p_ld_policy, walk(cell, plan),
+                                         plan.d_links, plan.ntiles, inp, plan.W, outp, ff, pf, rc->stream);
             return launch_gemv_t(op->dtype, plan.adj_ru, plan.adj_cw, (int)op->p_ld_policy, walk(cell, plan), plan.ntiles,
-                                 tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, FusedFinish{plan.d_items, plan.d_diags, plan.d_tickets},
-                                 Prefetch{plan.wave, (int)ctx->prefetch, (int)ctx->pdl,
-                                          trace_slot(*rc, DJETS_K_GEMV_T, plan.ntiles), {nullptr, nullptr}, {0u, 0u}, 0, nullptr},
-                                 rc->stream);
+                                 tile_grid(ctx, plan), plan.d_counter, inp, plan.W, outp, ff, pf, rc->stream);
           });
       }
       if (!owner && plan.nloose > 0) {

@@ -158,7 +158,7 @@ int32_t djets_ctx_kernel_timing(djets_ctx ctx, int32_t enable);
 int32_t djets_ctx_kernel_stats(djets_ctx ctx, int32_t kind, int64_t* launches, double* total_ms);
 int32_t djets_ctx_reset_stats(djets_ctx ctx);
 /* Tuning knob.  Schedule shapes (affect operators finalised or re-planned afterwards): "fwd_tx", "fwd_tc", "adj_ru",
- * "adj_tc", "ld_policy", "auto_tile", "adj_light", "wave_fit", "l2_keep" (MB of a cell's last tiles handed to the next
+ * "adj_tc", "ld_policy", "auto_tile", "adj_light", "chain", "wave_fit", "l2_keep" (MB of a cell's last tiles handed to the next
  * apply through L2; 0 = off).  Launch mechanisms (take effect on the next apply; applies captured under older settings
  * are dropped): "graphs", "p2p", "pdl", "prefetch", "persistent", "ipc" (before the operator is finalised), "xp_kwait",
  * "xp_side", "xp_push". */

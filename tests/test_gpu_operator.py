@@ -287,6 +287,49 @@ def test_random_operators_match_oracle(dj, O, ctx4):
         _check(dj, O, oop, gop, oblocks, rng, dtype)
 
 
+@pytest.mark.parametrize("heights", ["two warp-loads", "one warp-load"])
+@pytest.mark.parametrize("chain", [3, 16])
+def test_chained_tiles_match_oracle(dj, O, ctx4, chain, heights):
+    """Chains of small blocks (one CTA multiplies several blocks of a block column / block row and writes one
+    partial): forced on for small operators, ragged block sizes up to the two-warp-load limit (and up to one
+    warp-load: the adjoint then loads two blocks per batch), zero / diagonal blocks breaking the chains, forward
+    chains cut where the staged columns would overflow, every grid shape; against ground truth and the oracle."""
+    master = np.random.default_rng(77 + chain + len(heights))
+    grids = [(1, 1), (2, 1), (1, 2), (2, 2), (4, 1), (1, 4)]
+    ctx4.set_param("chain", chain)
+    try:
+        fewer = 0
+        for case in range(12):
+            n1, n2 = grids[master.integers(len(grids))]
+            N, M = int(master.integers(max(n1, 5), 12)), int(master.integers(max(n2, 4), 11))
+            dtype = np.float64 if master.integers(2) else np.float32
+            if heights == "one warp-load":
+                rsizes = [1, 2, 3, 5, 8, 17, 33, 63, 64] + ([100, 127, 128] if dtype == np.float32 else [])
+            else:
+                rsizes = [1, 3, 8, 17, 64, 65, 100, 127, 128] + ([129, 255, 256] if dtype == np.float32 else [])
+            csizes = [1, 2, 5, 17, 64, 100, 129, 256, 400]
+            rs = [int(rsizes[master.integers(len(rsizes))]) for _ in range(N)]
+            cs = [int(csizes[master.integers(len(csizes))]) for _ in range(M)]
+            pick = master.random((N, M))
+
+            def kind(i, j, rs=rs, cs=cs, pick=pick):
+                p = pick[i - 1, j - 1]
+                if p < 0.1:
+                    return "zero"
+                if p < 0.25 and rs[i - 1] == cs[j - 1]:
+                    return "diag"
+                return "dense"
+
+            rng = np.random.default_rng(5000 + case)
+            oop, gop, oblocks = build_pair(dj, O, rng, rs, cs, kind, dtype, list(range(n1 * n2)), [n1, n2], ctx=ctx4)
+            _check(dj, O, oop, gop, oblocks, rng, dtype)
+            ndense = sum(kind(i, j) == "dense" for i in range(1, N + 1) for j in range(1, M + 1))
+            fewer += gop.schedule_info(adjoint=True)[0] < ndense and gop.schedule_info(adjoint=False)[0] < ndense
+        assert fewer >= 10, "the chained schedules were not used"
+    finally:
+        ctx4.set_param("chain", 0)
+
+
 def test_perfstatfile_schema(dj, O, ctx4, tmp_path):
     """perfstatfile (src:723-745; schema pinned by test:618-651): one step per apply, one entry per worker
     with id / hostname / operation / localblock (8 and 4 local blocks for a 3x4 operator on grid [2,1])."""
