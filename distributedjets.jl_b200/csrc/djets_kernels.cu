@@ -298,12 +298,109 @@ __device__ __forceinline__ bool aligned16(const T* p) {
 }
 
 // Items made of diagonal blocks only -- the streaming `d .= diag .* m` of a diagonal operator and its
-// sums over a block row: 128-bit loads of the diagonals (streamed, L1 bypassed) and of the vector,
-// several terms in flight, when every slice is 16-byte aligned.
+// sums over a block row: 128-bit loads of the diagonals (streamed, L1 bypassed) and of the vector, when every slice is
+// 16-byte aligned.  A thread works on VU vectors (256 threads apart) and U terms at a time, VU*U = 8 diagonal loads
+// and as many vector loads issued back to back before the first product (loads into arrays: left to itself the
+// compiler interleaves load - multiply - load and keeps ONE term in flight per thread; ncu of a 24x24 grid of diagonal
+// blocks showed every DFMA waiting on its own pair of loads).  Terms are added in term order, as before.
+// Loads that keep their program order (asm volatile): the whole batch is issued before the first use.
+__device__ __forceinline__ float4 ld_ordered(const float4* p, bool streamed) {
+  float4 r;
+  if (streamed)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  else
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ld_ordered(const double2* p, bool streamed) {
+  double2 r;
+  if (streamed)
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  else
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+template <typename T, int VU, int U>
+__device__ __forceinline__ void diag_vec_terms(double (&acc)[VU][VecT<T>::N], const DiagTerm* __restrict__ diags, int d,
+                                               const T* __restrict__ in, int v) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  V dv[U][VU], xv[U][VU];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const V* dp = reinterpret_cast<const V*>(diags[d + u].d) + v;
+#pragma unroll
+    for (int j = 0; j < VU; ++j) dv[u][j] = ld_ordered(dp + j * kThreads, true);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const V* xp = reinterpret_cast<const V*>(in + diags[d + u].vin) + v;
+#pragma unroll
+    for (int j = 0; j < VU; ++j) xv[u][j] = ld_ordered(xp + j * kThreads, false);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int j = 0; j < VU; ++j) {
+      const T* de = reinterpret_cast<const T*>(&dv[u][j]);
+      const T* xe = reinterpret_cast<const T*>(&xv[u][j]);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[j][k] += (double)(de[k] * xe[k]);
+    }
+}
+
+template <typename T, int VU, int U>
+__device__ __forceinline__ void diag_vec_span(const FinishItem& it, const DiagTerm* __restrict__ diags,
+                                              const T* __restrict__ in, T* __restrict__ o, int v) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  double acc[VU][VEC];
+#pragma unroll
+  for (int j = 0; j < VU; ++j)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[j][k] = 0.0;
+  int d = it.diag_begin;
+  for (; d + U <= it.diag_end; d += U) diag_vec_terms<T, VU, U>(acc, diags, d, in, v);
+  for (; d < it.diag_end; ++d) diag_vec_terms<T, VU, 1>(acc, diags, d, in, v);
+#pragma unroll
+  for (int j = 0; j < VU; ++j) {
+    V r;
+    T* re = reinterpret_cast<T*>(&r);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) re[k] = (T)acc[j][k];
+    reinterpret_cast<V*>(o)[v + j * kThreads] = r;
+  }
+}
+
+// One term: the streaming `d .= diag .* m`.  The product needs no wide accumulator; `+ 0` keeps the sign of zero the
+// accumulating form produces (0 + -0 = +0).
+template <typename T, int VU>
+__device__ __forceinline__ void diag_vec_single(const DiagTerm& term, const T* __restrict__ in, T* __restrict__ o, int v) {
+  using V = typename VecT<T>::type;
+  constexpr int VEC = VecT<T>::N;
+  const V* dp = reinterpret_cast<const V*>(term.d) + v;
+  const V* xp = reinterpret_cast<const V*>(in + term.vin) + v;
+  V dv[VU], xv[VU];
+#pragma unroll
+  for (int j = 0; j < VU; ++j) dv[j] = ld_ordered(dp + j * kThreads, true);
+#pragma unroll
+  for (int j = 0; j < VU; ++j) xv[j] = ld_ordered(xp + j * kThreads, false);
+#pragma unroll
+  for (int j = 0; j < VU; ++j) {
+    const T* de = reinterpret_cast<const T*>(&dv[j]);
+    const T* xe = reinterpret_cast<const T*>(&xv[j]);
+    V r;
+    T* re = reinterpret_cast<T*>(&r);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) re[k] = rn_add(rn_mul(de[k], xe[k]), T(0));
+    reinterpret_cast<V*>(o)[v + j * kThreads] = r;
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ bool finish_item_diag_vec(const FinishItem& it, const DiagTerm* __restrict__ diags,
                                                      const T* __restrict__ in, T* __restrict__ out) {
-  using V = typename VecT<T>::type;
   constexpr int VEC = VecT<T>::N;
   T* o = out + it.out;
   bool ok = aligned16(o);
@@ -311,25 +408,18 @@ __device__ __forceinline__ bool finish_item_diag_vec(const FinishItem& it, const
     ok = aligned16(reinterpret_cast<const T*>(diags[d].d)) && aligned16(in + diags[d].vin);
   if (!ok) return false;  // uniform over the CTA
   const int nv = it.len / VEC;
-  for (int v = threadIdx.x; v < nv; v += kThreads) {
-    double acc[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.0;
-#pragma unroll 4
-    for (int d = it.diag_begin; d < it.diag_end; ++d) {
-      const V dv = ld_stream<0>(reinterpret_cast<const V*>(diags[d].d) + v, 0);
-      const V xv = *(reinterpret_cast<const V*>(in + diags[d].vin) + v);
-      const T* de = reinterpret_cast<const T*>(&dv);
-      const T* xe = reinterpret_cast<const T*>(&xv);
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] += (double)(de[k] * xe[k]);
-    }
-    V r;
-    T* re = reinterpret_cast<T*>(&r);
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) re[k] = (T)acc[k];
-    reinterpret_cast<V*>(o)[v] = r;
+  int v = threadIdx.x;
+  const int nt = it.diag_end - it.diag_begin;
+  if (nt == 1) {
+    const DiagTerm term = diags[it.diag_begin];
+    for (; v + 3 * kThreads < nv; v += 4 * kThreads) diag_vec_single<T, 4>(term, in, o, v);
+    for (; v < nv; v += kThreads) diag_vec_single<T, 1>(term, in, o, v);
+  } else if (nt >= 4) {
+    for (; v + kThreads < nv; v += 2 * kThreads) diag_vec_span<T, 2, 4>(it, diags, in, o, v);
+  } else {
+    for (; v + kThreads < nv; v += 2 * kThreads) diag_vec_span<T, 2, 2>(it, diags, in, o, v);
   }
+  for (; v < nv; v += kThreads) diag_vec_span<T, 1, 4>(it, diags, in, o, v);
   for (int e = nv * VEC + threadIdx.x; e < it.len; e += kThreads) {
     double s = 0.0;
     for (int d = it.diag_begin; d < it.diag_end; ++d)
@@ -1378,7 +1468,7 @@ __global__ void __launch_bounds__(kThreads, 2) djets_blockmul_adj_queue_kernel(c
 // Loose items: block rows / columns with no dense tile on this rank (diagonal-only: the fused
 // streaming `d .= diag .* m`), and every item of a rank that also sums planes received from peers.
 template <typename T, bool CPLX>
-__global__ void __launch_bounds__(kThreads) djets_segsum_kernel(const FinishItem* __restrict__ items,
+__global__ void __launch_bounds__(kThreads, 3) djets_segsum_kernel(const FinishItem* __restrict__ items,
                                                                 const DiagTerm* __restrict__ diags,
                                                                 const T* __restrict__ in, const T* __restrict__ W,
                                                                 const T* __restrict__ R, T* __restrict__ out) {

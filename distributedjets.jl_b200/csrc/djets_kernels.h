@@ -206,7 +206,8 @@ constexpr int kThreads = 256;
 constexpr int kFwdMaxTC = 1024;   // columns of x staged in shared memory by a forward tile
 constexpr int kAdjMaxTRBytes = 32768;  // bytes of y staged in shared memory by an adjoint tile
 constexpr int kAdjCW = 4;         // fewest columns a warp handles at once in the adjoint kernel (tall columns)
-constexpr int kFinishChunk = 4096;
+constexpr int kFinishChunk = 4096;        // elements of one loose segmented-sum item (one CTA), at least ...
+constexpr int kFinishChunkBytes = 32768;  // ... this many bytes per stream: Float32 items are 8192 elements
 inline int adj_max_rows(int dtype) { return kAdjMaxTRBytes / elem_size(dtype); }
 
 }  // namespace djets

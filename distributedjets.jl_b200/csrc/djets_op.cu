@@ -471,7 +471,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
       strip = chain_k > 1 ? olen : (adjoint ? sh.tile_cols : sh.tile_rows);
       fused_first = emit_items(fused, strip);
     } else if (!direct) {
-      emit_items(loose, kFinishChunk);
+      emit_items(loose, std::max<int64_t>(kFinishChunk, kFinishChunkBytes / es));
     }
 
     int64_t plane = 0;
@@ -568,8 +568,28 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     for (size_t k : order) sorted.push_back(tiles[k]);
     tiles.swap(sorted);
   }
+  // Small operators (everything the GPU holds of it is within twice the L2) keep a fixed resident set instead: the
+  // first `l2_keep` MB of the block order -- the same blocks in both directions and in every apply, shared evenly by
+  // the ranks that share the GPU -- are always loaded evict-last and stay in L2 from apply to apply, whatever the
+  // order CTAs run in (a cell that fits one wave has no walk order to speak of).
+  int64_t cell_bytes = 0;
+  for (const DenseTile& t : tiles) cell_bytes += (int64_t)t.rows * t.cols * (es / cs) * (1 + t.chain);
+  int sharing = 0;
+  for (const Cell& other : op->cells)
+    if (RankCtx* orc = ctx->local(other.rank)) sharing += orc->device == rc->device ? 1 : 0;
+  sharing = std::max(sharing, 1);
+  const bool resident_set = ctx->l2_keep > 0 && cell_bytes * sharing <= (int64_t)252 << 20;
+  if (resident_set) {
+    int64_t budget = (ctx->l2_keep << 20) / sharing;
+    for (DenseTile& t : tiles) {
+      t.keep = budget > 0 ? 1 : 0;
+      t.pad_ = 0;
+      budget -= (int64_t)t.rows * t.cols * (es / cs) * (1 + t.chain);
+    }
+  }
   std::vector<DenseTile> tiles_rev(tiles.rbegin(), tiles.rend());
   for (std::vector<DenseTile>* table : {&tiles, &tiles_rev}) {
+    if (resident_set) break;
     int64_t budget = ctx->l2_keep << 20;
     for (DenseTile& t : *table) {
       t.keep = 0;

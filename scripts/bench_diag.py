@@ -11,7 +11,16 @@ import djets_loader  # noqa: E402
 
 dj = djets_loader.load()
 ctx = dj.init(world=1, devices=[0])
-for name, nb, bl, full in (("f64", 512, 1 << 20, False), ("f32", 512, 1 << 21, False), ("f64", 24, 1 << 20, True)):
+only = None
+for kv in sys.argv[1:]:                                   # only=2 picks a case; anything else is a context parameter
+    k, v = kv.split("=")
+    if k == "only":
+        only = int(v)
+    else:
+        ctx.set_param(k, int(v))
+for case, (name, nb, bl, full) in enumerate((("f64", 512, 1 << 20, False), ("f32", 512, 1 << 21, False), ("f64", 24, 1 << 20, True))):
+    if only is not None and case != only:
+        continue
     dtype = np.float32 if name == "f32" else np.float64
     rng = np.random.default_rng(0)
     pool = [rng.random(bl, dtype=dtype) for _ in range(4)]

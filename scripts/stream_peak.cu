@@ -68,6 +68,73 @@ __global__ void __launch_bounds__(256) fill_kernel(uint4* __restrict__ dst, size
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) st_cs(dst + i, v);
 }
 
+// ---- store variants of the fill -------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void st_mode(uint4* p, uint4 v) {
+  if (MODE == 0) asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  if (MODE == 1) asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  if (MODE == 2) asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  if (MODE == 3) asm volatile("st.global.wt.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  if (MODE == 4) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+  }
+}
+// contiguous: every CTA owns one contiguous span of the buffer and walks it front to back (4 KB per step)
+template <int MODE, bool CONTIG>
+__global__ void __launch_bounds__(256) fill_mode_kernel(uint4* __restrict__ dst, size_t n16) {
+  const uint4 v = make_uint4(1u, 2u, 3u, 4u);
+  if (CONTIG) {
+    const size_t per = (n16 + gridDim.x - 1) / gridDim.x;
+    const size_t lo = per * blockIdx.x, hi = lo + per < n16 ? lo + per : n16;
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) st_mode<MODE>(dst + i, v);
+  } else {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) st_mode<MODE>(dst + i, v);
+  }
+}
+
+// ---- copy through shared memory with 1-D TMA bulk transfers (no registers on the data path) ---------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int CHUNK, int STAGES>
+__global__ void __launch_bounds__(32) tma_copy_kernel(const char* __restrict__ src, char* __restrict__ dst, size_t nchunks) {
+  extern __shared__ __align__(128) char buf[];
+  __shared__ __align__(8) uint64_t bar[STAGES];
+  if (threadIdx.x != 0) return;
+  for (int s = 0; s < STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[s])));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  const size_t first = blockIdx.x, step = gridDim.x;
+  const size_t mine = first < nchunks ? (nchunks - first + step - 1) / step : 0;
+  auto load = [&](size_t n) {
+    const int s = (int)(n % STAGES);
+    const uint32_t b = smem_u32(&bar[s]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(CHUNK) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(buf + (size_t)s * CHUNK)),
+                 "l"(src + (first + n * step) * (size_t)CHUNK), "r"(CHUNK), "r"(b)
+                 : "memory");
+  };
+  for (size_t n = 0; n < (size_t)STAGES && n < mine; ++n) load(n);
+  for (size_t n = 0; n < mine; ++n) {
+    const int s = (int)(n % STAGES);
+    const uint32_t parity = (uint32_t)((n / STAGES) & 1);
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done)
+                   : "r"(smem_u32(&bar[s])), "r"(parity)
+                   : "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + (first + n * step) * (size_t)CHUNK),
+                 "r"(smem_u32(buf + (size_t)s * CHUNK)), "r"(CHUNK)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the previous store has read its buffer
+    if (n >= 1 && n - 1 + STAGES < mine) load(n - 1 + STAGES);
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <class F>
 static double time_ms(F launch, int reps) {
   cudaEvent_t a, b;
@@ -119,6 +186,39 @@ int main(int argc, char** argv) {
     best_copy = r > best_copy ? r : best_copy;
     r = report("copy", 8, time_ms([&] { copy_kernel<8><<<grid, 256>>>(src, dst, n16); }, reps), 2.0 * bytes);
     best_copy = r > best_copy ? r : best_copy;
+  }
+  {
+    const char* names[5] = {"st", "st.cs", "st.cg", "st.wt", "st.L2::evict_first"};
+    double ms[5][2];
+    ms[0][0] = time_ms([&] { fill_mode_kernel<0, false><<<sms * 8, 256>>>(dst, n16); }, reps);
+    ms[1][0] = time_ms([&] { fill_mode_kernel<1, false><<<sms * 8, 256>>>(dst, n16); }, reps);
+    ms[2][0] = time_ms([&] { fill_mode_kernel<2, false><<<sms * 8, 256>>>(dst, n16); }, reps);
+    ms[3][0] = time_ms([&] { fill_mode_kernel<3, false><<<sms * 8, 256>>>(dst, n16); }, reps);
+    ms[4][0] = time_ms([&] { fill_mode_kernel<4, false><<<sms * 8, 256>>>(dst, n16); }, reps);
+    ms[0][1] = time_ms([&] { fill_mode_kernel<0, true><<<sms * 8, 256>>>(dst, n16); }, reps);
+    ms[1][1] = time_ms([&] { fill_mode_kernel<1, true><<<sms * 8, 256>>>(dst, n16); }, reps);
+    ms[2][1] = time_ms([&] { fill_mode_kernel<2, true><<<sms * 8, 256>>>(dst, n16); }, reps);
+    ms[3][1] = time_ms([&] { fill_mode_kernel<3, true><<<sms * 8, 256>>>(dst, n16); }, reps);
+    ms[4][1] = time_ms([&] { fill_mode_kernel<4, true><<<sms * 8, 256>>>(dst, n16); }, reps);
+    for (int m = 0; m < 5; ++m)
+      printf("{\"kernel\": \"fill\", \"store\": \"%s\", \"grid_stride_GBps\": %.0f, \"contiguous_per_cta_GBps\": %.0f}\n", names[m],
+             bytes / ms[m][0] * 1e-6, bytes / ms[m][1] * 1e-6);
+  }
+  {
+    auto tma = [&](auto kernel, int chunk, int stages, int per_sm) {
+      const size_t smem = (size_t)chunk * stages;
+      CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const size_t nchunks = bytes / chunk;
+      const double ms = time_ms([&] { kernel<<<sms * per_sm, 32, smem>>>((const char*)src, (char*)dst, nchunks); }, reps);
+      printf("{\"kernel\": \"tma_copy\", \"chunk\": %d, \"stages\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, \"GBps\": %.0f}\n", chunk, stages,
+             per_sm, ms, 2.0 * bytes / ms * 1e-6);
+    };
+    tma(tma_copy_kernel<8192, 4>, 8192, 4, 4);
+    tma(tma_copy_kernel<8192, 4>, 8192, 4, 6);
+    tma(tma_copy_kernel<16384, 4>, 16384, 4, 2);
+    tma(tma_copy_kernel<16384, 4>, 16384, 4, 3);
+    tma(tma_copy_kernel<32768, 3>, 32768, 3, 2);
+    tma(tma_copy_kernel<4096, 8>, 4096, 8, 6);
   }
   const double fill = (double)bytes / time_ms([&] { fill_kernel<<<sms * 8, 256>>>(dst, n16); }, reps) * 1e-6;
   const double memcpy_gbps =
