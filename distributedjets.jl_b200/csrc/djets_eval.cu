@@ -336,6 +336,11 @@ cudaError_t launch_vec_k(T* dest, const EvalDev& d, long long n, cudaStream_t st
   }
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  // Two resident CTAs per SM, not as many as fit: a read+write stream runs faster with few resident threads and the
+  // ring keeping the bytes in flight (abs.(d) 5.89 -> 6.03 TB/s, max.(d,0) 5.73 -> 6.14, sqrt.(abs.(x)) in place 5.52 ->
+  // 6.00 on 2^30 Float64; scripts/stream_peak.cu shows the same step at 512 resident threads).  DJETS_EVAL_CTAS overrides.
+  static const int cap = getenv("DJETS_EVAL_CTAS") ? atoi(getenv("DJETS_EVAL_CTAS")) : 2;
+  if (cap > 0) per_sm = std::min(per_sm, cap);
   const long long nvec = (n + Vec16<T>::N - 1) / Vec16<T>::N;
   const long long ntiles = (nvec + (long long)NV * kThreads - 1) / ((long long)NV * kThreads);
   const int grid = (int)std::min<long long>(ntiles, (long long)eval_sm_count() * per_sm);

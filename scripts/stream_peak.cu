@@ -62,6 +62,21 @@ __global__ void __launch_bounds__(256) copy_kernel(const uint4* __restrict__ src
   for (; i < n16; i += stride) st_cs(dst + i, ld_nc(src + i));
 }
 
+// copy with wider phases: U loads then U stores per thread, any block size
+template <int U>
+__global__ void __launch_bounds__(1024) copy_wide_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < n16; i += U * stride) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = ld_nc(src + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; ++u) st_cs(dst + i + u * stride, v[u]);
+  }
+  for (; i < n16; i += stride) st_cs(dst + i, ld_nc(src + i));
+}
+
 __global__ void __launch_bounds__(256) fill_kernel(uint4* __restrict__ dst, size_t n16) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const uint4 v = make_uint4(1u, 2u, 3u, 4u);
@@ -220,6 +235,16 @@ int main(int argc, char** argv) {
     tma(tma_copy_kernel<32768, 3>, 32768, 3, 2);
     tma(tma_copy_kernel<4096, 8>, 4096, 8, 6);
   }
+  for (int threads : {256, 512, 1024})
+    for (int per_sm : {1, 2, 3}) {
+      if (threads * per_sm > 2048) continue;
+      const int grid = sms * per_sm;
+      const double m4 = time_ms([&] { copy_wide_kernel<4><<<grid, threads>>>(src, dst, n16); }, reps);
+      const double m8 = time_ms([&] { copy_wide_kernel<8><<<grid, threads>>>(src, dst, n16); }, reps);
+      const double m16 = threads <= 512 ? time_ms([&] { copy_wide_kernel<16><<<grid, threads>>>(src, dst, n16); }, reps) : 0.0;
+      printf("{\"kernel\": \"copy_wide\", \"threads\": %d, \"ctas_per_sm\": %d, \"U4_GBps\": %.0f, \"U8_GBps\": %.0f, \"U16_GBps\": %.0f}\n", threads,
+             per_sm, 2.0 * bytes / m4 * 1e-6, 2.0 * bytes / m8 * 1e-6, m16 > 0 ? 2.0 * bytes / m16 * 1e-6 : 0.0);
+    }
   const double fill = (double)bytes / time_ms([&] { fill_kernel<<<sms * 8, 256>>>(dst, n16); }, reps) * 1e-6;
   const double memcpy_gbps =
       2.0 * bytes / time_ms([&] { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, 0)); }, reps) * 1e-6;
