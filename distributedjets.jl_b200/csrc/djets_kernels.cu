@@ -346,7 +346,7 @@ __device__ __forceinline__ void diag_vec_terms(double (&acc)[VU][VecT<T>::N], co
       const T* de = reinterpret_cast<const T*>(&dv[u][j]);
       const T* xe = reinterpret_cast<const T*>(&xv[u][j]);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[j][k] += (double)(de[k] * xe[k]);
+      for (int k = 0; k < VEC; ++k) acc[j][k] += (double)rn_mul(de[k], xe[k]);  // product rounded in T, like the broadcast `diag .* m`
     }
 }
 
@@ -423,7 +423,7 @@ __device__ __forceinline__ bool finish_item_diag_vec(const FinishItem& it, const
   for (int e = nv * VEC + threadIdx.x; e < it.len; e += kThreads) {
     double s = 0.0;
     for (int d = it.diag_begin; d < it.diag_end; ++d)
-      s += (double)(reinterpret_cast<const T*>(diags[d].d)[e] * in[diags[d].vin + e]);
+      s += (double)rn_mul(reinterpret_cast<const T*>(diags[d].d)[e], in[diags[d].vin + e]);
     o[e] = (T)s;
   }
   return true;
@@ -482,7 +482,7 @@ __device__ __forceinline__ void finish_item(const FinishItem& it, const DiagTerm
     for (int q = 0; q < it.nremote; ++q) s += (double)R[it.r0 + q * it.rstride + e];
     for (int d = it.diag_begin; d < it.diag_end; ++d) {
       const T* dd = reinterpret_cast<const T*>(diags[d].d);
-      s += (double)(dd[e] * in[diags[d].vin + e]);
+      s += (double)rn_mul(dd[e], in[diags[d].vin + e]);
     }
     out[it.out + e] = (T)s;
   }

@@ -330,6 +330,28 @@ def test_chained_tiles_match_oracle(dj, O, ctx4, chain, heights):
         ctx4.set_param("chain", 0)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("nb,blen", [(1, 20000), (3, 9001), (5, 12345), (6, 4096)])
+def test_long_diagonal_blocks_all_term_counts(dj, ctx1, dtype, nb, blen):
+    """Grids of long diagonal blocks: every batching shape of the diagonal-term sum (one term; two to three terms;
+    four and more; the vector tails and the scalar tail of a block length that is no multiple of anything), both
+    directions, against NumPy in Float64 with the products rounded in the working type like Julia's broadcast."""
+    rng = np.random.default_rng(31 * nb + blen)
+    diags = [[rng.standard_normal(blen).astype(dtype) for _ in range(nb)] for _ in range(nb)]
+    A = dj.JopDBlock([[dj.JopDiagonal(diags[i][j]) for j in range(nb)] for i in range(nb)], pids=[0], dist=[1, 1], ctx=ctx1)
+    x = rng.standard_normal(nb * blen).astype(dtype)
+    xg = A.domain().zeros()
+    for j in range(nb):
+        xg.setblock(j + 1, x[j * blen:(j + 1) * blen])
+    y = A.mul(A.range().zeros(), xg).to_array()
+    xt = A.mul_adjoint(A.domain().zeros(), xg).to_array()
+    for i in range(nb):
+        want = sum((diags[i][j] * x[j * blen:(j + 1) * blen]).astype(np.float64) for j in range(nb))
+        want_t = sum((diags[j][i] * x[j * blen:(j + 1) * blen]).astype(np.float64) for j in range(nb))
+        np.testing.assert_array_equal(y[i * blen:(i + 1) * blen], want.astype(dtype))
+        np.testing.assert_array_equal(xt[i * blen:(i + 1) * blen], want_t.astype(dtype))
+
+
 def test_perfstatfile_schema(dj, O, ctx4, tmp_path):
     """perfstatfile (src:723-745; schema pinned by test:618-651): one step per apply, one entry per worker
     with id / hostname / operation / localblock (8 and 4 local blocks for a 3x4 operator on grid [2,1])."""
