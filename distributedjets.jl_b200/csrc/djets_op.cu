@@ -287,6 +287,8 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
     const int64_t chunks = ceil_div(std::min<int64_t>(typical_rows, adj_max_rows(op->dtype)), 32 * vec_elems(op->dtype));
     // blocks too small to make a 128 KB tile (100x100 Float64 ...): fewer loads per lane, three CTAs per SM instead of
     // two (4.62 -> 4.99 TB/s on 90,000 blocks of 100x100 F64; no gain once tiles can be widened)
+    // (columns of 5 or 6 warp-loads were tried on the 2 x 8 shape as well: 333x777 Float64 6.79 -> 5.95 TB/s, 600x600
+    // Float32 6.87 -> 6.20 -- the 4 x 4 shape with its paired remainder stays)
     if (chunks <= 2 && ctx->adj_light && max_rows * max_cols * es < 128 * 1024) {
       adj_ru = 1;
       adj_cw = 8;
@@ -329,11 +331,13 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   bool chain_pair = false;
   if (cs == 1 && ctx->chain != 1) {
     int64_t nblk = 0, max_rows = 0, max_cols = 0, max_bytes = 1;
+    std::vector<int64_t> per_out((size_t)(adjoint ? c1 - c0 : r1 - r0), 0);  // dense blocks feeding each output block
     for (int64_t i = r0; i < r1; ++i)
       for (int64_t j = c0; j < c1; ++j) {
         if (op->isdiag && i != j) continue;
         if (op->block(i, j).kind != DJETS_BLOCK_DENSE || op->row_len[i] == 0 || op->col_len[j] == 0) continue;
         ++nblk;
+        ++per_out[(size_t)(adjoint ? j - c0 : i - r0)];
         max_rows = std::max(max_rows, op->row_len[i]);
         max_cols = std::max(max_cols, op->col_len[j]);
         max_bytes = std::max(max_bytes, op->row_len[i] * op->col_len[j] * es);
@@ -344,6 +348,9 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
         chain_k = std::min<int64_t>(ctx->chain, kChainMax);
       else if (ctx->auto_tile && chain_wave > 0)
         chain_k = std::max<int64_t>(1, std::min<int64_t>({(int64_t)kChainMax, (512 * 1024) / max_bytes, nblk / (4 * (int64_t)chain_wave)}));
+      // nothing to chain when every output block has one dense block (block-diagonal operators)
+      const int64_t longest = per_out.empty() ? 0 : *std::max_element(per_out.begin(), per_out.end());
+      chain_k = std::max<int64_t>(1, std::min(chain_k, longest));
       if (chain_k > 1) {
         plan.wave = chain_wave;
         chain_pair = max_rows <= chain_max_rows(op->dtype) / 2;

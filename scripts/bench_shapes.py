@@ -23,7 +23,7 @@ CASES = [  # dtype, m, n, nb (nb x nb blocks)
     ("f64", 1000, 1000, 32), ("f32", 1023, 1025, 45), ("f32", 256, 256, 128), ("f64", 100, 100, 300),
     ("f32", 4096, 512, 20), ("f32", 512, 4096, 20), ("f64", 5000, 64, 40), ("f64", 64, 5000, 40),
     ("f32", 8192, 8192, 4), ("f64", 333, 777, 60), ("c128", 2048, 2048, 12), ("c64", 2048, 2048, 16), ("c128", 300, 257, 60),
-    ("f32", 128, 128, 300), ("f64", 64, 64, 400), ("f64", 100, 100, 120),
+    ("f32", 128, 128, 300), ("f64", 64, 64, 400), ("f64", 100, 100, 120), ("f32", 600, 600, 60),
 ]
 for case, (name, m, n, nb) in enumerate(CASES):
     if only is not None and case not in only:
