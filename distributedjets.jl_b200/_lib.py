@@ -64,6 +64,7 @@ SIGNATURES = {
     "djets_even_cuts": [i64, i32, p_i64],
     "djets_grid_rank": [i32, i32, i32, i32, p_i32, p_i32],
     "djets_plan_tiles": [i32, i64, i64, i32, p_i64, p_i64, p_i64],
+    "djets_plan_chains": [i32, i32, i64, i64, i64, i64, i64, i32, i32, p_i32, p_i32],
     "djets_plan_exchange": [i32, i32, i32, i32, i32, p_i32, i32, p_i32],
     "djets_plan_eval": [C.POINTER(C.c_uint8), i32, i32, i32, p_i32, p_i32],
     "djets_device_count": [p_i32],

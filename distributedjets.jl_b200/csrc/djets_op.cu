@@ -218,6 +218,27 @@ TileShape plan_shape(int dtype, int64_t m, int64_t n, bool adjoint, int64_t fwd_
   return s;
 }
 
+// Blocks per chained tile of a cell (1 = no chains) and whether its adjoint may load two blocks per batch: see
+// build_plan and djets_plan_chains.  Real dtypes only; every dense block at most two warp-loads tall; forward chains
+// also need their columns to fit the staging buffer.
+struct ChainRule {
+  int64_t k = 1;
+  bool pair = false;
+};
+ChainRule chain_rule(int dtype, bool adjoint, int64_t nblocks, int64_t longest, int64_t max_rows, int64_t max_cols,
+                     int64_t max_bytes, int wave, int64_t chain_param, bool auto_tile) {
+  ChainRule r;
+  if (is_complex(dtype) || chain_param == 1 || nblocks <= 0) return r;
+  if (max_rows > chain_max_rows(dtype) || (!adjoint && max_cols > kFwdMaxTC / 2)) return r;
+  if (chain_param > 1)
+    r.k = std::min<int64_t>(chain_param, kChainMax);
+  else if (auto_tile && wave > 0)  // ~512 KB per chain, at least four waves of CTAs left in the cell
+    r.k = std::min<int64_t>({(int64_t)kChainMax, (512 * 1024) / std::max<int64_t>(max_bytes, 1), nblocks / (4 * (int64_t)wave)});
+  r.k = std::max<int64_t>(1, std::min(r.k, longest));  // block-diagonal operators have nothing to chain
+  r.pair = r.k > 1 && max_rows <= chain_max_rows(dtype) / 2;
+  return r;
+}
+
 // Builds one direction of one cell.  `outs` are the block indices along the output dimension that
 // the cell owns (block rows for forward, block columns for adjoint), `ins` along the input one.
 void build_plan(djets_op op, Cell& cell, bool adjoint) {
@@ -342,20 +363,15 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
         max_cols = std::max(max_cols, op->col_len[j]);
         max_bytes = std::max(max_bytes, op->row_len[i] * op->col_len[j] * es);
       }
-    if (nblk > 0 && max_rows <= chain_max_rows(op->dtype) && (adjoint || max_cols <= kFwdMaxTC / 2)) {
-      const int chain_wave = gemv_chain_resident_ctas(op->dtype, adjoint ? 1 : 0, (int)op->p_ld_policy);
-      if (ctx->chain > 1)
-        chain_k = std::min<int64_t>(ctx->chain, kChainMax);
-      else if (ctx->auto_tile && chain_wave > 0)
-        chain_k = std::max<int64_t>(1, std::min<int64_t>({(int64_t)kChainMax, (512 * 1024) / max_bytes, nblk / (4 * (int64_t)chain_wave)}));
-      // nothing to chain when every output block has one dense block (block-diagonal operators)
-      const int64_t longest = per_out.empty() ? 0 : *std::max_element(per_out.begin(), per_out.end());
-      chain_k = std::max<int64_t>(1, std::min(chain_k, longest));
-      if (chain_k > 1) {
-        plan.wave = chain_wave;
-        chain_pair = max_rows <= chain_max_rows(op->dtype) / 2;
-        if (!adjoint) plan.fwd_tx = chain_pair ? 32 : 64;  // one row strip covers the tallest block
-      }
+    const int chain_wave = gemv_chain_resident_ctas(op->dtype, adjoint ? 1 : 0, (int)op->p_ld_policy);
+    const int64_t longest = per_out.empty() ? 0 : *std::max_element(per_out.begin(), per_out.end());
+    const ChainRule rule = chain_rule(op->dtype, adjoint, nblk, longest, max_rows, max_cols, max_bytes, chain_wave,
+                                      ctx->chain, ctx->auto_tile != 0);
+    chain_k = rule.k;
+    chain_pair = rule.pair;
+    if (chain_k > 1) {
+      plan.wave = chain_wave;
+      if (!adjoint) plan.fwd_tx = chain_pair ? 32 : 64;  // one row strip covers the tallest block
     }
   }
   // Wave fit: a tile count between one and two resident waves leaves the second wave part empty and its CTAs finish
@@ -1327,6 +1343,18 @@ int32_t djets_plan_tiles(int32_t dtype, int64_t m, int64_t n, int32_t adjoint, i
     if (tile_rows) *tile_rows = s.tile_rows;
     if (tile_cols) *tile_cols = s.tile_cols;
     if (ntiles) *ntiles = s.ntiles;
+  });
+}
+
+int32_t djets_plan_chains(int32_t dtype, int32_t adjoint, int64_t nblocks, int64_t longest, int64_t max_rows,
+                          int64_t max_cols, int64_t max_bytes, int32_t wave, int32_t chain, int32_t* blocks_per_chain,
+                          int32_t* pair) {
+  return guard([&] {
+    REQUIRE(dtype >= DJETS_F32 && dtype <= DJETS_C128, DJETS_ERR_INVALID, "plan_chains: bad dtype");
+    REQUIRE(chain >= 0 && chain <= kChainMax, DJETS_ERR_INVALID, "plan_chains: chain in 0..16");
+    const ChainRule r = chain_rule(dtype, adjoint != 0, nblocks, longest, max_rows, max_cols, max_bytes, wave, chain, true);
+    if (blocks_per_chain) *blocks_per_chain = (int32_t)r.k;
+    if (pair) *pair = r.pair ? 1 : 0;
   });
 }
 

@@ -106,6 +106,16 @@ int32_t djets_grid_rank(int32_t n1, int32_t n2, int32_t r, int32_t c, const int3
 int32_t djets_plan_tiles(int32_t dtype, int64_t m, int64_t n, int32_t adjoint, int64_t* tile_rows,
                          int64_t* tile_cols, int64_t* ntiles);
 
+/* Chained tiles (small blocks): how many dense blocks of one block row (forward) / block column (adjoint) one CTA
+ * multiplies, by the rule the planner applies to a grid cell (pure function; no device).  `nblocks` dense blocks in the
+ * cell, at most `longest` of them feeding one output block, the largest `max_rows` x `max_cols` and `max_bytes` bytes;
+ * `wave` = resident CTAs of the chain kernel on the device; `chain` = the context parameter (0: sized by the rule, 1: off,
+ * k: forced).  Out: blocks per chain (1 = no chains) and whether the adjoint may load two blocks per batch (every block
+ * at most one warp-load tall). */
+int32_t djets_plan_chains(int32_t dtype, int32_t adjoint, int64_t nblocks, int64_t longest, int64_t max_rows,
+                          int64_t max_cols, int64_t max_bytes, int32_t wave, int32_t chain, int32_t* blocks_per_chain,
+                          int32_t* pair);
+
 /* The point-to-point messages of one apply on an n1 x n2 grid (0-based grid coordinates), six
  * int32 per message: src_r, src_c, dst_r, dst_c, part, slot.  phase 0: input parts from their owner
  * (grid row 0 for mul!, grid column 0 for the adjoint) to the other cells of the grid column / row

@@ -93,6 +93,34 @@ def test_plan_tiles_shapes(dj):
     assert plan(L.F32, 0, 5, 0)[2] == 0
 
 
+def test_chain_rule_for_small_blocks(dj):
+    """Blocks per chained tile (include/djets.h djets_plan_chains): ~512 KB per chain, at least four waves of CTAs
+    left, nothing for block-diagonal operators, complex types, tall blocks or wide forward blocks."""
+    import djets_b200._lib as L
+
+    def rule(dtype, adjoint, nblocks, longest, rows, cols, es, wave=296, chain=0):
+        k, pair = C.c_int32(), C.c_int32()
+        L.call("djets_plan_chains", dtype, adjoint, nblocks, longest, rows, cols, rows * cols * es, wave, chain,
+               C.byref(k), C.byref(pair))
+        return k.value, pair.value
+
+    assert rule(L.F64, 1, 90000, 300, 100, 100, 8) == (6, 0)        # 80 KB blocks: six make ~512 KB; 100 rows = two warp-loads
+    assert rule(L.F64, 1, 160000, 400, 64, 64, 8) == (16, 1)        # 32 KB blocks: the cap; one warp-load tall: pairs
+    assert rule(L.F32, 0, 90000, 300, 128, 128, 4) == (8, 1)
+    assert rule(L.F64, 1, 14400, 120, 100, 100, 8) == (6, 0)        # 14400 / (4 * 296) = 12 waves' worth: bytes rule decides
+    assert rule(L.F64, 1, 2400, 49, 100, 100, 8) == (2, 0)          # small cell: keep four waves of CTAs
+    assert rule(L.F64, 1, 16, 4, 100, 100, 8)[0] == 1               # tiny operator: one block per CTA
+    assert rule(L.F64, 1, 16, 4, 100, 100, 8, chain=4) == (4, 0)    # ... unless forced
+    assert rule(L.F64, 1, 16, 4, 100, 100, 8, chain=16)[0] == 4     # never longer than the blocks there are
+    assert rule(L.F64, 1, 100000, 1, 64, 64, 8)[0] == 1             # block-diagonal: nothing to chain
+    assert rule(L.F64, 1, 90000, 300, 129, 100, 8)[0] == 1          # taller than two warp-loads
+    assert rule(L.F32, 1, 90000, 300, 256, 100, 4)[0] > 1           # Float32 warp-loads are 128 rows
+    assert rule(L.F64, 0, 90000, 300, 100, 600, 8)[0] == 1          # forward: columns must fit the staging buffer
+    assert rule(L.C128, 1, 90000, 300, 64, 64, 16)[0] == 1          # complex blocks are not chained
+    assert rule(L.F64, 1, 90000, 300, 100, 100, 8, chain=1)[0] == 1  # switched off
+    assert rule(L.F64, 1, 90000, 300, 100, 100, 8, wave=0)[0] == 1  # no device: no rule
+
+
 def test_exchange_plan_is_complete(dj):
     """Every cell gets each input part it needs exactly once, every non-owner sends exactly one partial
     to the right owner slot, block-diagonal operators exchange nothing."""
