@@ -376,7 +376,8 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   }
   // Wave fit: a tile count between one and two resident waves leaves the second wave part empty and its CTAs finish
   // one by one (profiles/r02_trace_boundary_8blocks.txt).  If slightly larger tiles bring the whole cell into ONE wave,
-  // take them (0.5 GiB shard of the bench operator: 1024 -> 512 forward tiles, 512 -> 296 adjoint tiles, -1 % per step).
+  // take them -- only when the second wave would be less than 60 % full; the N=8 shard of the bench operator sits at 1.73
+  // waves (profiles/r02_gemv_shard8_ncu_summary.txt) and keeps its tiles.
   if (ctx->auto_tile && ctx->wave_fit && plan.wave > 0 && chain_k == 1) {
     auto count_tiles = [&](int64_t ftc, int64_t atc) {
       int64_t nt = 0;
