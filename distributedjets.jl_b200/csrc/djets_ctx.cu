@@ -61,6 +61,7 @@ cudaError_t device_alloc(djets_ctx ctx, void** p, size_t bytes) {
 }
 
 void control_allgather(djets_ctx ctx, const void* send, void* recv, size_t bytes) {
+  REQUIRE(bytes > 0 && bytes <= (size_t)1 << 24, DJETS_ERR_INVALID, "control all-gather: record size out of range");
   RankCtx& rc = ctx->ranks.front();
   if (ctx->host_allgather) {
     // the callback orders records by process; a process stands for its first local rank
