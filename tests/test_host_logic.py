@@ -94,7 +94,7 @@ def test_plan_tiles_shapes(dj):
 
 
 def test_chain_rule_for_small_blocks(dj):
-    """Blocks per chained tile (include/djets.h djets_plan_chains): ~512 KB per chain, at least four waves of CTAs
+    """Blocks per chained tile (include/djets.h djets_plan_chains): ~1 MB per chain, at least eight waves of CTAs
     left, nothing for block-diagonal operators, complex types, tall blocks or wide forward blocks."""
     import djets_b200._lib as L
 
@@ -104,11 +104,11 @@ def test_chain_rule_for_small_blocks(dj):
                C.byref(k), C.byref(pair))
         return k.value, pair.value
 
-    assert rule(L.F64, 1, 90000, 300, 100, 100, 8) == (6, 0)        # 80 KB blocks: six make ~512 KB; 100 rows = two warp-loads
+    assert rule(L.F64, 1, 90000, 300, 100, 100, 8) == (13, 0)       # 80 KB blocks: thirteen make ~1 MB; 100 rows = two warp-loads
     assert rule(L.F64, 1, 160000, 400, 64, 64, 8) == (16, 1)        # 32 KB blocks: the cap; one warp-load tall: pairs
-    assert rule(L.F32, 0, 90000, 300, 128, 128, 4) == (8, 1)
-    assert rule(L.F64, 1, 14400, 120, 100, 100, 8) == (6, 0)        # 14400 / (4 * 296) = 12 waves' worth: bytes rule decides
-    assert rule(L.F64, 1, 2400, 49, 100, 100, 8) == (2, 0)          # small cell: keep four waves of CTAs
+    assert rule(L.F32, 0, 90000, 300, 128, 128, 4) == (16, 1)
+    assert rule(L.F64, 1, 14400, 120, 100, 100, 8) == (6, 0)        # 14400 / (8 * 296) = 6: the eight-waves rule decides
+    assert rule(L.F64, 1, 4800, 49, 100, 100, 8) == (2, 0)          # small cell: keep eight waves of CTAs
     assert rule(L.F64, 1, 16, 4, 100, 100, 8)[0] == 1               # tiny operator: one block per CTA
     assert rule(L.F64, 1, 16, 4, 100, 100, 8, chain=4) == (4, 0)    # ... unless forced
     assert rule(L.F64, 1, 16, 4, 100, 100, 8, chain=16)[0] == 4     # never longer than the blocks there are
