@@ -221,11 +221,6 @@ TileShape plan_shape(int dtype, int64_t m, int64_t n, bool adjoint, int64_t fwd_
 // Blocks per chained tile of a cell (1 = no chains) and whether its adjoint may load two blocks per batch: see
 // build_plan and djets_plan_chains.  Real dtypes only; every dense block at most two warp-loads tall; forward chains
 // also need their columns to fit the staging buffer.
-static int64_t chain_target_kb() {  // bytes a chain aims for (DJETS_CHAIN_KB overrides).  90,000 blocks of 100x100 Float64,
-  // forward / adjoint TB/s: 256 KB 6.75 / 6.12, 512 KB 7.23 / 6.70, 1 MB 7.28 / 6.82, 2 MB (= 16 blocks) 7.29 / 6.85
-  static const int64_t v = getenv("DJETS_CHAIN_KB") ? atoll(getenv("DJETS_CHAIN_KB")) : 1024;
-  return v < 1 ? 1 : v;
-}
 struct ChainRule {
   int64_t k = 1;
   bool pair = false;
@@ -237,8 +232,17 @@ ChainRule chain_rule(int dtype, bool adjoint, int64_t nblocks, int64_t longest, 
   if (max_rows > chain_max_rows(dtype) || (!adjoint && max_cols > kFwdMaxTC / 2)) return r;
   if (chain_param > 1)
     r.k = std::min<int64_t>(chain_param, kChainMax);
-  else if (auto_tile && wave > 0)  // ~1 MB per chain, at least eight waves of CTAs left in the cell (a short last wave costs a whole chain's time)
-    r.k = std::min<int64_t>({(int64_t)kChainMax, (chain_target_kb() * 1024) / std::max<int64_t>(max_bytes, 1), nblocks / (8 * (int64_t)wave)});
+  else if (auto_tile && wave > 0) {
+    // ~1 MB per chain where that still leaves sixteen waves of CTAs (90,000 blocks of 100x100 Float64, forward / adjoint
+    // TB/s: 256 KB 6.75 / 6.12, 512 KB 7.23 / 6.70, 1 MB 7.28 / 6.82), otherwise ~512 KB and at least four waves (14,400
+    // blocks: 6.90 / 6.42 against 6.72 / 6.42 with longer chains and eight waves): a short last wave costs a whole chain.
+    const int64_t bytes = std::max<int64_t>(max_bytes, 1);
+    const int64_t big = (1024 * 1024) / bytes;
+    if (nblocks / (16 * (int64_t)wave) >= big)
+      r.k = std::min<int64_t>(kChainMax, big);
+    else
+      r.k = std::min<int64_t>({(int64_t)kChainMax, (512 * 1024) / bytes, nblocks / (4 * (int64_t)wave)});
+  }
   r.k = std::max<int64_t>(1, std::min(r.k, longest));  // block-diagonal operators have nothing to chain
   r.pair = r.k > 1 && max_rows <= chain_max_rows(dtype) / 2;
   return r;
@@ -350,7 +354,7 @@ void build_plan(djets_op op, Cell& cell, bool adjoint) {
   plan.wave = gemv_resident_ctas(op->dtype, adjoint ? 1 : 0, adjoint ? adj_ru : (int)fwd_tx, adj_cw, (int)op->p_ld_policy);
   // Chained tiles: when every dense block of the cell is at most two warp-loads tall (128 Float64 / 256 Float32 rows)
   // a CTA multiplies up to chain_k blocks of one block column (adjoint) / block row (forward) and writes one partial --
-  // enough blocks to make a tile of ~1 MB, but never so many that the cell is left with fewer than eight waves of
+  // enough blocks to make a tile of 0.5-1 MB, but never so many that the cell is left with fewer than four waves of
   // CTAs ("chain": 0 = this rule, 1 = off, k > 1 = k blocks whatever the operator's size).  90,000 blocks of 100x100
   // Float64: adjoint 5.0 -> 6.7 TB/s (profiles/r02_block_shapes_1gpu.jsonl).
   int64_t chain_k = 1;

@@ -94,7 +94,7 @@ def test_plan_tiles_shapes(dj):
 
 
 def test_chain_rule_for_small_blocks(dj):
-    """Blocks per chained tile (include/djets.h djets_plan_chains): ~1 MB per chain, at least eight waves of CTAs
+    """Blocks per chained tile (include/djets.h djets_plan_chains): 0.5-1 MB per chain, at least four waves of CTAs
     left, nothing for block-diagonal operators, complex types, tall blocks or wide forward blocks."""
     import djets_b200._lib as L
 
@@ -107,8 +107,9 @@ def test_chain_rule_for_small_blocks(dj):
     assert rule(L.F64, 1, 90000, 300, 100, 100, 8) == (13, 0)       # 80 KB blocks: thirteen make ~1 MB; 100 rows = two warp-loads
     assert rule(L.F64, 1, 160000, 400, 64, 64, 8) == (16, 1)        # 32 KB blocks: the cap; one warp-load tall: pairs
     assert rule(L.F32, 0, 90000, 300, 128, 128, 4) == (16, 1)
-    assert rule(L.F64, 1, 14400, 120, 100, 100, 8) == (6, 0)        # 14400 / (8 * 296) = 6: the eight-waves rule decides
-    assert rule(L.F64, 1, 4800, 49, 100, 100, 8) == (2, 0)          # small cell: keep eight waves of CTAs
+    assert rule(L.F32, 1, 16384, 128, 256, 256, 4) == (2, 0)        # 256 KB blocks, 16384 of them: pairs
+    assert rule(L.F64, 1, 14400, 120, 100, 100, 8) == (6, 0)        # too few blocks for 1 MB chains: six make ~512 KB
+    assert rule(L.F64, 1, 2400, 49, 100, 100, 8) == (2, 0)          # small cell: keep four waves of CTAs
     assert rule(L.F64, 1, 16, 4, 100, 100, 8)[0] == 1               # tiny operator: one block per CTA
     assert rule(L.F64, 1, 16, 4, 100, 100, 8, chain=4) == (4, 0)    # ... unless forced
     assert rule(L.F64, 1, 16, 4, 100, 100, 8, chain=16)[0] == 4     # never longer than the blocks there are
