@@ -459,18 +459,18 @@ end
 
 function JetDBlock_df!(d::DBArray, m::DBArray; op, perfstatfile="", kwargs...)                                      # src:663-674
     @dj djets_op_mul (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}) op.h d.h m.h
-    perfstat(op, "df", perfstatfile)
+    write_perfstat(op, "df", perfstatfile)
     d
 end
 function JetDBlock_df′!(m::DBArray, d::DBArray; op, perfstatfile="", kwargs...)                                     # src:710-721
     @dj djets_op_mul_adjoint (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}) op.h m.h d.h
-    perfstat(op, "df′", perfstatfile)
+    write_perfstat(op, "df′", perfstatfile)
     m
 end
 
 # perfstatfile (src:723-745): one step per apply, one entry per worker; "localblock" holds the worker's
 # elapsed milliseconds, one value per local block (the JSON layout the reference's test:618-651 pins)
-function perfstat(op, operation, perfstatfile)
+function write_perfstat(op, operation, perfstatfile)   # not `perfstat`: Jets exports that name (the reference extends Jets.perfstat, src:730)
     perfstatfile == "" && return nothing
     entries = Dict{String,Any}[]
     for c in 1:size(op.pids, 2), r in 1:size(op.pids, 1)

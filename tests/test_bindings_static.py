@@ -135,3 +135,65 @@ def test_python_ctypes_signatures_match_the_header():
         assert len(argtypes) == len(want), name
         for k, (a, w) in enumerate(zip(argtypes, want)):
             assert a is w or a == w, f"{name} argument {k + 1}: {a} vs {w}"
+
+
+def test_every_dj_call_passes_as_many_arguments_as_it_declares():
+    """`@dj f (T1, T2, ...) a1 a2 ...` expands to `ccall(f, Int32, (T1, T2, ...), a1, a2, ...)`: a call whose argument
+    list is shorter or longer than its type tuple would only fail when Julia first runs it.  Arguments are the
+    space-separated expressions up to the end of the statement (newline, `;` or the bracket that encloses the macro
+    call); an argument with a top-level space (`a + b`) would be miscounted here and is also ambiguous to Julia's
+    macro-call parser, so none is allowed."""
+    from test_julia_recipes import _strip_julia_literals
+    src = _strip_julia_literals(open(SHIM).read())
+    calls = 0
+    for m in re.finditer(r"@dj\s+(djets_[a-z0-9_]+)\s+\(", src):
+        i = j = m.end() - 1
+        depth = 0
+        while True:                                        # the type tuple
+            if src[j] in "({[":
+                depth += 1
+            elif src[j] in ")}]":
+                depth -= 1
+                if depth == 0:
+                    break
+            j += 1
+        types = split_top_level(src[i + 1:j])
+        args, cur, depth, k = [], "", 0, j + 1
+        while k < len(src):
+            c = src[k]
+            if c in "({[":
+                depth += 1
+            elif c in ")}]":
+                if depth == 0:
+                    break
+                depth -= 1
+            if depth == 0 and c in "\n;":
+                break
+            if depth == 0 and c in " \t":
+                if cur:
+                    args.append(cur)
+                cur = ""
+            else:
+                cur += c
+            k += 1
+        if cur:
+            args.append(cur)
+        calls += 1
+        assert len(args) == len(types), f"@dj {m.group(1)}: {len(types)} argument types, {len(args)} arguments {args}"
+    assert calls >= 40
+
+
+def test_shim_defines_no_function_under_a_name_jets_owns():
+    """Inside `module DistributedJetsB200` every name Jets exports is in scope through `using Jets`; a method meant to
+    EXTEND one must be written `Jets.name(...)`, and a helper of the shim must not reuse such a name unqualified (it
+    would shadow, or fail to define once the imported binding was used).  The names are the ones the reference itself
+    extends with a `Jets.` prefix (src:161-164, 383-412, 414-415, 730, 805-827) plus the accessors its tests call."""
+    from test_julia_recipes import _strip_julia_literals
+    src = _strip_julia_literals(open(SHIM).read())
+    jets_owned = {"getblock", "getblock!", "setblock!", "indices", "isblockop", "nblocks", "perfstat", "point!", "space",
+                  "state", "state!", "jet", "domain", "shape", "jacobian", "jacobian!", "JopBlock", "JetBlock", "close"}
+    defined = set(re.findall(r"^\s*(?:function\s+)?([A-Za-z_][\w!′]*)\s*(?:\{[^}\n]*\})?\(", src, flags=re.M))
+    clashes = defined & jets_owned
+    assert not clashes, f"unqualified definitions of names Jets owns: {sorted(clashes)}"
+    for name in ("getblock", "getblock!", "setblock!", "indices", "nblocks", "space", "isblockop", "JopBlock"):
+        assert re.search(rf"\bJets\.{re.escape(name)}\(", src), f"the shim should extend Jets.{name}"

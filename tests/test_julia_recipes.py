@@ -85,3 +85,83 @@ def test_bench_prefers_julia_when_present():
     assert '"kind": kind' in src and 'kind = "julia"' in src.replace("cores, kind = float", "x = float") or "\"julia\"" in src
     if shutil.which("julia") is None:
         pytest.skip("no julia on PATH: the reference arm falls back to the NumPy/OpenBLAS restatement")
+
+
+# ---- block structure of the Julia files (they cannot be parsed by Julia here) ---------------------------------------
+_OPENERS = {"type", "function", "if", "for", "while", "let", "begin", "do", "struct", "module", "try", "quote", "macro",
+            "baremodule"}
+
+
+def _strip_julia_literals(s: str) -> str:
+    """Drops comments (`#`, `#= =#`) and replaces string / character literals by empty ones."""
+    out, i, n = [], 0, len(s)
+    while i < n:
+        c = s[i]
+        if s.startswith("#=", i):
+            j = s.find("=#", i + 2)
+            i = n if j < 0 else j + 2
+        elif c == "#":
+            j = s.find("\n", i)
+            i = n if j < 0 else j
+        elif s.startswith('"""', i):
+            j = s.find('"""', i + 3)
+            i = n if j < 0 else j + 3
+            out.append('""')
+        elif c == '"':
+            j = i + 1
+            while j < n and s[j] != '"':
+                j += 2 if s[j] == "\\" else 1
+            i = j + 1
+            out.append('""')
+        elif c == "'" and i + 2 < n and (s[i + 2] == "'" or (s[i + 1] == "\\" and i + 3 < n and s[i + 3] == "'")):
+            i += 3 if s[i + 2] == "'" else 4
+            out.append("' '")
+        else:
+            out.append(c)
+            i += 1
+    return "".join(out)
+
+
+def julia_blocks_balanced(path: str):
+    """(ok, message): every block opener outside brackets has its `end`, every bracket closes.  `for` / `if` inside
+    brackets are comprehensions / generators, `end` inside brackets is the last index."""
+    stack, line = [], 1
+    for m in re.finditer(r"\n|[\[\]\(\)\{\}]|(?<![\w:.!])(?:[A-Za-z_]\w*)", _strip_julia_literals(open(path).read())):
+        tok = m.group(0)
+        if tok == "\n":
+            line += 1
+        elif tok in "[({":
+            stack.append((tok, line))
+        elif tok in "])}":
+            if not stack or stack[-1][0] not in "[({":
+                return False, f"unbalanced bracket at line {line}"
+            stack.pop()
+        else:
+            in_brackets = bool(stack) and stack[-1][0] in "[({"
+            if tok in _OPENERS and not (in_brackets and tok in ("for", "if")):
+                stack.append((tok, line))
+            elif tok == "end" and not in_brackets:
+                if not stack:
+                    return False, f"`end` without an opener at line {line}"
+                stack.pop()
+    return (not stack), (f"unclosed {stack[-3:]}" if stack else "balanced")
+
+
+JULIA_FILES = RECIPES + [os.path.join(ROOT, "distributedjets.jl_b200", "julia", "DistributedJetsB200.jl")]
+
+
+@pytest.mark.parametrize("path", JULIA_FILES, ids=[os.path.basename(p) for p in JULIA_FILES])
+def test_julia_files_have_balanced_blocks(path):
+    ok, msg = julia_blocks_balanced(path)
+    assert ok, f"{os.path.basename(path)}: {msg}"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only present in the build container")
+def test_block_checker_accepts_the_references_own_files(tmp_path):
+    """The checker is a heuristic: it must accept Julia that is known to parse, and notice a missing `end`."""
+    for rel in ("src/DistributedJets.jl", "test/runtests.jl", "benchmark/benchmarks.jl"):
+        ok, msg = julia_blocks_balanced(os.path.join(REF, rel))
+        assert ok, f"{rel}: {msg}"
+    broken = tmp_path / "broken.jl"
+    broken.write_text("function f(x)\n    if x > 0\n        x[end]\n    return [y for y in x if y > 0]\nend\n")
+    assert not julia_blocks_balanced(str(broken))[0]
